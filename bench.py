@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- Mpaths/s of the per-pixel / per-sample path-tracing loop on BASELINE.json's config 2
+(cover scene, 1920x1080, 1024 spp, max depth 50), 1..8 B200, next to the reference CPU renderer.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]             # our arm (torchrun launches one rank per GPU)
+    python bench.py --impl reference [--gpus N] [--steps K] ...     # the reference's own CPU implementation
+
+A step = one full render of the workload: zero the accumulation buffer, trace every (pixel, sample) path of this
+rank's sample shard, combine the shards with one NCCL reduce (N > 1), convert to the float accumulation buffer on
+GPU 0.  `value` = paths of the whole job / device time (inputs resident in HBM); `e2e` = the same through the host-buffer
+C-ABI call with host<->device copies inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (width, aspect, spp, max_child_rays, nsqrt, moving)
+    "cover_1080p_1024spp_depth50": (1920, 1.7777777777777777, 1024, 50, 11, True),   # BASELINE.json configs[1]
+    "cover_default_200x133_20spp_depth20": (200, 1.5, 20, 20, 11, True),            # configs[0]
+    "cover_4k_4096spp_depth50": (3840, 1.7777777777777777, 4096, 50, 11, True),     # configs[4]
+}
+# canonical FP32 flop costs of SURVEY.md 8(d) (FMA = 2)
+FLOP_STATIC_TEST, FLOP_MOVING_TEST, FLOP_HIT, FLOP_SHADE = 17.0, 23.0, 40.0, 80.0
+NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(width: int, aspect: float, spp_per_thread: int, depth: int, threads: int) -> dict:
+    """Times the reference's own CPU implementation (oracle/_ref/rtweekend_ref = its sources compiled unmodified) on a
+    bounded sample of the workload; falls back to the plain-C port of the oracle when the prebuilt reference is absent."""
+    import oracle
+    height = int(width / aspect)
+    if oracle.ref_available():
+        spp = spp_per_thread * threads
+        t0 = time.perf_counter()
+        with open(os.devnull, "wb") as null:
+            p = subprocess.run([str(oracle.REF_EXE), "-w", str(width), "-a", repr(aspect), "-s", str(spp), "-c", str(depth), "-t", str(threads)],
+                               stdout=null, stderr=subprocess.PIPE)
+        wall = time.perf_counter() - t0
+        m = re.findall(rb"Done in (\d+)ms", p.stderr)
+        if p.returncode != 0 or not m:
+            raise RuntimeError("reference executable failed: " + p.stderr[-300:].decode(errors="replace"))
+        secs = int(m[-1]) / 1e3  # the reference's own timer (render.cpp:188-190): BVH build + render + PPM write
+        paths = width * height * spp
+        return {"value": paths / secs / 1e6, "unit": "Mpaths/s", "cores": threads, "kind": "reference", "seconds": secs, "wall_seconds": wall,
+                "sample": f"cover scene {width}x{height}, {spp} spp ({spp_per_thread}/thread x {threads} threads), depth {depth}; "
+                          f"time = the reference's own 'Done in' timer (includes BVH build and P3 write)"}
+    port = oracle.port()
+    sc = port.scene_cover(11, aspect, True)
+    t0 = time.perf_counter()
+    _, _, rays = port.render_philox(sc, width, height, 0, spp_per_thread, depth, seed=1, nthreads=threads)
+    secs = time.perf_counter() - t0
+    paths = width * height * spp_per_thread
+    return {"value": paths / secs / 1e6, "unit": "Mpaths/s", "cores": threads, "kind": "port", "seconds": secs,
+            "sample": f"cover scene {width}x{height}, {spp_per_thread} spp, depth {depth}, oracle port (brute-force closest hit), rows split over {threads} threads"}
+
+
+def run_reference_arm(args, wl_name, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    width, aspect, spp, depth, _, _ = wl
+    threads = min(os.cpu_count() or 1, 64)  # all threads share ONE unsynchronised mt19937: more only adds contention
+    # bounded sample: quarter-resolution frame, 1 sample per thread (cost is linear in pixels x spp)
+    bw = max(width // 2, 200)
+    vals, secs = [], []
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_run(bw, aspect, 1, depth, threads)
+        if i >= args.warmup:
+            vals.append(r["value"]); secs.append(r["seconds"])
+    value = sum(v * s for v, s in zip(vals, secs)) / sum(secs)
+    line = {"impl": "reference", "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": {"workload": wl_name, "bounded_sample": r["sample"]},
+            "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+            "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cover_1080p_1024spp_depth50", choices=sorted(WORKLOADS))
+    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (a reduced-size run is NOT the headline)")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "spheres", "bvh"])
+    ap.add_argument("--rays-per-lane", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--traffic-bytes", type=float, default=None, help="dram bytes per launch of the render kernel from an ncu --set full capture")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference_arm(args, args.workload, wl)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    rtw = importlib.import_module("raytracing-one-weekend_b200")
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this renderer has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world and rank == 0:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; reporting n_gpus={world}", file=sys.stderr)
+
+    width, aspect, spp, depth, nsqrt, moving = wl
+    if args.spp:
+        spp = args.spp
+    height = rtw.image_height(width, aspect)
+    kernel = {"auto": rtw.KERNEL_AUTO, "spheres": rtw.KERNEL_SPHERES_SMEM, "bvh": rtw.KERNEL_BVH}[args.kernel]
+    scene = rtw.cover_scene(nsqrt, aspect, moving)
+    s_begin, s_end = rtw.sample_shard(spp, rank, world)
+    ds = rtw.DeviceScene(scene, local_rank)
+    npix = width * height
+    accum = torch.zeros((height, width, 4), dtype=torch.int64, device=dev)
+    out_f32 = torch.zeros((height, width, 4), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def step(collect_stats=False):
+        accum.zero_()
+        st = ds.render_into(accum, width, height, s_end - s_begin, depth, sample_begin=s_begin, stream_ptr=stream.cuda_stream, seed=0,
+                            kernel=kernel, rays_per_lane=args.rays_per_lane, want_stats=collect_stats)
+        rtw.reduce_accum(accum, dst=0)
+        if rank == 0:
+            ds.accum_to_float(accum, out_f32, npix, stream_ptr=stream.cuda_stream)
+        return st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    # one untimed instrumented pass: exact ray count of this shard (deterministic for a given seed) and the kernel's own time
+    st = step(collect_stats=True)
+    rays_local = st["rays"]
+    kernel_used = st["kernel_used"]
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, k, b in ev:
+        flush.fill_(1.0)  # evict L2 between timed iterations (outside the timed events)
+        a.record(stream)
+        accum.zero_()
+        ds.render_into(accum, width, height, s_end - s_begin, depth, sample_begin=s_begin, stream_ptr=stream.cuda_stream, seed=0, kernel=kernel,
+                       rays_per_lane=args.rays_per_lane)
+        k.record(stream)   # end of the render kernel (for the roofline)
+        rtw.reduce_accum(accum, dst=0)
+        if rank == 0:
+            ds.accum_to_float(accum, out_f32, npix, stream_ptr=stream.cuda_stream)
+        b.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(a.elapsed_time(b) for a, _, b in ev)
+    kernel_ms = sum(a.elapsed_time(k) for a, k, _ in ev) / args.steps  # zero_ (~10 us) + k_render
+    t = torch.tensor([total_ms, kernel_ms, float(rays_local)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        total_ms, kernel_ms, rays_total = tmax[0].item(), tmax[1].item(), tsum[2].item()
+    else:
+        rays_total = float(rays_local)
+    paths_total = float(npix) * spp
+    ms_per_step = total_ms / args.steps
+    value = paths_total / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the host-buffer C-ABI call -----------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h2d = scene.prims.nbytes + scene.mats.nbytes + 168
+        d2h = npix * 16
+        e_steps = max(1, min(args.steps, 2))
+        pinned = torch.empty((height, width, 4), dtype=torch.float32).pin_memory()
+        def e2e_step():
+            if world == 1:
+                cfg = rtw.make_cfg(width, height, spp, depth, kernel=kernel, seed=0, device=local_rank, rays_per_lane=args.rays_per_lane)
+                d = scene.desc()
+                import ctypes as C
+                stt = rtw.Stats()
+                rc = rtw.lib().rtw_render(C.byref(d), C.byref(cfg), C.c_void_p(pinned.data_ptr()), C.byref(stt))
+                if rc != 0:
+                    raise RuntimeError(rtw.lib().rtw_last_error().decode())
+            else:
+                ds2 = rtw.DeviceScene(scene, local_rank)  # host arrays -> HBM
+                accum.zero_()
+                ds2.render_into(accum, width, height, s_end - s_begin, depth, sample_begin=s_begin, stream_ptr=stream.cuda_stream, seed=0,
+                                kernel=kernel, rays_per_lane=args.rays_per_lane)
+                rtw.reduce_accum(accum, dst=0)
+                if rank == 0:
+                    ds2.accum_to_float(accum, out_f32, npix, stream_ptr=stream.cuda_stream)
+                    pinned.copy_(out_f32, non_blocking=False)
+                torch.cuda.synchronize()
+                ds2.close()
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step()
+        barrier()
+        e_ms = (time.perf_counter() - t0) * 1e3 / e_steps
+        te = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": paths_total / (te.item() * 1e-3) / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": te.item(), "steps": e_steps,
+               "api": "rtw_render (host buffers)" if world == 1 else "rtw_scene_upload + rtw_render_device + NCCL reduce + D2H to pinned memory"}
+        if rank == 0 and world == 1:
+            ref_img = out_f32.cpu()
+            assert torch.equal(ref_img, pinned), "host-buffer render and device-resident render disagree"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (k_render) ---------------------------------------------------------------
+    kinds = scene.prims["kind"]
+    radius = np.abs(scene.prims["radius"])
+    n_moving = int(((kinds == rtw.RTW_MOVING_SPHERE) & (radius < 100)).sum())
+    n_static = int(((kinds == rtw.RTW_SPHERE) & (radius < 100)).sum())
+    n_big = int((radius >= 100).sum())
+    rays_gpu = rays_total / world  # per launch (per GPU)
+    paths_gpu = paths_total / world
+    roofline = None
+    if kernel_used == rtw.KERNEL_SPHERES_SMEM:
+        flop = rays_gpu * ((n_static + n_big) * FLOP_STATIC_TEST + n_moving * FLOP_MOVING_TEST + FLOP_SHADE) + (rays_gpu - paths_gpu) * FLOP_HIT
+        peak_tflops, implied_mhz = rtw.fp32_peak(local_rank, 1.0)
+        achieved = flop / (kernel_ms * 1e-3) / 1e12
+        roofline = {"bound": "fp32_fma", "kernel": "k_render<R,0> (K1 sphere sweep)", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+                    "frac": achieved / peak_tflops, "traffic": args.traffic_bytes,
+                    "peak_source": "FFMA micro-benchmark (rtw_fp32_peak) measured in this run; MEASURED_PEAKS.json has no FP32 figure; nominal %.1f" % NOMINAL_FP32_TFLOPS,
+                    "algorithmic_flop_per_launch": flop, "kernel_ms": kernel_ms,
+                    "flop_model": f"rays x ({n_static}+{n_big} static x 17 + {n_moving} moving x 23 + 80) + hits x 40 (SURVEY 8(d))",
+                    "note": "no tensor cores and ~no HBM traffic on this path: the bounding unit is the FP32 FMA pipe (SURVEY 8(d))"}
+    else:
+        roofline = {"bound": "latency", "kernel": "k_render<1,1> (K2 BVH)", "achieved": None, "peak": None, "unit": "GB/s", "frac": None,
+                    "traffic": args.traffic_bytes, "kernel_ms": kernel_ms}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = min(os.cpu_count() or 1, 64)
+        cpu_baseline = cpu_reference_run(max(width // 2, 200), aspect, 1, depth, threads)
+
+    line = {
+        "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "width": width, "height": height, "spp": spp, "max_child_rays": depth, "primitives": int(len(scene.prims)),
+                   "parallelism": f"spp-shard x{world}, one int64 NCCL reduce", "kernel": "spheres_smem" if kernel_used == rtw.KERNEL_SPHERES_SMEM else "bvh",
+                   "l2": "256 MB buffer written between timed iterations (scene tables live in shared memory; accumulation buffer 66 MB)"},
+        "mrays_per_s": rays_total / (ms_per_step * 1e-3) / 1e6, "rays_per_path": rays_total / paths_total,
+        "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

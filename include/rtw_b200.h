@@ -1,0 +1,155 @@
+/* rtw_b200.h -- C ABI of the B200-native path tracer (librtw_b200.so).
+ *
+ * This is the device boundary that the host-side `rtweekend::render(const Scene&, const Config&)`
+ * (reference: src/render.h:35,42; body src/render.cpp:135-191) crosses.  Everything below the boundary is
+ * hand-written sm_100a CUDA; there is no CPU fallback: every entry point fails with a non-zero status and a
+ * message in rtw_last_error() when no CUDA device / kernel image is available.
+ *
+ * Plain C types only (pointers + sizes + PODs); caller owns every host buffer; the library owns device memory.
+ * All calls are blocking unless stated otherwise and are not re-entrant per device.
+ *
+ * Reference interface replaced by each entry point:
+ *   rtw_render / rtw_render_multi_gpu  do_work lambda + thread fan-out + sum   render.cpp:150-180
+ *                                      (ray_color :112-129, BVHNode::hit :52-71, Camera::get_ray
+ *                                      common-model.cpp:156-167, *::hit :64-125, *::scatter :13-62,
+ *                                      random-utils.cpp:6-41)
+ *   rtw_scene_upload                   Scene::get_root_bvh / BVHNode ctor       render.cpp:73-110,131-133
+ *   rtw_primary_hits                   BVHNode::hit on camera rays (parity mode; no reference entry point)
+ *   rtw_finalize_rgb8                  write_color                             render.cpp:11-20
+ */
+#ifndef RTW_B200_H
+#define RTW_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTW_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define RTW_API __attribute__((visibility("default")))
+#else
+#define RTW_API
+#endif
+
+enum rtw_prim_kind { RTW_SPHERE = 0, RTW_MOVING_SPHERE = 1, RTW_TRIANGLE = 2 };
+enum rtw_mat_kind { RTW_LAMBERTIAN = 0, RTW_METAL = 1, RTW_DIELECTRIC = 2 };
+enum rtw_kernel { RTW_KERNEL_AUTO = 0, RTW_KERNEL_SPHERES_SMEM = 1, RTW_KERNEL_BVH = 2 };
+enum rtw_flags { RTW_FLAG_STATS = 1 };
+
+/* One primitive, in scene insertion order (index in the array == primitive id used for parity).
+ * Mirrors the constructor arguments of Sphere / MovingSphere / Triangle (oo-primitives.h:28,49,76). */
+typedef struct rtw_primitive {
+  int32_t kind;     /* rtw_prim_kind */
+  int32_t material; /* index into rtw_scene_desc.mats */
+  double a[3];      /* sphere: centre (at time 0); triangle: vertex a */
+  double b[3];      /* moving sphere: centre at time 1; triangle: vertex b */
+  double c[3];      /* triangle: vertex c */
+  double radius;    /* spheres; may be negative (hollow sphere trick) */
+} rtw_primitive;
+
+/* Mirrors Lambertian{albedo}, Metal{albedo,fuzz}, Dielectric{ior,fuzz} (common-model.h:123-150). */
+typedef struct rtw_material {
+  int32_t kind; /* rtw_mat_kind */
+  int32_t reserved;
+  double albedo[3];
+  double fuzz; /* clamped to [0,1] by the library, like the reference constructors */
+  double ior;
+} rtw_material;
+
+/* The derived camera block computed by Camera's constructor (common-model.cpp:136-154). */
+typedef struct rtw_camera {
+  double origin[3], lower_left[3], horizontal[3], vertical[3], u[3], v[3];
+  double lens_radius, t0, t1;
+} rtw_camera;
+
+typedef struct rtw_scene_desc {
+  const rtw_primitive* prims;
+  int64_t nprims;
+  const rtw_material* mats;
+  int64_t nmats;
+  rtw_camera camera;
+} rtw_scene_desc;
+
+typedef struct rtw_render_cfg {
+  int32_t width, height;          /* height = int(width / aspect_ratio), render.cpp:137 */
+  int32_t sample_begin, sample_end; /* global sample indices [begin,end) rendered by this call (spp shard) */
+  int32_t max_child_rays;         /* Config::max_child_rays: up to this many scatters per path */
+  int32_t kernel;                 /* rtw_kernel */
+  uint64_t seed;                  /* Philox key */
+  int32_t device;                 /* CUDA device ordinal */
+  int32_t flags;                  /* rtw_flags */
+  int32_t rays_per_lane;          /* 0 = default; sphere kernel variant (1, 2 or 4 paths in flight per lane) */
+  int32_t reserved;
+} rtw_render_cfg;
+
+typedef struct rtw_stats {
+  uint64_t paths, rays;                       /* always filled by the blocking entry points */
+  uint64_t sphere_tests, sphere_candidates;   /* RTW_FLAG_STATS only */
+  uint64_t tri_tests, node_visits;            /* RTW_FLAG_STATS only */
+  double kernel_ms;                           /* CUDA-event time of the render kernel(s) */
+  double h2d_ms, d2h_ms, total_ms;            /* host-buffer entry points */
+  int32_t kernel_used;                        /* rtw_kernel actually launched */
+  int32_t launches;                           /* kernels of this library launched by the call */
+} rtw_stats;
+
+typedef struct rtw_scene rtw_scene; /* device-resident flattened scene (SoA tables, BVH, materials, camera) */
+
+RTW_API int rtw_abi_version(void);
+RTW_API const char* rtw_last_error(void);
+RTW_API int rtw_device_count(int* count);
+
+/* Flatten + upload (sphere tables, SAH BVH for meshes/mixed scenes, materials, camera) to `device`. */
+RTW_API int rtw_scene_upload(const rtw_scene_desc* desc, int32_t device, rtw_scene** out);
+RTW_API void rtw_scene_free(rtw_scene* scene);
+
+/* One-shot render with HOST buffers: upload, render samples [sample_begin,sample_end), download.
+ * accum_rgba: width*height*4 floats, (sum r, sum g, sum b, number of samples) per pixel, row 0 = top. */
+RTW_API int rtw_render(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, float* accum_rgba, rtw_stats* stats);
+
+/* Device-resident render.  accum_fx: width*height*4 int64 on the scene's device; the kernel ADDS
+ * fixed-point radiance (1 unit = 2^-32) per channel and 1 per finished path to channel 3, so shards rendered by
+ * different calls / GPUs combine with an exact integer sum (ncclSum on int64) independent of order.
+ * Work is enqueued on `cuda_stream` (a cudaStream_t, may be NULL); the call returns without synchronising unless
+ * `stats` is non-NULL, in which case it synchronises the stream and fills it. */
+RTW_API int rtw_render_device(const rtw_scene* scene, const rtw_render_cfg* cfg, int64_t* accum_fx, void* cuda_stream,
+                      rtw_stats* stats);
+/* accum_fx (int64 x4 per pixel, device) -> accum_rgba (float x4 per pixel, device), on `cuda_stream`. */
+RTW_API int rtw_accum_to_float(const int64_t* accum_fx, float* accum_rgba, int64_t npixels, int32_t device,
+                       void* cuda_stream);
+
+/* Single-process multi-GPU render: samples split evenly over devices 0..ngpus-1 (requires ngpus | spp), one
+ * ncclReduce(sum) of the accumulation buffers onto device 0 over NVLink, then one download. */
+RTW_API int rtw_render_multi_gpu(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, int32_t ngpus, float* accum_rgba,
+                         rtw_stats* stats);
+
+/* write_color (render.cpp:11-20) on the device: rgb8 = int(256 * clamp(sqrt(sum / spp), 0, 0.999)).
+ * accum_rgba and rgb8 are HOST buffers (npixels*4 floats in, npixels*3 bytes out). */
+RTW_API int rtw_finalize_rgb8(const float* accum_rgba, int64_t npixels, int32_t spp, int32_t device, uint8_t* rgb8);
+
+/* Deterministic primary-ray mode: aperture 0, shutter [time,time], rays through pixel centres.
+ * precision 32: the production fp32 intersection routines (kernel = SPHERES_SMEM or BVH as in rtw_render);
+ * precision 64: the reference formulas evaluated in double on the device (brute force over all primitives).
+ * Outputs (HOST, per pixel): prim_id (-1 = miss), t, normal[3], front_facing. */
+RTW_API int rtw_primary_hits(const rtw_scene_desc* desc, int32_t width, int32_t height, double time, int32_t precision,
+                     int32_t kernel, int32_t device, int32_t* prim_id, double* t, double* normal, uint8_t* front);
+
+/* Unit-level hooks used by the parity tests (HOST buffers, n items each).
+ * rtw_debug_scatter: the device scatter routines on explicit inputs. ball = the "random_unit_vector" sample,
+ *   coin = the Schlick random number.  out_dir/out_att: 3 floats per item; scattered: 0/1 per item.
+ * rtw_debug_samples: the device samplers driven by Philox (key=seed, counter=(i,0,dim,0)):
+ *   ball[3n] (octant-ball sample), disk[2n] (unit-disk sample), u01[4n] (raw uniforms of dimension 0). */
+RTW_API int rtw_debug_scatter(int32_t device, int64_t n, const rtw_material* mats, const float* dir_in, const float* normal,
+                      const uint8_t* front, const float* ball, const float* coin, float* out_dir, float* out_att,
+                      uint8_t* scattered);
+RTW_API int rtw_debug_samples(int32_t device, int64_t n, uint64_t seed, float* ball, float* disk, float* u01);
+
+/* FP32 FFMA micro-benchmark: sustained TFLOP/s (2 flop per FMA) and the SM clock seen, the denominator of the
+ * sphere-scene roofline (MEASURED_PEAKS.json carries only HBM and bf16 figures). */
+RTW_API int rtw_fp32_peak(int32_t device, double seconds, double* tflops, double* sm_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTW_B200_H */

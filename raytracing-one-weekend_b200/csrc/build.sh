@@ -1,0 +1,19 @@
+#!/bin/bash
+# Builds librtw_b200.so (CUDA kernels + C ABI) for sm_100a, in tree.
+set -euo pipefail
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+OUT=../librtw_b200.so
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -ccbin /usr/bin/g++"
+newer=0
+for f in rtw_kernels.cu rtw_abi.cu rtw_multi.cu rtw_device.cuh rtw_internal.h rtw_bvh.h ../../include/rtw_b200.h build.sh; do
+  if [ ! -e "$OUT" ] || [ "$f" -nt "$OUT" ]; then newer=1; fi
+done
+if [ "$newer" = 0 ] && [ "${1:-}" != "-f" ]; then echo "librtw_b200.so up to date"; exit 0; fi
+mkdir -p ../build
+$NVCC $FLAGS ${RTW_PTXAS_V:+-Xptxas -v} -c rtw_kernels.cu -o ../build/rtw_kernels.o &
+$NVCC $FLAGS -c rtw_abi.cu -o ../build/rtw_abi.o &
+$NVCC $FLAGS -c rtw_multi.cu -o ../build/rtw_multi.o &
+wait
+$NVCC -shared -o $OUT ../build/rtw_kernels.o ../build/rtw_abi.o ../build/rtw_multi.o -lcudart_static -ldl -lpthread -lrt
+echo "built $OUT"

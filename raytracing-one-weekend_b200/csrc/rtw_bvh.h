@@ -1,0 +1,174 @@
+// rtw_bvh.h -- host-side binned-SAH BVH builder producing the compact 64-byte two-child nodes the K2 kernel
+// walks.  Replaces the reference's median-split BVHNode constructor (render.cpp:73-110), whose quality the
+// survey measured at 63-108 node visits per ray; only the closest-hit semantics are kept.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <limits>
+#include <vector>
+
+namespace rtw {
+
+struct Box3 {
+  float lo[3], hi[3];
+  void reset() { for (int k = 0; k < 3; ++k) { lo[k] = std::numeric_limits<float>::infinity(); hi[k] = -std::numeric_limits<float>::infinity(); } }
+  void grow(const Box3& b) { for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], b.lo[k]); hi[k] = std::max(hi[k], b.hi[k]); } }
+  void grow(const float p[3]) { for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); } }
+  float half_area() const {
+    const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    return (dx < 0 || dy < 0 || dz < 0) ? 0.0f : dx * dy + dy * dz + dz * dx;
+  }
+};
+
+struct PackedNode {  // 4 x float4, see DevScene::nodes
+  float lmin[3], lmax_x;
+  float lmax_yz[2], rmin_xy[2];
+  float rmin_z, rmax[3];
+  int32_t left, right, pad0, pad1;
+};
+static_assert(sizeof(PackedNode) == 64, "node must be 64 bytes");
+
+class BvhBuilder {
+ public:
+  static constexpr int kMaxLeaf = 4;
+  static constexpr int kBins = 16;
+
+  // boxes[i] / refs[i]: bounds and encoded reference ((kind << 30) | index) of primitive i
+  void build(const std::vector<Box3>& boxes, const std::vector<uint32_t>& refs) {
+    nodes_.clear(); leaf_refs_.clear();
+    const size_t n = boxes.size();
+    if (n == 0) return;
+    boxes_ = &boxes; refs_ = &refs;
+    order_.resize(n);
+    cent_.resize(3 * n);
+    for (size_t i = 0; i < n; ++i) {
+      order_[i] = static_cast<uint32_t>(i);
+      for (int k = 0; k < 3; ++k) cent_[3 * i + k] = 0.5f * (boxes[i].lo[k] + boxes[i].hi[k]);
+    }
+    nodes_.reserve(2 * n / kMaxLeaf + 16);
+    leaf_refs_.reserve(n);
+    Box3 rb; rb.reset();
+    for (size_t i = 0; i < n; ++i) rb.grow(boxes[i]);
+    if (n <= static_cast<size_t>(kMaxLeaf)) {
+      // a single leaf still needs a root node: left = the leaf, right = empty leaf with an inverted box
+      PackedNode nd{};
+      set_child(nd, 0, rb, make_leaf(0, n));
+      Box3 e; e.reset();
+      set_child(nd, 1, e, ~0);  // ~0 -> first 0, count 0
+      nodes_.push_back(nd);
+      return;
+    }
+    nodes_.push_back(PackedNode{});
+    build_node(0, 0, n, rb);
+  }
+
+  const std::vector<PackedNode>& nodes() const { return nodes_; }
+  const std::vector<uint32_t>& leaf_refs() const { return leaf_refs_; }
+
+ private:
+  const std::vector<Box3>* boxes_ = nullptr;
+  const std::vector<uint32_t>* refs_ = nullptr;
+  std::vector<uint32_t> order_;
+  std::vector<float> cent_;
+  std::vector<PackedNode> nodes_;
+  std::vector<uint32_t> leaf_refs_;
+
+  static void pad(Box3& b) {  // conservative against the fp32 slab arithmetic
+    for (int k = 0; k < 3; ++k) {
+      if (!(b.lo[k] <= b.hi[k])) continue;
+      const float m = std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k]));
+      const float e = 4.0f * 1.1920929e-7f * m + 1e-30f;
+      b.lo[k] -= e; b.hi[k] += e;
+    }
+  }
+  static void set_child(PackedNode& nd, int which, Box3 b, int32_t code) {
+    pad(b);
+    if (which == 0) {
+      nd.lmin[0] = b.lo[0]; nd.lmin[1] = b.lo[1]; nd.lmin[2] = b.lo[2];
+      nd.lmax_x = b.hi[0]; nd.lmax_yz[0] = b.hi[1]; nd.lmax_yz[1] = b.hi[2];
+      nd.left = code;
+    } else {
+      nd.rmin_xy[0] = b.lo[0]; nd.rmin_xy[1] = b.lo[1]; nd.rmin_z = b.lo[2];
+      nd.rmax[0] = b.hi[0]; nd.rmax[1] = b.hi[1]; nd.rmax[2] = b.hi[2];
+      nd.right = code;
+    }
+  }
+  int32_t make_leaf(size_t begin, size_t end) {
+    const uint32_t first = static_cast<uint32_t>(leaf_refs_.size());
+    for (size_t i = begin; i < end; ++i) leaf_refs_.push_back((*refs_)[order_[i]]);
+    const uint32_t v = (first << 5) | static_cast<uint32_t>(end - begin);
+    return static_cast<int32_t>(~v);
+  }
+  Box3 range_box(size_t begin, size_t end) const {
+    Box3 b; b.reset();
+    for (size_t i = begin; i < end; ++i) b.grow((*boxes_)[order_[i]]);
+    return b;
+  }
+
+  // returns child code for [begin,end): either a leaf code or the index of a freshly built inner node
+  int32_t build_child(size_t begin, size_t end, const Box3& box) {
+    if (end - begin <= static_cast<size_t>(kMaxLeaf)) return make_leaf(begin, end);
+    const int32_t idx = static_cast<int32_t>(nodes_.size());
+    nodes_.push_back(PackedNode{});
+    build_node(idx, begin, end, box);
+    return idx;
+  }
+
+  void build_node(int32_t idx, size_t begin, size_t end, const Box3& box) {
+    (void)box;
+    // centroid bounds
+    float clo[3], chi[3];
+    for (int k = 0; k < 3; ++k) { clo[k] = std::numeric_limits<float>::infinity(); chi[k] = -clo[k]; }
+    for (size_t i = begin; i < end; ++i)
+      for (int k = 0; k < 3; ++k) { const float c = cent_[3 * order_[i] + k]; clo[k] = std::min(clo[k], c); chi[k] = std::max(chi[k], c); }
+    int best_axis = -1, best_split = -1; float best_cost = std::numeric_limits<float>::infinity();
+    for (int ax = 0; ax < 3; ++ax) {
+      const float ext = chi[ax] - clo[ax];
+      if (!(ext > 0.0f)) continue;
+      Box3 bb[kBins]; uint32_t cnt[kBins] = {0};
+      for (int b = 0; b < kBins; ++b) bb[b].reset();
+      const float scale = kBins / ext;
+      for (size_t i = begin; i < end; ++i) {
+        int b = static_cast<int>((cent_[3 * order_[i] + ax] - clo[ax]) * scale);
+        b = std::min(std::max(b, 0), kBins - 1);
+        bb[b].grow((*boxes_)[order_[i]]); ++cnt[b];
+      }
+      float right_area[kBins]; uint32_t right_cnt[kBins];
+      Box3 acc; acc.reset(); uint32_t c = 0;
+      for (int b = kBins - 1; b > 0; --b) { acc.grow(bb[b]); c += cnt[b]; right_area[b] = acc.half_area(); right_cnt[b] = c; }
+      acc.reset(); c = 0;
+      for (int b = 0; b < kBins - 1; ++b) {
+        acc.grow(bb[b]); c += cnt[b];
+        if (c == 0 || right_cnt[b + 1] == 0) continue;
+        const float cost = acc.half_area() * c + right_area[b + 1] * right_cnt[b + 1];
+        if (cost < best_cost) { best_cost = cost; best_axis = ax; best_split = b; }
+      }
+    }
+    size_t mid;
+    if (best_axis < 0) {
+      mid = begin + (end - begin) / 2;  // all centroids coincide: split the list in half
+    } else {
+      const float ext = chi[best_axis] - clo[best_axis];
+      const float scale = kBins / ext;
+      const float lo = clo[best_axis];
+      const int ax = best_axis, sp = best_split;
+      auto it = std::partition(order_.begin() + begin, order_.begin() + end, [&](uint32_t id) {
+        int b = static_cast<int>((cent_[3 * id + ax] - lo) * scale);
+        b = std::min(std::max(b, 0), kBins - 1);
+        return b <= sp;
+      });
+      mid = static_cast<size_t>(it - order_.begin());
+      if (mid == begin || mid == end) mid = begin + (end - begin) / 2;
+    }
+    const Box3 lb = range_box(begin, mid), rb = range_box(mid, end);
+    const int32_t lc = build_child(begin, mid, lb);
+    const int32_t rc = build_child(mid, end, rb);
+    PackedNode nd{};
+    set_child(nd, 0, lb, lc);
+    set_child(nd, 1, rb, rc);
+    nodes_[idx] = nd;
+  }
+};
+
+}  // namespace rtw

@@ -1,0 +1,310 @@
+// rtw_device.cuh -- device-side building blocks of the B200 path tracer (sm_100a).
+//
+// What each block replaces in the reference (/root/reference/src):
+//   philox4x32_10 / u01 / sample_*     random-utils.cpp:6-41 (global mt19937 + rejection loops) -> counter-based
+//                                      stream keyed on (pixel, sample, dimension), direct inversion
+//   camera_ray                         Camera::get_ray, common-model.cpp:156-167
+//   sphere_hit_t<T>                    sphere_hit_helper, common-model.cpp:64-91 (root selection, tmin/tmax rule)
+//   triangle_hit<T>                    Triangle::hit, common-model.cpp:103-125
+//   scatter_dir                        Lambertian/Metal/Dielectric::scatter, common-model.cpp:13-62
+//   sky_color                          ray_color miss branch, render.cpp:125-128
+// The reference computes in double; the render kernels compute in float (fp64 only for spheres flagged "big",
+// where |f|^2 - r^2 cancels catastrophically in fp32).  Quirks Q1-Q7 of SURVEY.md section 0 are kept on purpose.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rtw {
+
+constexpr float kTMin = 0.001f;  // render.cpp:33 default tmin of BVHNode::hit
+constexpr float kInf = __builtin_huge_valf();
+constexpr int kBvhStack = 48;
+
+// ---------------------------------------------------------------------------------------------------------
+// Device scene (flattened SoA; built by rtw_scene_upload)
+// ---------------------------------------------------------------------------------------------------------
+struct DevCamera {
+  float origin[3], lower_left[3], horizontal[3], vertical[3], u[3], v[3];
+  float lens_radius, t0, t1;
+};
+
+struct BigSphere {  // spheres with |r| >= kBigRadius: tested in fp64 for every ray, outside tables and BVH
+  double c0[3];
+  double dc[3];
+  double r;
+  int32_t prim_id;
+  int32_t material;
+};
+
+struct DevScene {
+  // small spheres, static ones first then moving ones
+  const float4* sphA;  // (c0.x, c0.y, c0.z, r2c)   r2c = conservative r^2 for the line-distance reject test
+  const float4* sphB;  // (dc.x, dc.y, dc.z, r)     dc = c1 - c0 (0 for static), r = true (signed) radius
+  const int2* sphId;   // (primitive id, material)
+  int32_t n_static, n_moving;
+  const BigSphere* big;
+  int32_t n_big;
+  // triangles: 3 float4 each: (a.xyz, n.x) (e1.xyz, n.y) (e2.xyz, n.z), n = cross(e1, e2) un-normalised
+  const float4* tri;
+  const int2* triId;
+  int32_t n_tri;
+  // BVH over small spheres + triangles: 4 float4 per node
+  //   q0 = (lmin.x, lmin.y, lmin.z, lmax.x) q1 = (lmax.y, lmax.z, rmin.x, rmin.y)
+  //   q2 = (rmin.z, rmax.x, rmax.y, rmax.z) q3 = (left, right, -, -) as int bits
+  //   child >= 0: inner node index; child < 0: leaf, ~child = (first << 5) | count  into leafRefs
+  const float4* nodes;
+  const uint32_t* leafRefs;  // (kind << 30) | index, kind 0 = sphere table index, 1 = triangle index
+  int32_t n_nodes;
+  // materials
+  const float4* matA;  // (albedo.r, albedo.g, albedo.b, fuzz)
+  const float2* matB;  // (ior, kind as int bits)
+  DevCamera cam;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// small vector helpers
+// ---------------------------------------------------------------------------------------------------------
+template <typename T> struct V3 { T x, y, z; };
+using F3 = V3<float>;
+using D3 = V3<double>;
+
+template <typename T> __host__ __device__ __forceinline__ V3<T> mk(T x, T y, T z) { V3<T> r; r.x = x; r.y = y; r.z = z; return r; }
+template <typename T> __host__ __device__ __forceinline__ V3<T> operator+(V3<T> a, V3<T> b) { return mk<T>(a.x + b.x, a.y + b.y, a.z + b.z); }
+template <typename T> __host__ __device__ __forceinline__ V3<T> operator-(V3<T> a, V3<T> b) { return mk<T>(a.x - b.x, a.y - b.y, a.z - b.z); }
+template <typename T> __host__ __device__ __forceinline__ V3<T> operator-(V3<T> a) { return mk<T>(-a.x, -a.y, -a.z); }
+template <typename T> __host__ __device__ __forceinline__ V3<T> operator*(V3<T> a, T s) { return mk<T>(a.x * s, a.y * s, a.z * s); }
+template <typename T> __host__ __device__ __forceinline__ V3<T> operator*(T s, V3<T> a) { return mk<T>(a.x * s, a.y * s, a.z * s); }
+template <typename T> __host__ __device__ __forceinline__ T dot(V3<T> a, V3<T> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <typename T> __host__ __device__ __forceinline__ V3<T> cross(V3<T> a, V3<T> b) {
+  return mk<T>(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
+}
+__device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }
+__device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+__device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+template <typename T> __device__ __forceinline__ V3<T> normalize(V3<T> a) { return a * rsqrt_(dot(a, a)); }
+
+// ---------------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11): counter = (pixel, sample, dimension, 0), key = seed.
+//   dimension 0: (pixel jitter x, pixel jitter y, lens radius, lens azimuth)
+//   dimension 1: (shutter time, -, -, -)
+//   dimension 2+k: k-th scatter of the path: (ball z, ball azimuth, ball radius, Schlick coin)
+// ---------------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return static_cast<uint32_t>((static_cast<uint64_t>(a) * b) >> 32);
+#endif
+}
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = mulhi32(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__host__ __device__ __forceinline__ float u01(uint32_t x) { return static_cast<float>(x >> 8) * 5.9604644775390625e-8f; }
+
+// Uniform point of the unit ball restricted to the positive octant, NOT normalised: the distribution the
+// reference's random_unit_vector() actually has (random-utils.cpp:23-33), by direct inversion:
+// z uniform in [0,1), azimuth uniform in [0,pi/2), radius = cbrt(xi).
+__device__ __forceinline__ F3 sample_octant_ball(float xz, float xphi, float xrho) {
+  const float rho = cbrtf(xrho);
+  const float sn = sqrtf(fmaf(-xz, xz, 1.0f));
+  float s, c;
+  sincospif(0.5f * xphi, &s, &c);
+  const float k = rho * sn;
+  return mk<float>(k * c, k * s, rho * xz);
+}
+// Uniform point of the unit disk (random-utils.cpp:34-41) by direct inversion.
+__device__ __forceinline__ float2 sample_disk(float xr, float xphi) {
+  const float r = sqrtf(xr);
+  float s, c;
+  sincospif(2.0f * xphi, &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+// Camera::get_ray (common-model.cpp:156-167): s,t in viewport units, disk sample and shutter time explicit.
+template <typename T, typename Cam>
+__device__ __forceinline__ void camera_ray(const Cam& cam, T s, T t, T diskx, T disky, V3<T>& org, V3<T>& dir) {
+  const T rx = static_cast<T>(cam.lens_radius) * diskx, ry = static_cast<T>(cam.lens_radius) * disky;
+  org = mk<T>(cam.origin[0] + cam.u[0] * rx + cam.v[0] * ry, cam.origin[1] + cam.u[1] * rx + cam.v[1] * ry,
+              cam.origin[2] + cam.u[2] * rx + cam.v[2] * ry);
+  dir = mk<T>(cam.lower_left[0] + s * cam.horizontal[0] + t * cam.vertical[0] - org.x,
+              cam.lower_left[1] + s * cam.horizontal[1] + t * cam.vertical[1] - org.y,
+              cam.lower_left[2] + s * cam.horizontal[2] + t * cam.vertical[2] - org.z);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Intersection
+// ---------------------------------------------------------------------------------------------------------
+// sphere_hit_helper (common-model.cpp:64-91).  Same roots and the same accept rule (nearer root if inside
+// [tmin,tmax], else the farther one), but the discriminant is evaluated as a*(r^2 - |oc - (h/a) d|^2), which is
+// algebraically h^2 - a*c and does not cancel in fp32 (Haines et al., "Precision improvements for ray/sphere
+// intersection", Ray Tracing Gems ch. 7, adapted to un-normalised d).  Returns t or -1.
+template <typename T>
+__device__ __forceinline__ T sphere_hit_t(V3<T> o, V3<T> d, T a, T inv_a, V3<T> c, T r, T tmin, T tmax) {
+  const V3<T> oc = o - c;
+  const T h = dot(oc, d);
+  const T k = h * inv_a;
+  const V3<T> l = mk<T>(oc.x - k * d.x, oc.y - k * d.y, oc.z - k * d.z);
+  const T disc = r * r - dot(l, l);
+  if (!(disc >= T(0))) return T(-1);
+  const T sq = sqrt_(a * disc);
+  T root = (-h - sq) * inv_a;
+  if (root < tmin || root > tmax) {
+    root = (-h + sq) * inv_a;
+    if (root < tmin || root > tmax) return T(-1);
+  }
+  return root;
+}
+
+// Triangle::hit (common-model.cpp:103-125) with e1, e2, n = e1 x e2 precomputed per triangle.  Un-normalised
+// n and d, back faces culled by det >= 1e-6 exactly as the reference.  Returns t or -1.
+template <typename T>
+__device__ __forceinline__ T triangle_hit(V3<T> o, V3<T> d, V3<T> a, V3<T> e1, V3<T> e2, V3<T> n, T tmin, T tmax) {
+  const T det = -dot(d, n);
+  const T invdet = T(1) / det;
+  const V3<T> ao = o - a;
+  const V3<T> dao = cross(ao, d);
+  const T u = dot(e2, dao) * invdet;
+  const T v = -dot(e1, dao) * invdet;
+  const T t = dot(ao, n) * invdet;
+  if (det >= T(1e-6) && t >= tmin && t <= tmax && u >= T(0) && v >= T(0) && (u + v) <= T(1)) return t;
+  return T(-1);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Materials (common-model.cpp:13-62).  Returns false when the path is absorbed.
+// ---------------------------------------------------------------------------------------------------------
+enum : int { kLambertian = 0, kMetal = 1, kDielectric = 2 };
+
+__device__ __forceinline__ F3 reflect3(F3 I, F3 N) { return I - N * (2.0f * dot(N, I)); }
+
+__device__ __forceinline__ bool scatter_dir(int kind, float fuzz, float ior, F3 d_in, F3 n, bool front, F3 ball,
+                                            float coin, F3& d_out) {
+  if (kind == kLambertian) {
+    // common-model.cpp:15-18: absorbed only if normal == ball component-wise within 1e-8
+    if (fabsf(n.x - ball.x) < 1e-8f && fabsf(n.y - ball.y) < 1e-8f && fabsf(n.z - ball.z) < 1e-8f) return false;
+    d_out = n + ball;
+    return true;
+  }
+  if (kind == kMetal) {  // always scatters, keeps |d_in|
+    d_out = reflect3(d_in, n) + ball * fuzz;
+    return true;
+  }
+  // Dielectric: Schlick on the normalised incoming direction; NaN from sqrt(1-cos^2) compares false exactly
+  // like the reference's doubles do (common-model.cpp:45-54).
+  const F3 unit = normalize(d_in);
+  const float cos_theta = dot(-unit, n);
+  const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+  const float ratio = front ? (1.0f / ior) : ior;
+  const bool cannot_refract = ratio * sin_theta > 1.0f;
+  float r0 = (1.0f - ratio) / (1.0f + ratio);
+  r0 = r0 * r0;
+  const float m = 1.0f - cos_theta;
+  const float m2 = m * m;
+  const float refl = r0 + (1.0f - r0) * (m2 * m2 * m);
+  F3 dir;
+  if (cannot_refract || refl > coin) {
+    dir = reflect3(unit, n);
+  } else {  // glm::refract
+    const float dn = dot(n, unit);
+    const float k = 1.0f - ratio * ratio * (1.0f - dn * dn);
+    dir = (k >= 0.0f) ? (unit * ratio - n * (ratio * dn + sqrtf(k))) : mk<float>(0.f, 0.f, 0.f);
+  }
+  d_out = dir + ball * fuzz;
+  return true;
+}
+
+// render.cpp:125-128
+__device__ __forceinline__ F3 sky_color(F3 d) {
+  const float uy = d.y * rsqrtf(dot(d, d));
+  const float t = 0.5f * (uy + 1.0f);
+  return mk<float>((1.0f - t) + t * 0.5f, (1.0f - t) + t * 0.7f, (1.0f - t) + t * 1.0f);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Hit encoding shared by the two tracers: >= 0 small-sphere table index; kHitTri | triangle index;
+// kHitBig | big-sphere index; kMiss.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kMiss = -1;
+constexpr int kHitTri = 0x40000000;
+constexpr int kHitBig = 0x20000000;
+
+// fp64 test of the big spheres (reference formula verbatim in double: common-model.cpp:70-82).
+__device__ __forceinline__ void trace_big_spheres(const DevScene& sc, F3 o, F3 d, float tm, float& best_t, int& best_i) {
+  for (int k = 0; k < sc.n_big; ++k) {
+    const BigSphere& b = sc.big[k];
+    const double time = tm;
+    const D3 c = mk<double>(b.c0[0] + time * b.dc[0], b.c0[1] + time * b.dc[1], b.c0[2] + time * b.dc[2]);
+    const D3 od = mk<double>(o.x, o.y, o.z), dd = mk<double>(d.x, d.y, d.z);
+    const D3 oc = od - c;
+    const double a = dot(dd, dd), h = dot(oc, dd), cc = dot(oc, oc) - b.r * b.r;
+    const double disc = h * h - a * cc;
+    if (disc < 0.0) continue;
+    const double sq = sqrt(disc);
+    const double tmin = static_cast<double>(kTMin), tmax = static_cast<double>(best_t);
+    double root = (-h - sq) / a;
+    if (root < tmin || root > tmax) {
+      root = (-h + sq) / a;
+      if (root < tmin || root > tmax) continue;
+    }
+    best_t = static_cast<float>(root);
+    best_i = kHitBig | k;
+  }
+}
+
+// Geometry of the accepted hit: point, shading normal (as the reference defines it), front flag, material.
+struct HitGeom {
+  F3 p, n;
+  bool front;
+  int material, prim_id;
+};
+
+__device__ __forceinline__ HitGeom hit_geometry(const DevScene& sc, const float4* sphA, const float4* sphB, F3 o, F3 d,
+                                                float tm, float t, int hit) {
+  HitGeom g;
+  if (hit & kHitTri) {
+    const int i = hit & ~kHitTri;
+    const float4 q0 = __ldg(&sc.tri[3 * i]), q1 = __ldg(&sc.tri[3 * i + 1]), q2 = __ldg(&sc.tri[3 * i + 2]);
+    g.p = o + d * t;
+    g.n = mk<float>(q0.w, q1.w, q2.w);  // un-normalised geometric normal, front_facing always true (Q7)
+    g.front = true;
+    const int2 id = __ldg(&sc.triId[i]);
+    g.prim_id = id.x; g.material = id.y;
+  } else if (hit & kHitBig) {
+    const BigSphere& b = sc.big[hit & ~kHitBig];
+    const double time = tm, td = t;
+    const D3 c = mk<double>(b.c0[0] + time * b.dc[0], b.c0[1] + time * b.dc[1], b.c0[2] + time * b.dc[2]);
+    const D3 p = mk<double>(o.x + td * d.x, o.y + td * d.y, o.z + td * d.z);
+    const D3 n = normalize(p - c);
+    const bool front = ((d.x * n.x + d.y * n.y + d.z * n.z) < 0.0) != (b.r < 0.0);
+    g.p = mk<float>(static_cast<float>(p.x), static_cast<float>(p.y), static_cast<float>(p.z));
+    g.n = front ? mk<float>(static_cast<float>(n.x), static_cast<float>(n.y), static_cast<float>(n.z))
+                : mk<float>(static_cast<float>(-n.x), static_cast<float>(-n.y), static_cast<float>(-n.z));
+    g.front = front;
+    g.prim_id = b.prim_id; g.material = b.material;
+  } else {
+    const float4 A = sphA[hit], B = sphB[hit];
+    const F3 c = mk<float>(fmaf(tm, B.x, A.x), fmaf(tm, B.y, A.y), fmaf(tm, B.z, A.z));
+    const F3 oc = o - c;
+    // p - c = oc + t d, both terms are O(r)-accurate differences; normal = normalize(p - c) (common-model.cpp:86)
+    const F3 pc = mk<float>(fmaf(t, d.x, oc.x), fmaf(t, d.y, oc.y), fmaf(t, d.z, oc.z));
+    F3 n = normalize(pc);
+    const bool front = (dot(d, n) < 0.0f) != (B.w < 0.0f);  // common-model.cpp:88
+    g.p = c + pc;
+    g.n = front ? n : -n;
+    g.front = front;
+    const int2 id = __ldg(&sc.sphId[hit]);
+    g.prim_id = id.x; g.material = id.y;
+  }
+  return g;
+}
+
+}  // namespace rtw

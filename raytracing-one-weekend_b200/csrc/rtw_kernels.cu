@@ -1,0 +1,663 @@
+// rtw_kernels.cu -- sm_100a kernels of the B200 path tracer and their launchers.
+//
+//   k_render<R, MODE>   the per-pixel / per-sample loop of render.cpp:150-167 with ray_color (render.cpp:112-129)
+//                       turned into an iterative bounce loop.  Persistent warps pull units of (128 pixels x SU
+//                       samples) from a global atomic counter; inside a warp every lane keeps R paths in flight
+//                       and a finished path is replaced at once from the warp's pool (ballot + popc ranking), so
+//                       the uniform sphere sweep always runs on full warps regardless of path length.
+//       MODE 0 (K1)     sphere scenes: the whole sphere table is staged in shared memory with TMA bulk copies
+//                       (cp.async.bulk + mbarrier) and swept brute force: per (ray, sphere) 8 FMA for the
+//                       line-distance reject test (+3 for the centre lerp of moving spheres); survivors go through
+//                       the exact reference-rule root selection.
+//       MODE 1 (K2)     meshes / mixed scenes: SAH BVH in 64-byte two-child nodes, per-thread stack.
+//   k_primary_f32       K3: deterministic primary hits through the SAME tracing routines (parity mode)
+//   k_primary_f64       K3 in double: reference formulas verbatim, brute force over the raw primitive list
+//   k_accum_to_float, k_finalize_rgb8   render.cpp:11-20,176-186 on the device
+//   k_debug_*, k_ffma_peak              unit hooks and the FP32 roofline denominator
+//
+// Radiance is accumulated as int64 fixed point (2^-32) with RED.ADD.64: integer sums are exact, so the image
+// does not depend on scheduling order or on how samples are sharded over GPUs.
+#include "rtw_internal.h"
+
+namespace rtw {
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA bulk copy + mbarrier (PTX; SASS: UBLKCP / SYNCS)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(phase)
+      : "memory");
+  return ok != 0;
+}
+
+// Stage the sphere tables into shared memory.  sA/sB: n float4 each.  One thread issues the copies.
+__device__ __forceinline__ void stage_spheres(const DevScene& sc, float4* sA, float4* sB, uint64_t* bar) {
+  const int n = sc.n_static + sc.n_moving;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && n > 0) {
+    const uint32_t bytes = static_cast<uint32_t>(n) * 16u;
+    mbar_expect_tx(bar, 2u * bytes);
+    constexpr uint32_t kChunk = 32768u;
+    for (uint32_t off = 0; off < bytes; off += kChunk) {
+      const uint32_t sz = min(kChunk, bytes - off);
+      tma_bulk_g2s(reinterpret_cast<char*>(sA) + off, reinterpret_cast<const char*>(sc.sphA) + off, sz, bar);
+      tma_bulk_g2s(reinterpret_cast<char*>(sB) + off, reinterpret_cast<const char*>(sc.sphB) + off, sz, bar);
+    }
+  }
+  if (n > 0) {
+    // bounded spin: a copy that never lands must surface as a launch failure, not as a hung GPU
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, 0)) {
+      if (++spins > (1u << 26)) __trap();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1 tracer: brute-force sweep of the shared-memory sphere table for R rays per lane.
+// Reject test per (ray, sphere): with (u, v) an orthonormal basis of the plane perpendicular to the ray,
+// |((c - o).u, (c - o).v)|^2 <= r^2  <=>  the ray's LINE passes within r of the centre.  8 FMA for a static
+// sphere, 11 for a moving one; r2c carries a conservative slack so fp32 rounding can only add candidates.
+// ---------------------------------------------------------------------------------------------------------
+template <int R>
+struct RaySet {
+  float ox[R], oy[R], oz[R], dx[R], dy[R], dz[R], tm[R];
+};
+
+template <int R, bool STATS>
+__device__ __forceinline__ void trace_spheres(const DevScene& sc, const float4* __restrict__ sA, const float4* __restrict__ sB,
+                                              const RaySet<R>& ray, const bool (&alive)[R], float (&best_t)[R], int (&best_i)[R],
+                                              unsigned long long& n_cand) {
+  float ux[R], uy[R], uz[R], vx[R], vy[R], vz[R], ou[R], ov[R], aa[R], ia[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const float a = ray.dx[r] * ray.dx[r] + ray.dy[r] * ray.dy[r] + ray.dz[r] * ray.dz[r];
+    const float il = rsqrtf(a);
+    const float nx = ray.dx[r] * il, ny = ray.dy[r] * il, nz = ray.dz[r] * il;
+    // branchless orthonormal basis (Duff et al. 2017)
+    const float sg = copysignf(1.0f, nz);
+    const float p = -1.0f / (sg + nz);
+    const float q = nx * ny * p;
+    ux[r] = 1.0f + sg * nx * nx * p; uy[r] = sg * q; uz[r] = -sg * nx;
+    vx[r] = q; vy[r] = sg + ny * ny * p; vz[r] = -ny;
+    ou[r] = ray.ox[r] * ux[r] + ray.oy[r] * uy[r] + ray.oz[r] * uz[r];
+    ov[r] = ray.ox[r] * vx[r] + ray.oy[r] * vy[r] + ray.oz[r] * vz[r];
+    aa[r] = a; ia[r] = 1.0f / a;
+    best_t[r] = kInf; best_i[r] = kMiss;
+    if (!alive[r]) { ux[r] = uy[r] = uz[r] = vx[r] = vy[r] = vz[r] = 0.0f; ou[r] = 1e18f; ov[r] = 0.0f; }
+  }
+  const int ns = sc.n_static, nt = sc.n_static + sc.n_moving;
+
+  auto candidate = [&](int i, int r, float cx, float cy, float cz, float rad) {
+    if (STATS) ++n_cand;
+    const float t = sphere_hit_t<float>(mk<float>(ray.ox[r], ray.oy[r], ray.oz[r]), mk<float>(ray.dx[r], ray.dy[r], ray.dz[r]),
+                                        aa[r], ia[r], mk<float>(cx, cy, cz), rad, kTMin, best_t[r]);
+    if (t >= 0.0f) { best_t[r] = t; best_i[r] = i; }
+  };
+
+#pragma unroll 2
+  for (int i = 0; i < ns; ++i) {
+    const float4 A = sA[i];
+    float s[R];
+    int any = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float pu = fmaf(A.x, ux[r], fmaf(A.y, uy[r], fmaf(A.z, uz[r], -ou[r])));
+      const float pv = fmaf(A.x, vx[r], fmaf(A.y, vy[r], fmaf(A.z, vz[r], -ov[r])));
+      s[r] = fmaf(pu, pu, fmaf(pv, pv, -A.w));
+      any |= __float_as_int(s[r]);
+    }
+    if (any < 0) {
+      const float rad = sB[i].w;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (s[r] < 0.0f) candidate(i, r, A.x, A.y, A.z, rad);
+    }
+  }
+#pragma unroll 2
+  for (int i = ns; i < nt; ++i) {
+    const float4 A = sA[i];
+    const float4 B = sB[i];
+    float s[R];
+    int any = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float cx = fmaf(ray.tm[r], B.x, A.x), cy = fmaf(ray.tm[r], B.y, A.y), cz = fmaf(ray.tm[r], B.z, A.z);
+      const float pu = fmaf(cx, ux[r], fmaf(cy, uy[r], fmaf(cz, uz[r], -ou[r])));
+      const float pv = fmaf(cx, vx[r], fmaf(cy, vy[r], fmaf(cz, vz[r], -ov[r])));
+      s[r] = fmaf(pu, pu, fmaf(pv, pv, -A.w));
+      any |= __float_as_int(s[r]);
+    }
+    if (any < 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (s[r] < 0.0f)
+          candidate(i, r, fmaf(ray.tm[r], B.x, A.x), fmaf(ray.tm[r], B.y, A.y), fmaf(ray.tm[r], B.z, A.z), B.w);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if (alive[r]) trace_big_spheres(sc, mk<float>(ray.ox[r], ray.oy[r], ray.oz[r]), mk<float>(ray.dx[r], ray.dy[r], ray.dz[r]),
+                                    ray.tm[r], best_t[r], best_i[r]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2 tracer: BVH traversal (one ray per lane), closest hit, near child first.
+// ---------------------------------------------------------------------------------------------------------
+template <bool STATS>
+__device__ __forceinline__ void trace_bvh(const DevScene& sc, F3 o, F3 d, float tm, float& best_t, int& best_i,
+                                          unsigned long long& n_nodes, unsigned long long& n_sph, unsigned long long& n_tri) {
+  best_t = kInf; best_i = kMiss;
+  const float a = dot(d, d), ia = 1.0f / a;
+  const float idx = 1.0f / d.x, idy = 1.0f / d.y, idz = 1.0f / d.z;
+  const float odx = o.x * idx, ody = o.y * idy, odz = o.z * idz;
+  int stack[kBvhStack];
+  int sp = 0;
+  int node = sc.n_nodes > 0 ? 0 : kMiss;
+
+  auto leaf = [&](int code) {
+    const uint32_t v = static_cast<uint32_t>(~code);
+    const uint32_t first = v >> 5, cnt = v & 31u;
+    for (uint32_t k = 0; k < cnt; ++k) {
+      const uint32_t ref = __ldg(&sc.leafRefs[first + k]);
+      const int i = static_cast<int>(ref & 0x3fffffffu);
+      if (ref >> 30) {
+        if (STATS) ++n_tri;
+        const float4 q0 = __ldg(&sc.tri[3 * i]), q1 = __ldg(&sc.tri[3 * i + 1]), q2 = __ldg(&sc.tri[3 * i + 2]);
+        const float t = triangle_hit<float>(o, d, mk<float>(q0.x, q0.y, q0.z), mk<float>(q1.x, q1.y, q1.z), mk<float>(q2.x, q2.y, q2.z),
+                                            mk<float>(q0.w, q1.w, q2.w), kTMin, best_t);
+        if (t >= 0.0f) { best_t = t; best_i = kHitTri | i; }
+      } else {
+        if (STATS) ++n_sph;
+        const float4 A = __ldg(&sc.sphA[i]), B = __ldg(&sc.sphB[i]);
+        const float t = sphere_hit_t<float>(o, d, a, ia, mk<float>(fmaf(tm, B.x, A.x), fmaf(tm, B.y, A.y), fmaf(tm, B.z, A.z)), B.w,
+                                            kTMin, best_t);
+        if (t >= 0.0f) { best_t = t; best_i = i; }
+      }
+    }
+  };
+
+  while (node != kMiss) {
+    if (node < 0) {
+      leaf(node);
+      node = sp > 0 ? stack[--sp] : kMiss;
+      continue;
+    }
+    if (STATS) ++n_nodes;
+    const float4 q0 = __ldg(&sc.nodes[4 * node]), q1 = __ldg(&sc.nodes[4 * node + 1]), q2 = __ldg(&sc.nodes[4 * node + 2]),
+                 q3 = __ldg(&sc.nodes[4 * node + 3]);
+    // slab test of both children against [tmin, best_t]
+    float t0x = fmaf(q0.x, idx, -odx), t1x = fmaf(q0.w, idx, -odx);
+    float t0y = fmaf(q0.y, idy, -ody), t1y = fmaf(q1.x, idy, -ody);
+    float t0z = fmaf(q0.z, idz, -odz), t1z = fmaf(q1.y, idz, -odz);
+    const float ln = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), kTMin));
+    const float lf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best_t));
+    t0x = fmaf(q1.z, idx, -odx); t1x = fmaf(q2.y, idx, -odx);
+    t0y = fmaf(q1.w, idy, -ody); t1y = fmaf(q2.z, idy, -ody);
+    t0z = fmaf(q2.x, idz, -odz); t1z = fmaf(q2.w, idz, -odz);
+    const float rn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), kTMin));
+    const float rf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best_t));
+    const bool hl = ln <= lf, hr = rn <= rf;
+    const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
+    if (hl && hr) {
+      const bool lfirst = ln <= rn;
+      node = lfirst ? left : right;
+      if (sp < kBvhStack) stack[sp++] = lfirst ? right : left;
+    } else if (hl) {
+      node = left;
+    } else if (hr) {
+      node = right;
+    } else {
+      node = sp > 0 ? stack[--sp] : kMiss;
+    }
+  }
+  trace_big_spheres(sc, o, d, tm, best_t, best_i);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The render kernel
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void accum_add(unsigned long long* accum, uint32_t pix, float r, float g, float b) {
+  // NaN / negative / absurd contributions are dropped (the reference would print garbage for them)
+  const float lim = 1.0e9f;
+  r = (r >= 0.0f && r < lim) ? r : 0.0f;
+  g = (g >= 0.0f && g < lim) ? g : 0.0f;
+  b = (b >= 0.0f && b < lim) ? b : 0.0f;
+  unsigned long long* px = accum + 4ull * pix;
+  atomicAdd(px + 0, static_cast<unsigned long long>(__float2ll_rn(r * 4294967296.0f)));
+  atomicAdd(px + 1, static_cast<unsigned long long>(__float2ll_rn(g * 4294967296.0f)));
+  atomicAdd(px + 2, static_cast<unsigned long long>(__float2ll_rn(b * 4294967296.0f)));
+}
+
+template <int R, int MODE, bool STATS>
+__global__ void __launch_bounds__(kRenderThreads, (MODE == 0 ? (R >= 4 ? 2 : (R == 2 ? 3 : 4)) : 3))
+k_render(const __grid_constant__ RenderParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const DevScene& sc = p.sc;
+  const float4* sA = sc.sphA;
+  const float4* sB = sc.sphB;
+  if (MODE == 0) {
+    const int n = sc.n_static + sc.n_moving;
+    float4* a = reinterpret_cast<float4*>(smem_raw + 16);
+    float4* b = a + n;
+    stage_spheres(sc, a, b, reinterpret_cast<uint64_t*>(smem_raw));
+    sA = a; sB = b;
+  }
+
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint2 key = make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32));
+
+  RaySet<R> ray;
+  float tr[R], tg[R], tb[R];
+  uint32_t pix[R], smp[R];
+  int depth[R];
+  bool alive[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    alive[r] = false; pix[r] = 0; smp[r] = 0; depth[r] = 0;
+    ray.ox[r] = ray.oy[r] = ray.oz[r] = 0.f; ray.dx[r] = ray.dy[r] = 0.f; ray.dz[r] = 1.f; ray.tm[r] = 0.f;
+    tr[r] = tg[r] = tb[r] = 0.f;
+  }
+  uint32_t pool_next = 0, pool_end = 0, grp = 0, s0 = 0;
+  bool exhausted = false;
+  unsigned long long n_rays = 0, n_paths = 0, n_tests = 0, n_cand = 0, n_nodes = 0, n_tri = 0;
+
+  for (;;) {
+    // ---- refill: every dead slot takes the next (pixel, sample) of the warp's pool --------------------------
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        const uint32_t need = __ballot_sync(0xffffffffu, !alive[r]);
+        if (need == 0u) break;
+        if (pool_next == pool_end) {
+          if (exhausted) break;
+          unsigned long long u = 0;
+          if (lane == 0) u = atomicAdd(p.counters + kCtrWork, 1ull);
+          u = __shfl_sync(0xffffffffu, u, 0);
+          if (u >= p.n_units) { exhausted = true; break; }
+          grp = static_cast<uint32_t>(u / p.n_chunks);
+          const uint32_t chunk = static_cast<uint32_t>(u - static_cast<unsigned long long>(grp) * p.n_chunks);
+          s0 = p.s_begin + chunk * p.su;
+          const uint32_t ns = min(p.su, p.s_end - s0);
+          pool_next = 0; pool_end = ns * kGroupPixels;
+        }
+        const uint32_t avail = pool_end - pool_next;
+        const uint32_t rank = __popc(need & lt);
+        if (!alive[r] && rank < avail) {
+          const uint32_t within = pool_next + rank;
+          const uint32_t px = grp * kGroupPixels + (within & (kGroupPixels - 1u));
+          const uint32_t sm = s0 + within / kGroupPixels;
+          if (px < p.npix) {
+            // primary ray: render.cpp:158-160 with the pixel mapping of SURVEY Q12
+            const uint4 x0 = philox4x32_10(make_uint4(px, sm, 0u, 0u), key);
+            const uint4 x1 = philox4x32_10(make_uint4(px, sm, 1u, 0u), key);
+            const uint32_t i = px / p.width, j = px - i * p.width;
+            const float u = (static_cast<float>(j) + u01(x0.x)) * p.inv_wm1;
+            const float v = (static_cast<float>(p.height - 1u - i) + u01(x0.y)) * p.inv_hm1;
+            const float2 dk = sample_disk(u01(x0.z), u01(x0.w));
+            F3 o, d;
+            camera_ray<float>(sc.cam, u, v, dk.x, dk.y, o, d);
+            ray.ox[r] = o.x; ray.oy[r] = o.y; ray.oz[r] = o.z;
+            ray.dx[r] = d.x; ray.dy[r] = d.y; ray.dz[r] = d.z;
+            ray.tm[r] = fmaf(u01(x1.x), sc.cam.t1 - sc.cam.t0, sc.cam.t0);
+            tr[r] = tg[r] = tb[r] = 1.0f;
+            pix[r] = px; smp[r] = sm; depth[r] = 0;
+            alive[r] = true;
+          }
+        }
+        pool_next += min(static_cast<uint32_t>(__popc(need)), avail);
+      }
+    }
+    bool any_alive = false;
+#pragma unroll
+    for (int r = 0; r < R; ++r) any_alive |= alive[r];
+    if (!__any_sync(0xffffffffu, any_alive)) {
+      if (exhausted) break;
+      continue;
+    }
+
+    // ---- trace ---------------------------------------------------------------------------------------------
+    float best_t[R];
+    int best_i[R];
+    if (MODE == 0) {
+      trace_spheres<R, STATS>(sc, sA, sB, ray, alive, best_t, best_i, n_cand);
+      if (STATS) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) if (alive[r]) n_tests += static_cast<unsigned long long>(sc.n_static + sc.n_moving);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        best_t[r] = kInf; best_i[r] = kMiss;
+        if (alive[r])
+          trace_bvh<STATS>(sc, mk<float>(ray.ox[r], ray.oy[r], ray.oz[r]), mk<float>(ray.dx[r], ray.dy[r], ray.dz[r]), ray.tm[r],
+                           best_t[r], best_i[r], n_nodes, n_tests, n_tri);
+      }
+    }
+
+    // ---- shade: ray_color, render.cpp:112-129, one bounce ------------------------------------------------
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (!alive[r]) continue;
+      ++n_rays;
+      const F3 o = mk<float>(ray.ox[r], ray.oy[r], ray.oz[r]), d = mk<float>(ray.dx[r], ray.dy[r], ray.dz[r]);
+      if (best_i[r] == kMiss) {
+        const F3 c = sky_color(d);
+        accum_add(p.accum, pix[r], tr[r] * c.x, tg[r] * c.y, tb[r] * c.z);
+        alive[r] = false;
+      } else if (depth[r] >= p.max_depth) {
+        alive[r] = false;  // hit at depth 0 of the recursion: black
+      } else {
+        const HitGeom g = hit_geometry(sc, sA, sB, o, d, ray.tm[r], best_t[r], best_i[r]);
+        const float4 mA = __ldg(&sc.matA[g.material]);
+        const float2 mB = __ldg(&sc.matB[g.material]);
+        const int kind = __float_as_int(mB.y);
+        const uint4 x = philox4x32_10(make_uint4(pix[r], smp[r], 2u + static_cast<uint32_t>(depth[r]), 0u), key);
+        const F3 ball = sample_octant_ball(u01(x.x), u01(x.y), u01(x.z));
+        F3 dn;
+        if (scatter_dir(kind, mA.w, mB.x, d, g.n, g.front, ball, u01(x.w), dn)) {
+          ray.ox[r] = g.p.x; ray.oy[r] = g.p.y; ray.oz[r] = g.p.z;
+          ray.dx[r] = dn.x; ray.dy[r] = dn.y; ray.dz[r] = dn.z;
+          if (kind != kDielectric) { tr[r] *= mA.x; tg[r] *= mA.y; tb[r] *= mA.z; }
+          ++depth[r];
+        } else {
+          alive[r] = false;
+        }
+      }
+      if (!alive[r]) {
+        ++n_paths;
+        atomicAdd(p.accum + 4ull * pix[r] + 3, 1ull);
+      }
+    }
+  }
+
+  // ---- counters: one atomic per warp -------------------------------------------------------------------------
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    n_rays += __shfl_xor_sync(0xffffffffu, n_rays, off);
+    n_paths += __shfl_xor_sync(0xffffffffu, n_paths, off);
+    if (STATS) {
+      n_tests += __shfl_xor_sync(0xffffffffu, n_tests, off);
+      n_cand += __shfl_xor_sync(0xffffffffu, n_cand, off);
+      n_nodes += __shfl_xor_sync(0xffffffffu, n_nodes, off);
+      n_tri += __shfl_xor_sync(0xffffffffu, n_tri, off);
+    }
+  }
+  if (lane == 0) {
+    atomicAdd(p.counters + kCtrRays, n_rays);
+    atomicAdd(p.counters + kCtrPaths, n_paths);
+    if (STATS) {
+      atomicAdd(p.counters + kCtrSphereTests, n_tests);
+      atomicAdd(p.counters + kCtrCandidates, n_cand);
+      atomicAdd(p.counters + kCtrNodes, n_nodes);
+      atomicAdd(p.counters + kCtrTriTests, n_tri);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K3: deterministic primary hits
+// ---------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kRenderThreads) k_primary_f32(const __grid_constant__ PrimaryParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const DevScene& sc = p.sc;
+  const float4* sA = sc.sphA;
+  const float4* sB = sc.sphB;
+  if (MODE == 0) {
+    const int n = sc.n_static + sc.n_moving;
+    float4* a = reinterpret_cast<float4*>(smem_raw + 16);
+    float4* b = a + n;
+    stage_spheres(sc, a, b, reinterpret_cast<uint64_t*>(smem_raw));
+    sA = a; sB = b;
+  }
+  const uint32_t px = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = px < p.npix;
+  const uint32_t pc = valid ? px : 0u;
+  const uint32_t i = pc / p.width, j = pc - i * p.width;
+  const float u = (static_cast<float>(j) + 0.5f) / static_cast<float>(p.width - 1);
+  const float v = (static_cast<float>(p.height - 1u - i) + 0.5f) / static_cast<float>(p.height - 1);
+  F3 o, d;
+  camera_ray<float>(sc.cam, u, v, 0.0f, 0.0f, o, d);
+  const float tm = p.time;
+  float best_t;
+  int best_i;
+  unsigned long long c0 = 0, c1 = 0, c2 = 0;
+  if (MODE == 0) {
+    RaySet<1> ray;
+    ray.ox[0] = o.x; ray.oy[0] = o.y; ray.oz[0] = o.z; ray.dx[0] = d.x; ray.dy[0] = d.y; ray.dz[0] = d.z; ray.tm[0] = tm;
+    const bool alive[1] = {true};
+    float bt[1]; int bi[1];
+    trace_spheres<1, false>(sc, sA, sB, ray, alive, bt, bi, c0);
+    best_t = bt[0]; best_i = bi[0];
+  } else {
+    trace_bvh<false>(sc, o, d, tm, best_t, best_i, c0, c1, c2);
+  }
+  if (!valid) return;
+  if (best_i == kMiss) {
+    p.prim_id[px] = -1; p.t[px] = 0.0; p.normal[3 * px] = p.normal[3 * px + 1] = p.normal[3 * px + 2] = 0.0; p.front[px] = 0;
+  } else {
+    const HitGeom g = hit_geometry(sc, sA, sB, o, d, tm, best_t, best_i);
+    p.prim_id[px] = g.prim_id; p.t[px] = best_t;
+    p.normal[3 * px] = g.n.x; p.normal[3 * px + 1] = g.n.y; p.normal[3 * px + 2] = g.n.z;
+    p.front[px] = g.front ? 1 : 0;
+  }
+}
+
+struct CamD {
+  double origin[3], lower_left[3], horizontal[3], vertical[3], u[3], v[3];
+  double lens_radius, t0, t1;
+};
+
+// Reference formulas in double, brute force in insertion order, "later primitive wins exact ties" accept rule
+// (render.cpp:57-64): sphere_hit_helper common-model.cpp:64-91, MovingSphere::center oo-primitives.h:64-66,
+// Triangle::hit common-model.cpp:103-125.
+__global__ void __launch_bounds__(256) k_primary_f64(const rtw_primitive* __restrict__ prims, int nprims, rtw_camera cam, uint32_t width,
+                                                     uint32_t height, double time, int32_t* prim_id, double* tout, double* normal,
+                                                     uint8_t* front) {
+  const uint32_t px = blockIdx.x * blockDim.x + threadIdx.x;
+  if (px >= width * height) return;
+  const uint32_t i = px / width, j = px - i * width;
+  const double u = (j + 0.5) / (width - 1.0), v = ((height - 1u - i) + 0.5) / (height - 1.0);
+  D3 o, d;
+  camera_ray<double>(cam, u, v, 0.0, 0.0, o, d);
+  double upper = __longlong_as_double(0x7ff0000000000000ll);
+  int best = -1; D3 bn = mk<double>(0, 0, 0); bool bfront = false;
+  const double tmin = 0.001;
+  for (int k = 0; k < nprims; ++k) {
+    const rtw_primitive& P = prims[k];
+    if (P.kind == RTW_TRIANGLE) {
+      const D3 A = mk<double>(P.a[0], P.a[1], P.a[2]), B = mk<double>(P.b[0], P.b[1], P.b[2]), C = mk<double>(P.c[0], P.c[1], P.c[2]);
+      const D3 e1 = B - A, e2 = C - A, n = cross(e1, e2);
+      const double t = triangle_hit<double>(o, d, A, e1, e2, n, tmin, upper);
+      if (t >= 0.0) { upper = t; best = k; bn = n; bfront = true; }
+    } else {
+      D3 c = mk<double>(P.a[0], P.a[1], P.a[2]);
+      if (P.kind == RTW_MOVING_SPHERE) c = c + time * (mk<double>(P.b[0], P.b[1], P.b[2]) - c);
+      const D3 oc = o - c;
+      const double a = dot(d, d), h = dot(oc, d), cc = dot(oc, oc) - P.radius * P.radius;
+      const double disc = h * h - a * cc;
+      if (disc < 0.0) continue;
+      double root = (-h - sqrt(disc)) / a;
+      if (root < tmin || root > upper) {
+        root = (-h + sqrt(disc)) / a;
+        if (root < tmin || root > upper) continue;
+      }
+      const D3 hp = o + d * root;
+      D3 n = normalize(hp - c);
+      const bool ff = (dot(d, n) < 0.0) != (P.radius < 0.0);
+      upper = root; best = k; bn = ff ? n : -n; bfront = ff;
+    }
+  }
+  prim_id[px] = best; tout[px] = best >= 0 ? upper : 0.0;
+  normal[3 * px] = bn.x; normal[3 * px + 1] = bn.y; normal[3 * px + 2] = bn.z;
+  front[px] = bfront ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Finalize (render.cpp:11-20, 176-186)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_accum_to_float(const long long* __restrict__ fx, float4* __restrict__ out, long long npix) {
+  const long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (k >= npix) return;
+  const double s = 1.0 / 4294967296.0;
+  out[k] = make_float4(static_cast<float>(fx[4 * k] * s), static_cast<float>(fx[4 * k + 1] * s), static_cast<float>(fx[4 * k + 2] * s),
+                       static_cast<float>(fx[4 * k + 3]));
+}
+__global__ void k_finalize_rgb8(const float4* __restrict__ acc, uint8_t* __restrict__ rgb, long long npix, float inv_spp) {
+  const long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (k >= npix) return;
+  const float4 a = acc[k];
+  const float c[3] = {sqrtf(a.x * inv_spp), sqrtf(a.y * inv_spp), sqrtf(a.z * inv_spp)};
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) rgb[3 * k + ch] = static_cast<uint8_t>(static_cast<int>(256.0f * fminf(fmaxf(c[ch], 0.0f), 0.999f)));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Unit hooks
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_debug_scatter(long long n, const int* kind, const float* fuzz, const float* ior, const float* dir_in, const float* normal,
+                                const uint8_t* front, const float* ball, const float* coin, float* out_dir, float* out_att,
+                                const float* albedo, uint8_t* scattered) {
+  const long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (k >= n) return;
+  F3 dn = mk<float>(0.f, 0.f, 0.f);
+  const bool ok = scatter_dir(kind[k], fuzz[k], ior[k], mk<float>(dir_in[3 * k], dir_in[3 * k + 1], dir_in[3 * k + 2]),
+                              mk<float>(normal[3 * k], normal[3 * k + 1], normal[3 * k + 2]), front[k] != 0,
+                              mk<float>(ball[3 * k], ball[3 * k + 1], ball[3 * k + 2]), coin[k], dn);
+  scattered[k] = ok ? 1 : 0;
+  out_dir[3 * k] = dn.x; out_dir[3 * k + 1] = dn.y; out_dir[3 * k + 2] = dn.z;
+  const bool die = kind[k] == kDielectric;
+  for (int c = 0; c < 3; ++c) out_att[3 * k + c] = die ? 1.0f : albedo[3 * k + c];
+}
+__global__ void k_debug_samples(long long n, uint2 key, float* ball, float* disk, float* uni) {
+  const long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (k >= n) return;
+  const uint4 x = philox4x32_10(make_uint4(static_cast<uint32_t>(k), 0u, 0u, 0u), key);
+  const uint4 y = philox4x32_10(make_uint4(static_cast<uint32_t>(k), 0u, 2u, 0u), key);
+  const F3 b = sample_octant_ball(u01(y.x), u01(y.y), u01(y.z));
+  const float2 dk = sample_disk(u01(x.z), u01(x.w));
+  ball[3 * k] = b.x; ball[3 * k + 1] = b.y; ball[3 * k + 2] = b.z;
+  disk[2 * k] = dk.x; disk[2 * k + 1] = dk.y;
+  uni[4 * k] = u01(x.x); uni[4 * k + 1] = u01(x.y); uni[4 * k + 2] = u01(x.z); uni[4 * k + 3] = u01(x.w);
+}
+
+// 8 independent FFMA chains per thread: the sustained FP32 FMA rate that bounds K1.
+__global__ void __launch_bounds__(256) k_ffma_peak(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Launchers (host)
+// ---------------------------------------------------------------------------------------------------------
+template <int R, int MODE, bool STATS>
+static cudaError_t launch_render_t(const RenderParams& p, int sm_count, size_t smem, cudaStream_t stream, int* blocks_out) {
+  auto kern = k_render<R, MODE, STATS>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRenderThreads, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  // persistent grid: a whole number of CTAs per SM, never more warps than units of work
+  unsigned long long want = (p.n_units + (kRenderThreads / 32) - 1) / (kRenderThreads / 32);
+  unsigned long long blocks = static_cast<unsigned long long>(sm_count) * per_sm;
+  if (want < blocks) blocks = want < 1 ? 1 : want;
+  if (blocks_out) *blocks_out = static_cast<int>(blocks);
+  kern<<<static_cast<unsigned>(blocks), kRenderThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_render(const RenderParams& p, int mode, int rays_per_lane, bool stats, int sm_count, cudaStream_t stream) {
+  const size_t smem = mode == 0 ? 16 + static_cast<size_t>(p.sc.n_static + p.sc.n_moving) * 32 : 0;
+#define RTW_LAUNCH(R, M)                                                                      \
+  return stats ? launch_render_t<R, M, true>(p, sm_count, smem, stream, nullptr)               \
+               : launch_render_t<R, M, false>(p, sm_count, smem, stream, nullptr)
+  if (mode == 0) {
+    if (rays_per_lane == 1) { RTW_LAUNCH(1, 0); }
+    if (rays_per_lane == 2) { RTW_LAUNCH(2, 0); }
+    RTW_LAUNCH(4, 0);
+  }
+  RTW_LAUNCH(1, 1);
+#undef RTW_LAUNCH
+}
+
+cudaError_t launch_primary_f32(const PrimaryParams& p, int mode, cudaStream_t stream) {
+  const size_t smem = mode == 0 ? 16 + static_cast<size_t>(p.sc.n_static + p.sc.n_moving) * 32 : 0;
+  const unsigned blocks = (p.npix + kRenderThreads - 1) / kRenderThreads;
+  if (mode == 0) {
+    cudaError_t e = cudaFuncSetAttribute(k_primary_f32<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    k_primary_f32<0><<<blocks, kRenderThreads, smem, stream>>>(p);
+  } else {
+    k_primary_f32<1><<<blocks, kRenderThreads, 0, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_primary_f64(const rtw_primitive* prims, int nprims, const rtw_camera& cam, uint32_t width, uint32_t height, double time,
+                               int32_t* prim_id, double* t, double* normal, uint8_t* front, cudaStream_t stream) {
+  const unsigned npix = width * height;
+  k_primary_f64<<<(npix + 255) / 256, 256, 0, stream>>>(prims, nprims, cam, width, height, time, prim_id, t, normal, front);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_accum_to_float(const long long* fx, float* out, long long npix, cudaStream_t stream) {
+  k_accum_to_float<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, stream>>>(fx, reinterpret_cast<float4*>(out), npix);
+  return cudaGetLastError();
+}
+cudaError_t launch_finalize_rgb8(const float* acc, uint8_t* rgb, long long npix, int spp, cudaStream_t stream) {
+  k_finalize_rgb8<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(acc), rgb, npix,
+                                                                                  1.0f / static_cast<float>(spp));
+  return cudaGetLastError();
+}
+cudaError_t launch_debug_scatter(long long n, const int* kind, const float* fuzz, const float* ior, const float* dir_in, const float* normal,
+                                 const uint8_t* front, const float* ball, const float* coin, float* out_dir, float* out_att,
+                                 const float* albedo, uint8_t* scattered, cudaStream_t stream) {
+  k_debug_scatter<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(n, kind, fuzz, ior, dir_in, normal, front, ball, coin, out_dir,
+                                                                               out_att, albedo, scattered);
+  return cudaGetLastError();
+}
+cudaError_t launch_debug_samples(long long n, uint64_t seed, float* ball, float* disk, float* uni, cudaStream_t stream) {
+  k_debug_samples<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+      n, make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)), ball, disk, uni);
+  return cudaGetLastError();
+}
+cudaError_t launch_ffma_peak(float* out, int blocks, int iters, cudaStream_t stream) {
+  k_ffma_peak<<<blocks, 256, 0, stream>>>(out, iters, 0.999999f, 1e-7f);
+  return cudaGetLastError();
+}
+
+}  // namespace rtw

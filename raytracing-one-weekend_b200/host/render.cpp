@@ -1,0 +1,140 @@
+// render.cpp -- host side of the drop-in render(): flatten the scene, cross the C ABI, format the PPM.
+// Replaces the body of the reference's render() (render.cpp:135-191).  The three nested loops, ray_color, the BVH and
+// the thread fan-out/sum all run behind rtw_render / rtw_render_multi_gpu; what stays on the host is exactly what the
+// reference does outside its hot loop: image height from the aspect ratio (:137), the effective sample count (:174,185),
+// gamma + quantisation + P3 text (:11-20,182-186) and the timing line (:188-190).
+#include "render.h"
+
+#include <chrono>
+#include <cstdlib>
+#include <iostream>
+#include <stdexcept>
+#include <unordered_map>
+
+namespace rtweekend::detail {
+
+DeviceOptions& device_options() {
+  static DeviceOptions opts = [] {
+    DeviceOptions o;
+    if (const char* e = std::getenv("RTW_GPUS")) o.ngpus = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("RTW_SEED")) o.seed = std::strtoull(e, nullptr, 0);
+    if (const char* e = std::getenv("RTW_KERNEL")) o.kernel = std::atoi(e);
+    if (const char* e = std::getenv("RTW_DEVICE")) o.device = std::atoi(e);
+    if (const char* e = std::getenv("RTW_STATS")) o.stats = std::atoi(e) != 0;
+    return o;
+  }();
+  return opts;
+}
+
+Scene::Flat Scene::flatten() const {
+  Flat f;
+  std::unordered_map<const Material*, int> index;
+  f.mats.reserve(boutique_.size());
+  for (const auto& m : boutique_) {
+    index.emplace(m.get(), static_cast<int>(f.mats.size()));
+    f.mats.push_back(m->flat());
+  }
+  f.prims.reserve(primitives_.size());
+  for (const auto& p : primitives_) {
+    rtw_primitive q = p->flat();
+    auto it = index.find(&p->material());
+    if (it == index.end()) {  // material owned by someone else: append it
+      it = index.emplace(&p->material(), static_cast<int>(f.mats.size())).first;
+      f.mats.push_back(p->material().flat());
+    }
+    q.material = it->second;
+    f.prims.push_back(q);
+  }
+  f.desc.prims = f.prims.data();
+  f.desc.nprims = static_cast<int64_t>(f.prims.size());
+  f.desc.mats = f.mats.data();
+  f.desc.nmats = static_cast<int64_t>(f.mats.size());
+  f.desc.camera = cam_.block();
+  return f;
+}
+
+int image_height(const Config& cfg) { return static_cast<int>(cfg.image_width / cfg.aspect_ratio); }
+
+int effective_spp(const Config& cfg) {
+  if (cfg.nthreads <= 0) throw std::invalid_argument("nthreads must be positive");
+  return cfg.samples_per_pixel / cfg.nthreads * cfg.nthreads;
+}
+
+Accum render_accum(const Scene& world, const Config& cfg) {
+  const DeviceOptions& opt = device_options();
+  Accum img;
+  img.width = cfg.image_width;
+  img.height = image_height(cfg);
+  img.spp = effective_spp(cfg);
+  // The reference divides by zero here (nthreads > spp) and prints a NaN image; refuse instead.
+  if (img.spp <= 0) throw std::invalid_argument("samples_per_pixel / nthreads * nthreads is 0: nothing to render");
+  if (img.width < 2 || img.height < 2) throw std::invalid_argument("image must be at least 2x2");
+
+  const Scene::Flat flat = world.flatten();
+  rtw_render_cfg rc{};
+  rc.width = img.width;
+  rc.height = img.height;
+  rc.sample_begin = 0;
+  rc.sample_end = img.spp;
+  rc.max_child_rays = cfg.max_child_rays;
+  rc.kernel = opt.kernel;
+  rc.seed = opt.seed;
+  rc.device = opt.device;
+  rc.flags = opt.stats ? RTW_FLAG_STATS : 0;
+  img.rgba.assign(static_cast<std::size_t>(img.width) * static_cast<std::size_t>(img.height) * 4, 0.0f);
+  const int status = opt.ngpus > 1 ? rtw_render_multi_gpu(&flat.desc, &rc, opt.ngpus, img.rgba.data(), &img.stats)
+                                   : rtw_render(&flat.desc, &rc, img.rgba.data(), &img.stats);
+  if (status != 0) throw std::runtime_error(std::string("rtw_b200: ") + rtw_last_error());
+  return img;
+}
+
+void write_ppm(std::ostream& out, const Accum& img) {
+  // c = sqrt(sum / spp); int(256 * clamp(c, 0, 0.999)) per channel, "r g b\n" per pixel, top row first
+  std::string text;
+  text.reserve(static_cast<std::size_t>(img.width) * static_cast<std::size_t>(img.height) * 12 + 32);
+  text += "P3\n" + std::to_string(img.width) + ' ' + std::to_string(img.height) + "\n255\n";
+  const std::size_t npix = static_cast<std::size_t>(img.width) * static_cast<std::size_t>(img.height);
+  const double spp = static_cast<double>(img.spp);
+  char buf[4];
+  for (std::size_t k = 0; k < npix; ++k) {
+    for (int ch = 0; ch < 3; ++ch) {
+      const double c = std::sqrt(static_cast<double>(img.rgba[4 * k + ch]) / spp);
+      int v = static_cast<int>(256 * std::clamp(c, 0.0, 0.999));
+      int n = 0;
+      do { buf[n++] = static_cast<char>('0' + v % 10); v /= 10; } while (v > 0);
+      while (n > 0) text += buf[--n];
+      text += ch == 2 ? '\n' : ' ';
+    }
+  }
+  out.write(text.data(), static_cast<std::streamsize>(text.size()));
+}
+
+void render(const Scene& world, const Config& cfg) {
+  namespace khr = std::chrono;
+  const DeviceOptions& opt = device_options();
+  std::cerr << "Started rendering on " << opt.ngpus << " GPU(s)\n";
+  const auto start = khr::steady_clock::now();
+  const Accum img = render_accum(world, cfg);
+  write_ppm(std::cout, img);
+  std::cout.flush();
+  const auto took = khr::duration_cast<khr::milliseconds>(khr::steady_clock::now() - start);
+  const double paths = static_cast<double>(img.stats.paths), rays = static_cast<double>(img.stats.rays);
+  std::cerr << "kernel " << img.stats.kernel_ms << " ms: " << paths / (img.stats.kernel_ms * 1e3) << " Mpaths/s, "
+            << rays / (img.stats.kernel_ms * 1e3) << " Mrays/s (" << rays / std::max(paths, 1.0) << " rays/path)\n";
+  std::cerr << "\nDone in " << took.count() << "ms\n";
+}
+
+std::ostream& operator<<(std::ostream& o, const Config& c) {
+  // same seven lines, same order, as the reference's printer (render.cpp:193-203; `model` is not printed there either)
+  o << "Config {\n";
+  o << "aspect_ratio: " << c.aspect_ratio << "\n";
+  o << "number_of_balls_sqrt: " << c.number_of_balls_sqrt << "\n";
+  o << "moving_spheres: " << c.moving_spheres << "\n";
+  o << "image_width: " << c.image_width << "\n";
+  o << "samples_per_pixel: " << c.samples_per_pixel << "\n";
+  o << "max_child_rays: " << c.max_child_rays << "\n";
+  o << "nthreads: " << c.nthreads << "\n";
+  return o << "}\n";
+}
+
+}  // namespace rtweekend::detail

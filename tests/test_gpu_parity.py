@@ -1,0 +1,376 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI of include/rtw_b200.h, against
+  * the golden fixtures generated from the unmodified reference (tests/golden/),
+  * the CPU oracle (oracle/rtw_oracle.c) on the same seeded inputs,
+  * size-independent properties at BASELINE.json's full sizes (exact sample counts, shard invariance, determinism).
+
+Stated tolerances (the reference computes in double, the kernels in float):
+  primary hits, fp64 mode : primitive id exact, t relative 1e-12, normal absolute 1e-12
+  primary hits, fp32 mode : primitive id exact except knife-edge pixels (other primitive's t within 1e-4 relative),
+                            t relative 1e-5, unit normals absolute 1e-4 (r=0.2 sphere seen from 13 units away in fp32),
+                            triangle normals relative 1e-5
+  same-random-stream image: <1% of pixels may differ by more than 1e-3 in mean radiance (paths that cross an fp32/fp64
+                            knife edge diverge), image mean within 2e-3
+  converged image         : PSNR >= 40 dB in the 8-bit gamma domain, per-channel image mean within 3 sigma of Monte Carlo noise
+"""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+SUZANNE = str(ROOT / "tests" / "golden" / "suzanne.obj")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------------------------
+def check_primary(got, want, fp64, unit_normals=True, max_knife_edge=0):
+    pid, t, nrm, front = got
+    oid, ot, onrm, ofront = want
+    oid = np.asarray(oid).astype(np.int32)
+    mism = pid != oid
+    n_mism = int(mism.sum())
+    if fp64:
+        assert n_mism == 0
+    else:
+        assert n_mism <= max_knife_edge, f"{n_mism} pixels hit a different primitive"
+    same = ~mism & (oid >= 0)
+    rel = np.abs(t[same] - ot[same]) / ot[same]
+    assert rel.max() < (1e-12 if fp64 else 1e-5), rel.max()
+    onrm = np.asarray(onrm, np.float64)
+    if unit_normals:
+        err = np.abs(nrm[same] - onrm[same]).max()
+        assert err < (1e-6 if fp64 else 1e-4), err  # golden normals are stored as float32
+    else:
+        scale = np.linalg.norm(onrm[same], axis=1, keepdims=True)
+        err = (np.abs(nrm[same] - onrm[same]) / scale).max()
+        assert err < 1e-5, err
+    assert np.array_equal(front[same], np.asarray(ofront)[same])
+    # misses agree, and any knife-edge mismatch is between two surfaces at (nearly) the same depth
+    assert np.array_equal(pid < 0, oid < 0) or not fp64
+    if n_mism:
+        both = mism & (pid >= 0) & (oid >= 0)
+        assert (np.abs(t[both] - ot[both]) / ot[both]).max() < 1e-4 if both.any() else True
+    return n_mism
+
+
+def psnr8(a, b):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return 10 * np.log10(255.0 ** 2 / mse)
+
+
+def image_mean_z(mean_a, var_a, n_a, mean_b, var_b, n_b):
+    npix = mean_a.shape[0] * mean_a.shape[1]
+    se = np.sqrt((var_a / n_a + var_b / n_b).sum(axis=(0, 1))) / npix
+    return (mean_a - mean_b).mean(axis=(0, 1)) / se
+
+
+def same_stream_check(rtw, port, scene, osc, W, H, spp, depth, seed, kernel, frac_tol=0.01, **kw):
+    acc, st = rtw.render(scene, W, H, spp, depth, seed=seed, kernel=kernel, **kw)
+    want, _, rays = port.render_philox(osc, W, H, 0, spp, depth, seed=seed, nthreads=8)
+    assert st["paths"] == W * H * spp
+    assert np.all(acc[..., 3] == spp)
+    got = acc[..., :3].astype(np.float64) / spp
+    want = want / spp
+    bad = (np.abs(got - want).max(axis=2) > 1e-3).mean()
+    assert bad < frac_tol, f"{bad:.4f} of pixels differ from the oracle on the same random stream"
+    assert np.abs((got - want).mean(axis=(0, 1))).max() < 2e-3
+    assert abs(st["rays"] - rays) / rays < 5e-3, (st["rays"], rays)
+    return acc, st
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# K3: deterministic primary-ray mode
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,time", [("cover_primary_200x133_t0.npz", 0.0), ("cover_primary_200x133_t0.5.npz", 0.5)])
+@pytest.mark.parametrize("mode", ["fp64", "fp32-spheres", "fp32-bvh"])
+def test_primary_hits_cover_vs_golden(gpu, golden, name, time, mode):
+    g = golden(name)
+    scene = gpu.cover_scene()
+    kernel = {"fp64": gpu.KERNEL_AUTO, "fp32-spheres": gpu.KERNEL_SPHERES_SMEM, "fp32-bvh": gpu.KERNEL_BVH}[mode]
+    got = gpu.primary_hits(scene, 200, 133, time, 64 if mode == "fp64" else 32, kernel)
+    check_primary(got, (g["id"], g["t"], g["normal"], g["front"]), fp64=(mode == "fp64"))
+
+
+@pytest.mark.parametrize("precision", [64, 32])
+def test_primary_hits_suzanne_vs_golden(gpu, golden, precision):
+    g = golden("suzanne_primary_200x133.npz")
+    scene = gpu.obj_scene(SUZANNE)
+    got = gpu.primary_hits(scene, 200, 133, 0.0, precision)
+    check_primary(got, (g["id"], g["t"], g["normal"], g["front"]), fp64=(precision == 64), unit_normals=False, max_knife_edge=2)
+
+
+def test_primary_hits_full_hd_vs_oracle(gpu, oracle_mod, port):
+    """BASELINE config-2 geometry (1920x1080): fp64 mode must equal the oracle exactly, fp32 mode up to knife edges."""
+    aspect = 1.7777777777777777
+    scene = gpu.cover_scene(11, aspect)
+    W, H = 1920, gpu.image_height(1920, aspect)
+    assert H == 1080
+    osc = (oracle_mod.ref() if oracle_mod.ref_available() else port).scene_cover(11, aspect)
+    want = osc.primary_hits(W, H, 0.25)
+    check_primary(gpu.primary_hits(scene, W, H, 0.25, 64), want, fp64=True)
+    for kernel in (gpu.KERNEL_SPHERES_SMEM, gpu.KERNEL_BVH):
+        n = check_primary(gpu.primary_hits(scene, W, H, 0.25, 32, kernel), want, fp64=False, max_knife_edge=8)
+        print("knife-edge pixels at 1080p:", n)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# unit level: scatter routines and samplers
+# ------------------------------------------------------------------------------------------------------------------
+def test_scatter_matches_oracle(gpu, port):
+    rng = np.random.default_rng(5)
+    n = 6000
+    mats = np.zeros(n, gpu.MAT_DTYPE)
+    mats["kind"] = rng.integers(0, 3, n)
+    mats["albedo"] = rng.uniform(0, 1, (n, 3))
+    mats["fuzz"] = rng.uniform(-0.2, 1.3, n)
+    mats["ior"] = rng.choice([1.5, 1.33, 2.4, 1.0 / 1.5], n)
+    normal = rng.normal(size=(n, 3)); normal /= np.linalg.norm(normal, axis=1, keepdims=True)
+    dir_in = rng.normal(size=(n, 3)) * rng.uniform(0.2, 12, (n, 1))
+    flip = (dir_in * normal).sum(axis=1) > 0
+    normal[flip] *= -1  # shading normals always oppose the ray, as the hit routines guarantee
+    front = rng.integers(0, 2, n).astype(np.uint8)
+    ball = np.abs(rng.normal(size=(n, 3))) * 0.3
+    coin = rng.uniform(0, 1, n)
+    dir_in, normal, ball, coin = (x.astype(np.float32) for x in (dir_in, normal, ball, coin))
+    out_dir, out_att, sc = gpu.debug_scatter(mats, dir_in, normal, front, ball, coin)
+    undecided = 0
+    for k in range(n):
+        want = port.scatter(tuple(mats[k]), dir_in[k].astype(np.float64), normal[k].astype(np.float64), front[k], ball[k].astype(np.float64), float(coin[k]))
+        assert (want is not None) == bool(sc[k])
+        d, a = want
+        if not np.allclose(out_dir[k], d, rtol=2e-5, atol=2e-5 * max(1.0, np.linalg.norm(d))):
+            assert mats["kind"][k] == gpu.RTW_DIELECTRIC  # reflect/refract decision on a Schlick knife edge
+            undecided += 1
+        assert np.allclose(out_att[k], a, atol=1e-7)
+    assert undecided <= 3
+
+
+def test_samplers_have_the_reference_distribution(gpu, port):
+    """Direct-inversion samplers vs the reference's rejection loops (random-utils.cpp:23-41) driven by mt19937."""
+    n = 400_000
+    ball, disk, u = gpu.debug_samples(n, seed=3)
+    assert u.min() >= 0 and u.max() < 1 and abs(u.mean() - 0.5) < 2e-3
+    # octant ball: non-negative, inside the unit ball, NOT normalised (Q1); moments of the uniform octant ball
+    assert ball.min() >= 0 and (np.linalg.norm(ball, axis=1) < 1.0 + 1e-6).all()
+    r = np.linalg.norm(ball.astype(np.float64), axis=1)
+    assert abs(r.mean() - 0.75) < 2e-3 and abs((r ** 3).mean() - 0.5) < 3e-3      # r^3 uniform
+    assert np.abs(ball.mean(axis=0) - 0.375).max() < 2e-3                          # E[x] = 3/8 in the octant ball
+    assert np.abs((ball.astype(np.float64) ** 2).mean(axis=0) - 0.2).max() < 2e-3  # E[x^2] = 1/5
+    # against the reference sampler itself: two-sample KS on each coordinate and on the radius
+    from scipy import stats
+    port.seed(123)
+    m = 60_000
+    ref = np.empty((m, 3))
+    k = 0
+    while k < m:
+        v = np.array([port.random_double(), port.random_double(), port.random_double()])
+        if v @ v < 1:
+            ref[k] = v; k += 1
+    for c in range(3):
+        assert stats.ks_2samp(ball[:m, c], ref[:, c]).pvalue > 1e-3
+    assert stats.ks_2samp(r[:m], np.linalg.norm(ref, axis=1)).pvalue > 1e-3
+    # disk: uniform in the unit disk
+    rd = np.linalg.norm(disk.astype(np.float64), axis=1)
+    assert rd.max() < 1 + 1e-6 and abs((rd ** 2).mean() - 0.5) < 2e-3 and np.abs(disk.mean(axis=0)).max() < 3e-3
+    assert stats.kstest(rd ** 2, "uniform").pvalue > 1e-3
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# K1 / K2: the render loop on the oracle's random stream
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel_name,rpl", [("spheres", 4), ("spheres", 2), ("spheres", 1), ("bvh", 0)])
+def test_render_same_stream_cover(gpu, port, kernel_name, rpl):
+    kernel = gpu.KERNEL_SPHERES_SMEM if kernel_name == "spheres" else gpu.KERNEL_BVH
+    scene, osc = gpu.cover_scene(), port.scene_cover()
+    acc, st = same_stream_check(gpu, port, scene, osc, 200, 133, 20, 20, seed=0, kernel=kernel, rays_per_lane=rpl)
+    assert abs(st["rays"] / st["paths"] - 2.30) < 0.02  # SURVEY: 2.30 rays per path at depth 20
+    assert st["kernel_used"] == kernel
+
+
+@pytest.mark.parametrize("depth", [0, 1, 2, 50])
+def test_render_depth_rule(gpu, port, depth):
+    """a path traces up to max_child_rays+1 rays; a hit at depth 0 is black, a miss is still sky."""
+    scene, osc = gpu.cover_scene(11, 1.7777777777777777, False), port.scene_cover(11, 1.7777777777777777, False)
+    acc, st = same_stream_check(gpu, port, scene, osc, 96, 54, 8, depth, seed=depth + 1, kernel=gpu.KERNEL_AUTO)
+    if depth == 0:
+        assert st["rays"] == st["paths"]
+        assert (acc[..., :3].sum(axis=2) == 0).mean() > 0.3  # everything that hits is black
+
+
+def test_render_same_stream_suzanne_and_mixed_scene(gpu, port, oracle_mod):
+    scene, osc = gpu.obj_scene(SUZANNE), port.scene_obj(SUZANNE)
+    same_stream_check(gpu, port, scene, osc, 96, 64, 8, 20, seed=4, kernel=gpu.KERNEL_AUTO, frac_tol=0.02)
+    # triangles + spheres of every material + the r=1000 ground, through the same Scene API the reference exposes
+    ms = gpu.mesh_on_ground_scene(SUZANNE)
+    extra_m = np.zeros(3, gpu.MAT_DTYPE)
+    extra_m["kind"] = [gpu.RTW_METAL, gpu.RTW_DIELECTRIC, gpu.RTW_LAMBERTIAN]
+    extra_m["albedo"] = [[0.8, 0.8, 0.9], [1, 1, 1], [0.2, 0.7, 0.3]]
+    extra_m["fuzz"] = [0.1, 0, 0]
+    extra_m["ior"] = [0, 1.5, 0]
+    extra_p = np.zeros(4, gpu.PRIM_DTYPE)
+    extra_p["kind"] = [gpu.RTW_SPHERE, gpu.RTW_SPHERE, gpu.RTW_SPHERE, gpu.RTW_MOVING_SPHERE]
+    extra_p["material"] = np.array([0, 1, 1, 2]) + len(ms.mats)
+    extra_p["a"] = [[-2.2, 0.6, 0.3], [2.0, 0.5, 1.0], [2.0, 0.5, 1.0], [0.5, 0.3, 2.0]]
+    extra_p["b"] = [[-2.2, 0.6, 0.3], [2.0, 0.5, 1.0], [2.0, 0.5, 1.0], [0.9, 0.5, 2.0]]
+    extra_p["radius"] = [0.6, 0.5, -0.45, 0.3]  # hollow glass sphere: negative inner radius
+    mixed = gpu.Scene(np.concatenate([ms.prims, extra_p]), np.concatenate([ms.mats, extra_m]), ms.camera, ms.params)
+    omats = mixed.mats.view(oracle_mod.MAT_DTYPE)
+    osc = port.scene_custom(mixed.prims, omats, oracle_mod.camera_params(**mixed.params))
+    got = gpu.primary_hits(mixed, 160, 106, 0.3, 64)
+    check_primary(got, osc.primary_hits(160, 106, 0.3), fp64=True, unit_normals=False)
+    same_stream_check(gpu, port, mixed, osc, 120, 80, 8, 20, seed=9, kernel=gpu.KERNEL_AUTO, frac_tol=0.02)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# converged images vs the reference's own render (golden linear-domain statistics)
+# ------------------------------------------------------------------------------------------------------------------
+def converged_check(gpu, golden, name, scene, kernel, spp=4096):
+    g = golden(name)
+    m = g["meta"]
+    W, H = m["width"], m["height"]
+    acc, st = gpu.render(scene, W, H, spp, m["max_child_rays"], seed=2024, kernel=kernel)
+    mean = acc[..., :3].astype(np.float64) / spp
+    ref_mean, ref_var = g["mean"].astype(np.float64), g["var"].astype(np.float64)
+    p = psnr8(gpu.quantize(acc, spp), gpu.quantize(ref_mean, 1))
+    z = image_mean_z(mean, ref_var, spp, ref_mean, ref_var, m["spp"])  # the two renders share the per-pixel variance
+    print(f"{name}: PSNR {p:.2f} dB, image-mean z {z}")
+    assert p >= 40.0, p
+    assert np.abs(z).max() < 3.0, z
+    se = np.sqrt(ref_var / spp + ref_var / m["spp"])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        zp = np.where(se > 0, (mean - ref_mean) / se, 0.0)
+    assert (np.abs(zp) > 5).mean() < 2e-3
+    return p
+
+
+@pytest.mark.parametrize("kernel_name", ["spheres", "bvh"])
+def test_converged_cover_vs_reference(gpu, golden, kernel_name):
+    kernel = gpu.KERNEL_SPHERES_SMEM if kernel_name == "spheres" else gpu.KERNEL_BVH
+    converged_check(gpu, golden, "cover_converged_120x80.npz", gpu.cover_scene(), kernel)
+
+
+def test_converged_static_cover_16x9_depth50_vs_reference(gpu, golden):
+    converged_check(gpu, golden, "cover_static_converged_96x54.npz", gpu.cover_scene(11, 1.7777777777777777, False), gpu.KERNEL_AUTO)
+
+
+def test_converged_suzanne_vs_reference(gpu, golden):
+    converged_check(gpu, golden, "suzanne_converged_96x64.npz", gpu.obj_scene(SUZANNE), gpu.KERNEL_AUTO)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# size-independent properties, edge cases, errors
+# ------------------------------------------------------------------------------------------------------------------
+def test_determinism_and_shard_invariance(gpu):
+    """Integer accumulation makes the image independent of scheduling and of how samples are split (multi-GPU rule)."""
+    import torch
+    scene = gpu.cover_scene()
+    W, H, S = 160, 106, 32
+    ds = gpu.DeviceScene(scene, 0)
+    def run(ranges, **kw):
+        buf = torch.zeros((H, W, 4), dtype=torch.int64, device="cuda:0")
+        for b, e in ranges:
+            ds.render_into(buf, W, H, e - b, 20, sample_begin=b, stream_ptr=torch.cuda.current_stream().cuda_stream, seed=5, **kw)
+        torch.cuda.synchronize()
+        return buf.cpu()
+    full = run([(0, S)])
+    assert torch.equal(full, run([(0, S)]))
+    assert torch.equal(full, run([(0, 8), (8, 16), (16, 24), (24, 32)]))
+    assert torch.equal(full, run([(16, 32), (0, 16)]))
+    assert torch.equal(full, run([(0, S)], rays_per_lane=1))
+    assert torch.equal(full, run([(0, S)], kernel=gpu.KERNEL_SPHERES_SMEM, rays_per_lane=2))
+    assert (full[..., 3] == S).all()
+    other = run([(0, S)], kernel=gpu.KERNEL_BVH)  # a different tracer: same paths except at fp32 ties
+    assert (full[..., :3] != other[..., :3]).any(dim=2).float().mean() < 0.02
+    out = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda:0")
+    ds.accum_to_float(full.cuda(), out, W * H)
+    torch.cuda.synchronize()
+    acc, _ = gpu.render(scene, W, H, S, 20, seed=5)
+    assert np.array_equal(out.cpu().numpy(), acc)
+    ds.close()
+
+
+def test_full_size_properties_1080p(gpu):
+    """BASELINE config 2 geometry at reduced spp: every pixel receives exactly spp paths, radiance is within the
+    convex hull of sky colours, rays per path matches the survey's 2.31-2.38."""
+    aspect = 1.7777777777777777
+    scene = gpu.cover_scene(11, aspect)
+    W, H, spp = 1920, 1080, 8
+    acc, st = gpu.render(scene, W, H, spp, 50, seed=1)
+    assert st["paths"] == W * H * spp and np.all(acc[..., 3] == spp)
+    assert acc[..., :3].min() >= 0 and acc[..., :3].max() <= spp * 1.0 + 1e-3
+    assert 2.25 < st["rays"] / st["paths"] < 2.45
+    top = acc[:40, :, :3].mean(axis=(0, 1)) / spp
+    assert top[2] > top[0]  # sky is bluer at the top rows (row 0 is the top, Q12)
+    rgb = gpu.finalize_rgb8(acc, spp)
+    want = gpu.quantize(acc, spp)
+    d = np.abs(rgb.astype(int) - want.astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3  # float vs double sqrt at integer boundaries
+
+
+def test_edge_cases(gpu, port, oracle_mod):
+    cam = dict(lookfrom=(0, 0, 0), lookat=(0, 0, -1), vup=(0, 1, 0), vfov=60.0, aspect=1.0, aperture=0.0, focus_dist=1.0, t0=0.0, t1=0.0)
+    mats = np.zeros(1, gpu.MAT_DTYPE); mats["albedo"] = 0.5
+    # empty scene: pure sky, one ray per path
+    empty = gpu.custom_scene(np.zeros(0, gpu.PRIM_DTYPE), mats, **cam)
+    acc, st = gpu.render(empty, 2, 2, 4, 5)
+    assert st["rays"] == st["paths"] == 16 and np.all(acc[..., 3] == 4) and np.all(acc[..., :3] > 0)
+    pid, *_ = gpu.primary_hits(empty, 3, 2)
+    assert (pid == -1).all()
+    # a single sphere filling the view at depth 0: black
+    one = np.zeros(1, gpu.PRIM_DTYPE); one["kind"] = gpu.RTW_SPHERE; one["a"] = one["b"] = [0, 0, -2]; one["radius"] = 1.9
+    s1 = gpu.custom_scene(one, mats, **cam)
+    acc, st = gpu.render(s1, 5, 5, 3, 0)
+    assert np.all(acc[2, 2, :3] == 0) and np.all(acc[..., 3] == 3)
+    # only a huge sphere (fp64 path), ragged image size, odd sample range
+    big = np.zeros(1, gpu.PRIM_DTYPE); big["a"] = big["b"] = [0, -1000.5, 0]; big["radius"] = 1000.0
+    sb = gpu.custom_scene(big, mats, **cam)
+    osc = port.scene_custom(sb.prims, sb.mats.view(oracle_mod.MAT_DTYPE), oracle_mod.camera_params(**sb.params))
+    check_primary(gpu.primary_hits(sb, 131, 67, 0.0, 32), osc.primary_hits(131, 67, 0.0), fp64=False)
+    same_stream_check(gpu, port, sb, osc, 131, 67, 5, 20, seed=3, kernel=gpu.KERNEL_AUTO)
+    acc, st = gpu.render(sb, 131, 67, 3, 20, sample_begin=7)
+    assert np.all(acc[..., 3] == 3)
+
+
+def test_errors_are_reported_not_swallowed(gpu):
+    scene = gpu.cover_scene(1)
+    with pytest.raises(gpu.RtwError, match=">= 2"):
+        gpu.render(scene, 1, 10, 4)
+    with pytest.raises(gpu.RtwError, match="sample range"):
+        gpu.render(scene, 8, 8, 0)
+    with pytest.raises(gpu.RtwError, match="device"):
+        gpu.render(scene, 8, 8, 1, device=99)
+    bad = gpu.Scene(scene.prims.copy(), scene.mats.copy(), scene.camera)
+    bad.prims["material"][0] = 10_000
+    with pytest.raises(gpu.RtwError, match="material"):
+        gpu.render(bad, 8, 8, 1)
+    tri = gpu.obj_scene(SUZANNE)
+    with pytest.raises(gpu.RtwError, match="sphere-only"):
+        gpu.render(tri, 8, 8, 1, kernel=gpu.KERNEL_SPHERES_SMEM)
+
+
+def test_host_executable_end_to_end(gpu, golden):
+    """The drop-in: `rtweekend` (C++ host -> C ABI -> CUDA) prints the reference's P3 format; the picture matches the
+    reference's converged render within the noise of its own 20 spp."""
+    r = subprocess.run([str(gpu.EXE_PATH), "-w", "120", "-s", "1024", "-t", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.startswith("P3\n120 80\n255\n") and "Done in" in r.stderr
+    img = gpu.read_ppm(r.stdout)
+    g = golden("cover_converged_120x80.npz")
+    assert psnr8(img, gpu.quantize(g["mean"].astype(np.float64), 1)) >= 38.0
+    # -t 8 with 20 spp renders 16 effective samples (Q10): still a valid image, normalised by 16
+    r = subprocess.run([str(gpu.EXE_PATH), "-t", "8"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("P3\n200 133\n255\n")
+    d = golden("cover_default_t1.npz")
+    assert psnr8(gpu.read_ppm(r.stdout), d["rgb"]) > 22.0  # two independent 16-20 spp renders
+
+
+def test_multi_gpu_in_process(gpu):
+    if gpu.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    scene = gpu.cover_scene()
+    one, _ = gpu.render(scene, 200, 133, 32, 20, seed=8)
+    two, st = gpu.render_multi_gpu(scene, 200, 133, 32, 2, 20, seed=8)
+    assert np.array_equal(one, two) and st["paths"] == 200 * 133 * 32

@@ -1,0 +1,177 @@
+"""CPU-side tests: the C-ABI library loads and exports what include/rtw_b200.h declares, the host C++ model mirrors
+the reference's API and data (scenes, camera, Config printer, PPM writer, OBJ loader, CLI), and nothing falls back to
+a CPU renderer when there is no GPU.  No compute kernels are launched here."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+SUZANNE = str(ROOT / "tests" / "golden" / "suzanne.obj")
+
+
+def test_library_exports_every_declared_symbol(rtw):
+    header = rtw.HEADER_PATH.read_text()
+    declared = set(re.findall(r"RTW_API[^;]*?\b(rtw_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 14
+    L = rtw.lib()
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in rtw_b200.h but not exported by librtw_b200.so"
+    assert declared == set(rtw.ABI), "python binding and header disagree"
+    assert L.rtw_abi_version() == int(re.search(r"#define RTW_ABI_VERSION (\d+)", header).group(1))
+    exported = subprocess.run(["nm", "-D", "--defined-only", str(rtw.LIB_PATH)], capture_output=True, text=True).stdout
+    assert set(re.findall(r" T (rtw_[a-z0-9_]+)", exported)) == declared
+
+
+def test_struct_layouts_match_the_header(rtw, tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "rtw_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+                   "sizeof(rtw_primitive),sizeof(rtw_material),sizeof(rtw_camera),sizeof(rtw_scene_desc),sizeof(rtw_render_cfg),"
+                   "sizeof(rtw_stats),offsetof(rtw_render_cfg,seed),offsetof(rtw_scene_desc,camera));return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.run(["/usr/bin/gcc", "-std=c11", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [C.sizeof(rtw.Primitive), C.sizeof(rtw.Material), C.sizeof(rtw.Camera), C.sizeof(rtw.SceneDesc), C.sizeof(rtw.RenderCfg),
+            C.sizeof(rtw.Stats), rtw.RenderCfg.seed.offset, rtw.SceneDesc.camera.offset]
+    assert got == want
+
+
+def test_no_cpu_fallback(rtw):
+    """Without a CUDA device every compute entry point must fail loudly."""
+    if rtw.device_count() > 0:
+        pytest.skip("a GPU is present")
+    scene = rtw.cover_scene(2)
+    with pytest.raises(rtw.RtwError, match="no CUDA device|cudaGetDeviceCount"):
+        rtw.render(scene, 8, 8, 1)
+    with pytest.raises(rtw.RtwError):
+        rtw.primary_hits(scene, 8, 8)
+    with pytest.raises(rtw.RtwError):
+        rtw.DeviceScene(scene)
+    r = subprocess.run([str(rtw.EXE_PATH), "-w", "16", "-s", "4"], capture_output=True, text=True)
+    assert r.returncode != 0 and "P3" not in r.stdout and "rtw_b200" in r.stderr
+
+
+def test_product_does_not_reference_the_oracle(rtw):
+    """The oracle is test infrastructure: nothing under the package may import, link or execute it."""
+    for path in rtw.PKG_DIR.rglob("*"):
+        if path.suffix in {".py", ".cu", ".cuh", ".h", ".cpp", ".sh"}:
+            text = path.read_text()
+            for needle in ("import oracle", "oracle/", "librtw_oracle", "libref_oracle", "rtwo_", "rtw_oracle"):
+                assert needle not in text, f"{path} mentions {needle}"
+
+
+def test_cover_scene_matches_oracle_scene(rtw, port):
+    for nsqrt, moving in [(11, True), (11, False), (3, True)]:
+        s = rtw.cover_scene(nsqrt, 1.5, moving)
+        pp, pm = port.scene_cover(nsqrt, 1.5, moving).dump()
+        assert len(s.prims) == len(pp) and len(s.mats) == len(pm)
+        for f in ("kind", "material", "a", "b", "radius"):
+            assert np.array_equal(s.prims[f], pp[f]), f
+        for f in ("kind", "albedo", "fuzz", "ior"):
+            assert np.array_equal(s.mats[f], pm[f]), f
+    s = rtw.cover_scene()
+    kinds = s.prims["kind"]
+    assert len(s.prims) == 485 and (kinds == rtw.RTW_MOVING_SPHERE).sum() == 389 and (kinds == rtw.RTW_SPHERE).sum() == 96
+    mk = s.mats["kind"]
+    assert [(mk == k).sum() for k in (0, 1, 2)] == [391, 75, 19]
+
+
+def test_camera_block_matches_oracle(rtw, port):
+    import ctypes
+    for aspect in (1.5, 1.7777777777777777):
+        s = rtw.cover_scene(1, aspect)
+        out = (ctypes.c_double * 21)()
+        osc = port.scene_cover(1, aspect)
+        port.L.rtwo_scene_camera_derived.argtypes = [ctypes.c_void_p, ctypes.c_double * 21]
+        port.L.rtwo_scene_camera_derived(osc.h, out)
+        c = s.camera
+        mine = list(c.origin) + list(c.lower_left) + list(c.horizontal) + list(c.vertical) + list(c.u) + list(c.v) + [c.lens_radius, c.t0, c.t1]
+        assert mine == list(out)
+    c = rtw.make_camera((1, 0, -1), (0, 0, 0), (0, 1, 0), 35.0, 1.5, 0.01, None, 0, 1)
+    assert c.lens_radius == 0.005 and np.isclose(np.linalg.norm(c.horizontal) / np.linalg.norm(c.vertical), 1.5)
+
+
+def test_obj_loader(rtw, port, tmp_path):
+    s = rtw.obj_scene(SUZANNE)
+    pp, _ = port.scene_obj(SUZANNE).dump()
+    assert len(s.prims) == 968 and np.all(s.prims["kind"] == rtw.RTW_TRIANGLE)
+    for f in "abc":
+        assert np.array_equal(s.prims[f], pp[f])
+    assert len(s.mats) == 1 and s.mats["kind"][0] == rtw.RTW_LAMBERTIAN and np.allclose(s.mats["albedo"][0], 0.5)
+    # polygons are fan-triangulated, negative indices are relative, only the first shape is read
+    obj = tmp_path / "quad.obj"
+    obj.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 0.5 0.5 1e0\nf 1 2 3 4\nf -1/1/1 -5//2 -4\ng second\nf 1 2 3\n")
+    q = rtw.obj_scene(str(obj))
+    assert len(q.prims) == 3
+    assert np.array_equal(q.prims["a"][1], [0, 0, 0]) and np.array_equal(q.prims["b"][1], [1, 1, 0]) and np.array_equal(q.prims["c"][1], [0, 1, 0])
+    assert np.array_equal(q.prims["a"][2], [0.5, 0.5, 1.0]) and np.array_equal(q.prims["b"][2], [0, 0, 0])
+    with pytest.raises(rtw.RtwError, match="Can't load because"):
+        rtw.obj_scene(str(tmp_path / "missing.obj"))
+
+
+def test_high_poly_stand_in_generator(rtw, tmp_path):
+    out = tmp_path / "fine.obj"
+    n = C.c_longlong(0)
+    assert rtw.host().rtwh_make_mesh(SUZANNE.encode(), str(out).encode(), 2, 7, 0.08, C.byref(n)) == 0
+    assert n.value == 968 * 16
+    s = rtw.obj_scene(str(out))
+    assert len(s.prims) == 968 * 16
+    out2 = tmp_path / "fine2.obj"
+    rtw.host().rtwh_make_mesh(SUZANNE.encode(), str(out2).encode(), 2, 7, 0.08, None)
+    assert out.read_bytes() == out2.read_bytes()  # deterministic
+
+
+def test_config_printer_and_cli(rtw, oracle_mod):
+    buf = C.create_string_buffer(1024)
+    n = rtw.host().rtwh_config_string(11, 1.5, 200, 20, 1, 20, 4, buf, 1024)
+    want = "Config {\naspect_ratio: 1.5\nnumber_of_balls_sqrt: 11\nmoving_spheres: 1\nimage_width: 200\nsamples_per_pixel: 20\nmax_child_rays: 20\nnthreads: 4\n}\n"
+    assert buf.value.decode() == want and n == len(want)
+    r = subprocess.run([str(rtw.EXE_PATH), "--dry-run"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout == want
+    args = ["--dry-run", "-t", "8", "-w1920", "--samples-per-pixel=1024", "-c", "50", "-a", "1.7777777777777777", "-n", "5", "-m", "-q"]
+    r = subprocess.run([str(rtw.EXE_PATH), *args], capture_output=True, text=True)
+    assert "image_width: 1920\nsamples_per_pixel: 1024\nmax_child_rays: 50\nnthreads: 8" in r.stdout and "aspect_ratio: 1.77778" in r.stdout
+    if oracle_mod.ref_available():
+        q = subprocess.run([str(oracle_mod.REF_EXE), *args], capture_output=True, text=True)
+        assert q.stdout == r.stdout
+    r = subprocess.run([str(rtw.EXE_PATH), "--no-such-flag"], capture_output=True, text=True)
+    assert r.returncode != 0 and "not expected" in r.stderr
+    r = subprocess.run([str(rtw.EXE_PATH), "-w", "abc"], capture_output=True, text=True)
+    assert r.returncode != 0
+
+
+def test_image_geometry_and_effective_spp(rtw):
+    assert rtw.image_height(200, 1.5) == 133
+    assert rtw.image_height(1920, 1.7777777777777777) == 1080
+    assert rtw.image_height(1920, 1.7778) == 1079
+    assert rtw.image_height(3840, 1.7777777777777777) == 2160
+    H = rtw.host()
+    assert H.rtwh_effective_spp(20, 4) == 20 and H.rtwh_effective_spp(20, 8) == 16 and H.rtwh_effective_spp(20, 1) == 20
+    assert H.rtwh_effective_spp(3, 8) == 0 and H.rtwh_effective_spp(3, 0) == -1
+
+
+def test_ppm_writer_matches_write_color(rtw, port, tmp_path):
+    rng = np.random.default_rng(1)
+    W, H, spp = 37, 11, 20
+    acc = np.zeros((H, W, 4), np.float32)
+    acc[..., :3] = rng.uniform(0, 1.2, (H, W, 3)) * spp
+    acc[0, 0, :3] = [0, spp * 0.25, spp * 4.0]
+    acc[..., 3] = spp
+    path = tmp_path / "x.ppm"
+    assert rtw.host().rtwh_write_ppm(acc.ctypes.data_as(C.c_void_p), W, H, spp, str(path).encode()) == 0
+    text = path.read_text()
+    assert text.startswith(f"P3\n{W} {H}\n255\n") and text.count("\n") == 3 + W * H
+    img = rtw.read_ppm(text)
+    want = port.quantize(acc[..., :3].astype(np.float64), spp)
+    assert np.array_equal(img, want)
+    assert img[0, 0].tolist() == [0, 128, 255]
+
+
+def test_sample_shard(rtw):
+    assert rtw.sample_shard(1024, 0, 8) == (0, 128) and rtw.sample_shard(1024, 7, 8) == (896, 1024)
+    assert [rtw.sample_shard(12, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 12)]
+    with pytest.raises(ValueError):
+        rtw.sample_shard(20, 0, 8)
