@@ -229,7 +229,7 @@ int flatten_and_upload(const rtw_scene_desc* desc, int device, rtw_scene* sc) {
   }
   d.cam.lens_radius = (float)c.lens_radius; d.cam.t0 = (float)c.t0; d.cam.t1 = (float)c.t1;
   sc->has_triangles = !triId.empty();
-  sc->smem_bytes = 16 + sA.size() * 32;
+  sc->smem_bytes = 16 + (sA.size() + 1) * 32;
   RTW_CUDA(cudaStreamSynchronize(nullptr));
   return 0;
 }
@@ -275,6 +275,7 @@ int fill_params(const rtw_scene* sc, const rtw_render_cfg* cfg, int mode, unsign
   p->inv_wm1 = 1.0f / static_cast<float>(cfg->width - 1);
   p->inv_hm1 = 1.0f / static_cast<float>(cfg->height - 1);
   p->seed = cfg->seed;
+  p->n_leaf_refs = static_cast<uint32_t>(sc->leafRefs.n);
   (void)mode;
   return 0;
 }
@@ -323,7 +324,7 @@ int rtw_render_device(const rtw_scene* scene, const rtw_render_cfg* cfg, int64_t
   if (int rc = choose_mode(scene, cfg->kernel, &mode)) return rc;
   rtw::RenderParams p{};
   if (int rc = fill_params(scene, cfg, mode, reinterpret_cast<unsigned long long*>(accum_fx), &p)) return rc;
-  const int rpl = (cfg->rays_per_lane == 1 || cfg->rays_per_lane == 2 || cfg->rays_per_lane == 4) ? cfg->rays_per_lane : 4;
+  const int rpl = cfg->rays_per_lane;
   const bool want_stats = (cfg->flags & RTW_FLAG_STATS) != 0;
   RTW_CUDA(cudaMemsetAsync(scene->counters.p, 0, rtw::kCtrCount * sizeof(unsigned long long), stream));
   cudaEvent_t e0 = nullptr, e1 = nullptr;

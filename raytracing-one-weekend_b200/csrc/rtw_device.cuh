@@ -84,6 +84,23 @@ __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
 __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
 template <typename T> __device__ __forceinline__ V3<T> normalize(V3<T> a) { return a * rsqrt_(dot(a, a)); }
 
+// Double-precision reciprocal / reciprocal square root without the software div/sqrt sequences: fp32 seed (MUFU) +
+// two Newton steps in DFMA.  Relative error ~1e-14 for arguments inside the float range, which is all the renderer
+// feeds them (squared lengths and discriminants of scene-scale quantities).
+__device__ __forceinline__ double rcp_nr(double x) {
+  double y = static_cast<double>(__frcp_rn(static_cast<float>(x)));
+  y = y * fma(-x, y, 2.0);
+  y = y * fma(-x, y, 2.0);
+  return y;
+}
+__device__ __forceinline__ double rsqrt_nr(double x) {
+  double y = static_cast<double>(rsqrtf(static_cast<float>(x)));
+  y = y * fma(-0.5 * x, y * y, 1.5);
+  y = y * fma(-0.5 * x, y * y, 1.5);
+  return y;
+}
+__device__ __forceinline__ double sqrt_nr(double x) { return x > 1e-35 ? x * rsqrt_nr(x) : 0.0; }
+
 // ---------------------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11): counter = (pixel, sample, dimension, 0), key = seed.
 //   dimension 0: (pixel jitter x, pixel jitter y, lens radius, lens azimuth)
@@ -241,6 +258,16 @@ constexpr int kHitBig = 0x20000000;
 __device__ __forceinline__ void trace_big_spheres(const DevScene& sc, F3 o, F3 d, float tm, float& best_t, int& best_i) {
   for (int k = 0; k < sc.n_big; ++k) {
     const BigSphere& b = sc.big[k];
+    {
+      // fp32 early out: origin clearly outside (|oc|^2 - r^2 far beyond its fp32 rounding error) and the ray pointing
+      // away from the centre can only miss; everything else takes the exact fp64 test below
+      const float ocx = o.x - static_cast<float>(b.c0[0] + tm * b.dc[0]), ocy = o.y - static_cast<float>(b.c0[1] + tm * b.dc[1]),
+                  ocz = o.z - static_cast<float>(b.c0[2] + tm * b.dc[2]);
+      const float rf = static_cast<float>(b.r);
+      const float q = ocx * ocx + ocy * ocy + ocz * ocz;
+      const float r2 = rf * rf;
+      if (q - r2 > 1e-4f * (q + r2) && ocx * d.x + ocy * d.y + ocz * d.z > 0.0f) continue;
+    }
     const double time = tm;
     const D3 c = mk<double>(b.c0[0] + time * b.dc[0], b.c0[1] + time * b.dc[1], b.c0[2] + time * b.dc[2]);
     const D3 od = mk<double>(o.x, o.y, o.z), dd = mk<double>(d.x, d.y, d.z);
@@ -248,11 +275,11 @@ __device__ __forceinline__ void trace_big_spheres(const DevScene& sc, F3 o, F3 d
     const double a = dot(dd, dd), h = dot(oc, dd), cc = dot(oc, oc) - b.r * b.r;
     const double disc = h * h - a * cc;
     if (disc < 0.0) continue;
-    const double sq = sqrt(disc);
+    const double sq = sqrt_nr(disc), ia = rcp_nr(a);
     const double tmin = static_cast<double>(kTMin), tmax = static_cast<double>(best_t);
-    double root = (-h - sq) / a;
+    double root = (-h - sq) * ia;
     if (root < tmin || root > tmax) {
-      root = (-h + sq) / a;
+      root = (-h + sq) * ia;
       if (root < tmin || root > tmax) continue;
     }
     best_t = static_cast<float>(root);
@@ -263,6 +290,7 @@ __device__ __forceinline__ void trace_big_spheres(const DevScene& sc, F3 o, F3 d
 // Geometry of the accepted hit: point, shading normal (as the reference defines it), front flag, material.
 struct HitGeom {
   F3 p, n;
+  float t;  // refined parameter of the hit
   bool front;
   int material, prim_id;
 };
@@ -274,6 +302,7 @@ __device__ __forceinline__ HitGeom hit_geometry(const DevScene& sc, const float4
     const int i = hit & ~kHitTri;
     const float4 q0 = __ldg(&sc.tri[3 * i]), q1 = __ldg(&sc.tri[3 * i + 1]), q2 = __ldg(&sc.tri[3 * i + 2]);
     g.p = o + d * t;
+    g.t = t;
     g.n = mk<float>(q0.w, q1.w, q2.w);  // un-normalised geometric normal, front_facing always true (Q7)
     g.front = true;
     const int2 id = __ldg(&sc.triId[i]);
@@ -283,24 +312,40 @@ __device__ __forceinline__ HitGeom hit_geometry(const DevScene& sc, const float4
     const double time = tm, td = t;
     const D3 c = mk<double>(b.c0[0] + time * b.dc[0], b.c0[1] + time * b.dc[1], b.c0[2] + time * b.dc[2]);
     const D3 p = mk<double>(o.x + td * d.x, o.y + td * d.y, o.z + td * d.z);
-    const D3 n = normalize(p - c);
+    const D3 pc = p - c;
+    const D3 n = pc * rsqrt_nr(dot(pc, pc));
     const bool front = ((d.x * n.x + d.y * n.y + d.z * n.z) < 0.0) != (b.r < 0.0);
     g.p = mk<float>(static_cast<float>(p.x), static_cast<float>(p.y), static_cast<float>(p.z));
     g.n = front ? mk<float>(static_cast<float>(n.x), static_cast<float>(n.y), static_cast<float>(n.z))
                 : mk<float>(static_cast<float>(-n.x), static_cast<float>(-n.y), static_cast<float>(-n.z));
     g.front = front;
+    g.t = t;
     g.prim_id = b.prim_id; g.material = b.material;
   } else {
+    // Accepted small-sphere hit: re-evaluate the reference formula (common-model.cpp:70-88) once in double from
+    // the fp32 ray and table entries, keeping the root the fp32 sweep selected.  The sweep only has to FIND the
+    // hit; point and normal then carry fp32 rounding of the result instead of fp32 cancellation (|o-c| ~ 13
+    // against r = 0.2 in the cover scene).  ~40 DP operations per bounce against ~5000 FP32 ones for the sweep.
     const float4 A = sphA[hit], B = sphB[hit];
-    const F3 c = mk<float>(fmaf(tm, B.x, A.x), fmaf(tm, B.y, A.y), fmaf(tm, B.z, A.z));
-    const F3 oc = o - c;
-    // p - c = oc + t d, both terms are O(r)-accurate differences; normal = normalize(p - c) (common-model.cpp:86)
-    const F3 pc = mk<float>(fmaf(t, d.x, oc.x), fmaf(t, d.y, oc.y), fmaf(t, d.z, oc.z));
-    F3 n = normalize(pc);
-    const bool front = (dot(d, n) < 0.0f) != (B.w < 0.0f);  // common-model.cpp:88
-    g.p = c + pc;
-    g.n = front ? n : -n;
+    const double time = tm;
+    const D3 c = mk<double>(A.x + time * B.x, A.y + time * B.y, A.z + time * B.z);
+    const D3 od = mk<double>(o.x, o.y, o.z), dd = mk<double>(d.x, d.y, d.z);
+    const D3 oc = od - c;
+    const double rr = B.w;
+    const double a = dot(dd, dd), h = dot(oc, dd), cc = dot(oc, oc) - rr * rr;
+    const double disc = h * h - a * cc;
+    const double sq = sqrt_nr(disc), ia = rcp_nr(a);
+    const double r1 = (-h - sq) * ia, r2 = (-h + sq) * ia;
+    const double td = (fabs(r1 - static_cast<double>(t)) <= fabs(r2 - static_cast<double>(t))) ? r1 : r2;
+    const D3 p = od + dd * td;
+    const D3 pc = p - c;
+    const D3 n = pc * rsqrt_nr(dot(pc, pc));
+    const bool front = (dot(dd, n) < 0.0) != (rr < 0.0);  // common-model.cpp:88
+    g.p = mk<float>(static_cast<float>(p.x), static_cast<float>(p.y), static_cast<float>(p.z));
+    g.n = front ? mk<float>(static_cast<float>(n.x), static_cast<float>(n.y), static_cast<float>(n.z))
+                : mk<float>(static_cast<float>(-n.x), static_cast<float>(-n.y), static_cast<float>(-n.z));
     g.front = front;
+    g.t = static_cast<float>(td);
     const int2 id = __ldg(&sc.sphId[hit]);
     g.prim_id = id.x; g.material = id.y;
   }

@@ -26,6 +26,7 @@ struct RenderParams {
   int32_t max_depth;
   float inv_wm1, inv_hm1;
   uint64_t seed;
+  uint32_t n_leaf_refs;
 };
 
 struct PrimaryParams {

@@ -80,11 +80,15 @@ __device__ __forceinline__ void stage_spheres(const DevScene& sc, float4* sA, fl
 // Reject test per (ray, sphere): with (u, v) an orthonormal basis of the plane perpendicular to the ray,
 // |((c - o).u, (c - o).v)|^2 <= r^2  <=>  the ray's LINE passes within r of the centre.  8 FMA for a static
 // sphere, 11 for a moving one; r2c carries a conservative slack so fp32 rounding can only add candidates.
+// The sweep is branch-free: the sign bit of each test is funnel-shifted into a per-ray candidate mask (one SHF per
+// test); after every kMaskWords x 32 spheres the ~1 candidate per ray goes through the exact root selection.
 // ---------------------------------------------------------------------------------------------------------
 template <int R>
 struct RaySet {
   float ox[R], oy[R], oz[R], dx[R], dy[R], dz[R], tm[R];
 };
+
+constexpr int kMaskWords = 2;  // 64 spheres between candidate flushes
 
 template <int R, bool STATS>
 __device__ __forceinline__ void trace_spheres(const DevScene& sc, const float4* __restrict__ sA, const float4* __restrict__ sB,
@@ -110,53 +114,109 @@ __device__ __forceinline__ void trace_spheres(const DevScene& sc, const float4* 
   }
   const int ns = sc.n_static, nt = sc.n_static + sc.n_moving;
 
-  auto candidate = [&](int i, int r, float cx, float cy, float cz, float rad) {
-    if (STATS) ++n_cand;
-    const float t = sphere_hit_t<float>(mk<float>(ray.ox[r], ray.oy[r], ray.oz[r]), mk<float>(ray.dx[r], ray.dy[r], ray.dz[r]),
-                                        aa[r], ia[r], mk<float>(cx, cy, cz), rad, kTMin, best_t[r]);
-    if (t >= 0.0f) { best_t[r] = t; best_i[r] = i; }
+  uint32_t mm[R][kMaskWords];
+  int word_base[kMaskWords];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int w = 0; w < kMaskWords; ++w) mm[r][w] = 0u;
+
+  // exact test of the flagged spheres of the words gathered so far
+  auto flush = [&](int nwords) {
+    uint32_t any = 0u;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int w = 0; w < kMaskWords; ++w) any |= mm[r][w];
+    if (any != 0u) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int w = 0; w < kMaskWords; ++w) {
+          if (w >= nwords) continue;
+          uint32_t m = mm[r][w];
+          while (m != 0u) {
+            const int b = __clz(m);
+            m &= ~(0x80000000u >> b);
+            const int i = word_base[w] + b;
+            if (STATS) ++n_cand;
+            const float4 A = sA[i], B = sB[i];
+            const float t = sphere_hit_t<float>(mk<float>(ray.ox[r], ray.oy[r], ray.oz[r]), mk<float>(ray.dx[r], ray.dy[r], ray.dz[r]), aa[r],
+                                                ia[r], mk<float>(fmaf(ray.tm[r], B.x, A.x), fmaf(ray.tm[r], B.y, A.y), fmaf(ray.tm[r], B.z, A.z)),
+                                                B.w, kTMin, best_t[r]);
+            if (t >= 0.0f) { best_t[r] = t; best_i[r] = i; }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int w = 0; w < kMaskWords; ++w) mm[r][w] = 0u;
   };
 
-#pragma unroll 2
-  for (int i = 0; i < ns; ++i) {
-    const float4 A = sA[i];
-    float s[R];
-    int any = 0;
+  // one word = up to 32 consecutive table entries; bit 31-j of the word's mask <- sign of the test of entry base+j
+  auto sweep_word = [&](int base, int cnt, bool moving, uint32_t (&m)[R]) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const float pu = fmaf(A.x, ux[r], fmaf(A.y, uy[r], fmaf(A.z, uz[r], -ou[r])));
-      const float pv = fmaf(A.x, vx[r], fmaf(A.y, vy[r], fmaf(A.z, vz[r], -ov[r])));
-      s[r] = fmaf(pu, pu, fmaf(pv, pv, -A.w));
-      any |= __float_as_int(s[r]);
+    for (int r = 0; r < R; ++r) m[r] = 0u;
+    // software pipeline: the next table entry is in flight while the current one is tested (the tables carry one
+    // spare entry so the last prefetch stays in bounds)
+    if (!moving) {
+      float4 A = sA[base];
+#pragma unroll 4
+      for (int j = 0; j < cnt; ++j) {
+        const float4 An = sA[base + j + 1];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float pu = fmaf(A.x, ux[r], fmaf(A.y, uy[r], fmaf(A.z, uz[r], -ou[r])));
+          const float pv = fmaf(A.x, vx[r], fmaf(A.y, vy[r], fmaf(A.z, vz[r], -ov[r])));
+          const float sgn = fmaf(pu, pu, fmaf(pv, pv, -A.w));
+          m[r] = __funnelshift_l(__float_as_uint(sgn), m[r], 1);
+        }
+        A = An;
+      }
+    } else {
+      float4 A = sA[base], B = sB[base];
+#pragma unroll 4
+      for (int j = 0; j < cnt; ++j) {
+        const float4 An = sA[base + j + 1];
+        const float4 Bn = sB[base + j + 1];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float cx = fmaf(ray.tm[r], B.x, A.x), cy = fmaf(ray.tm[r], B.y, A.y), cz = fmaf(ray.tm[r], B.z, A.z);
+          const float pu = fmaf(cx, ux[r], fmaf(cy, uy[r], fmaf(cz, uz[r], -ou[r])));
+          const float pv = fmaf(cx, vx[r], fmaf(cy, vy[r], fmaf(cz, vz[r], -ov[r])));
+          const float sgn = fmaf(pu, pu, fmaf(pv, pv, -A.w));
+          m[r] = __funnelshift_l(__float_as_uint(sgn), m[r], 1);
+        }
+        A = An; B = Bn;
+      }
     }
-    if (any < 0) {
-      const float rad = sB[i].w;
+    if (cnt < 32) {
 #pragma unroll
-      for (int r = 0; r < R; ++r)
-        if (s[r] < 0.0f) candidate(i, r, A.x, A.y, A.z, rad);
+      for (int r = 0; r < R; ++r) m[r] <<= (32 - cnt);
+    }
+  };
+
+  int w = 0;
+#pragma unroll 1
+  for (int seg = 0; seg < 2; ++seg) {
+    const int seg_begin = seg == 0 ? 0 : ns, seg_end = seg == 0 ? ns : nt;
+#pragma unroll 1
+    for (int base = seg_begin; base < seg_end; base += 32) {
+      uint32_t m[R];
+      sweep_word(base, min(32, seg_end - base), seg == 1, m);
+#pragma unroll
+      for (int k = 0; k < kMaskWords; ++k)
+        if (k == w) {
+          word_base[k] = base;
+#pragma unroll
+          for (int r = 0; r < R; ++r) mm[r][k] = m[r];
+        }
+      if (++w == kMaskWords) { flush(kMaskWords); w = 0; }
     }
   }
-#pragma unroll 2
-  for (int i = ns; i < nt; ++i) {
-    const float4 A = sA[i];
-    const float4 B = sB[i];
-    float s[R];
-    int any = 0;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const float cx = fmaf(ray.tm[r], B.x, A.x), cy = fmaf(ray.tm[r], B.y, A.y), cz = fmaf(ray.tm[r], B.z, A.z);
-      const float pu = fmaf(cx, ux[r], fmaf(cy, uy[r], fmaf(cz, uz[r], -ou[r])));
-      const float pv = fmaf(cx, vx[r], fmaf(cy, vy[r], fmaf(cz, vz[r], -ov[r])));
-      s[r] = fmaf(pu, pu, fmaf(pv, pv, -A.w));
-      any |= __float_as_int(s[r]);
-    }
-    if (any < 0) {
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-        if (s[r] < 0.0f)
-          candidate(i, r, fmaf(ray.tm[r], B.x, A.x), fmaf(ray.tm[r], B.y, A.y), fmaf(ray.tm[r], B.z, A.z), B.w);
-    }
-  }
+  if (w > 0) flush(w);
 #pragma unroll
   for (int r = 0; r < R; ++r)
     if (alive[r]) trace_big_spheres(sc, mk<float>(ray.ox[r], ray.oy[r], ray.oz[r]), mk<float>(ray.dx[r], ray.dy[r], ray.dz[r]),
@@ -261,7 +321,7 @@ k_render(const __grid_constant__ RenderParams p) {
   if (MODE == 0) {
     const int n = sc.n_static + sc.n_moving;
     float4* a = reinterpret_cast<float4*>(smem_raw + 16);
-    float4* b = a + n;
+    float4* b = a + n + 1;
     stage_spheres(sc, a, b, reinterpret_cast<uint64_t*>(smem_raw));
     sA = a; sB = b;
   }
@@ -420,6 +480,262 @@ k_render(const __grid_constant__ RenderParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// K2 render kernel: BVH traversal as a resumable per-lane state machine.
+//   A lane is DEAD (needs a path), TRAV (walking the tree; node, stack and closest hit live across outer iterations)
+//   or DONE (traversal finished, waiting to be shaded).  The outer loop alternates
+//     service phase  -- only when at least SERVICE_MIN lanes are DONE/DEAD (or nobody is traversing): big spheres in fp64,
+//                       shade DONE lanes (scatter -> next ray, or terminate), refill DEAD lanes from the warp's pool
+//                       (ballot + popc ranking, units fetched by lane 0 from the global counter);
+//     traversal phase -- STEPS node/leaf steps for every TRAV lane.
+//   A short traversal therefore never waits for the longest one in its warp, which is what held the first version of
+//   this kernel at 15 of 32 active lanes per instruction.  With SMEM the nodes, leaf references, sphere tables and
+//   triangles are staged into shared memory with TMA bulk copies when they fit.
+// ---------------------------------------------------------------------------------------------------------
+struct BvhTables {
+  const float4* nodes;
+  const uint32_t* leafRefs;
+  const float4* sphA;
+  const float4* sphB;
+  const float4* tri;
+};
+
+template <bool SMEM>
+__device__ __forceinline__ float4 ld4(const float4* p, int i) { return SMEM ? p[i] : __ldg(p + i); }
+template <bool SMEM>
+__device__ __forceinline__ uint32_t ld1(const uint32_t* p, int i) { return SMEM ? p[i] : __ldg(p + i); }
+
+template <bool SMEM, bool STATS, int STEPS, int SERVICE_MIN>
+__global__ void __launch_bounds__(kRenderThreads, 3) k_render_bvh(const __grid_constant__ RenderParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const DevScene& sc = p.sc;
+  BvhTables tb{sc.nodes, sc.leafRefs, sc.sphA, sc.sphB, sc.tri};
+  if (SMEM) {
+    // segment sizes (bytes, multiples of 16) in the order nodes, leafRefs, sphA, sphB, tri
+    const uint32_t nspheres = static_cast<uint32_t>(sc.n_static + sc.n_moving);
+    const uint32_t bytes[5] = {static_cast<uint32_t>(sc.n_nodes) * 64u, (static_cast<uint32_t>(p.n_leaf_refs) * 4u + 15u) & ~15u, nspheres * 16u,
+                               nspheres * 16u, static_cast<uint32_t>(sc.n_tri) * 48u};
+    const void* src[5] = {sc.nodes, sc.leafRefs, sc.sphA, sc.sphB, sc.tri};
+    unsigned char* dst[5];
+    unsigned char* cur = smem_raw + 16;
+    for (int k = 0; k < 5; ++k) { dst[k] = cur; cur += bytes[k]; }
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t total = 0;
+      for (int k = 0; k < 5; ++k) total += bytes[k];
+      mbar_expect_tx(bar, total);
+      constexpr uint32_t kChunk = 32768u;
+      for (int k = 0; k < 5; ++k)
+        for (uint32_t off = 0; off < bytes[k]; off += kChunk)
+          tma_bulk_g2s(dst[k] + off, static_cast<const unsigned char*>(src[k]) + off, min(kChunk, bytes[k] - off), bar);
+    }
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, 0)) {
+      if (++spins > (1u << 26)) __trap();
+    }
+    tb.nodes = reinterpret_cast<const float4*>(dst[0]);
+    tb.leafRefs = reinterpret_cast<const uint32_t*>(dst[1]);
+    tb.sphA = reinterpret_cast<const float4*>(dst[2]);
+    tb.sphB = reinterpret_cast<const float4*>(dst[3]);
+    tb.tri = reinterpret_cast<const float4*>(dst[4]);
+  }
+
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint2 key = make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32));
+  enum : int { DEAD = 0, TRAV = 1, DONE = 2 };
+
+  int state = DEAD;
+  F3 o = mk<float>(0.f, 0.f, 0.f), d = mk<float>(0.f, 0.f, 1.f);
+  float tm = 0.f, tr = 0.f, tg = 0.f, tbl = 0.f;
+  uint32_t pix = 0, smp = 0;
+  int depth = 0;
+  // traversal state
+  float idx = 0.f, idy = 0.f, idz = 0.f, odx = 0.f, ody = 0.f, odz = 0.f, qa = 1.f, qia = 1.f, best_t = kInf;
+  int best_i = kMiss, node = kMiss, sp = 0;
+  int stack[kBvhStack];
+
+  uint32_t pool_next = 0, pool_end = 0, grp = 0, s0 = 0;
+  bool exhausted = false;
+  unsigned long long n_rays = 0, n_paths = 0, n_tests = 0, n_nodes = 0, n_tri = 0;
+
+  auto start_traversal = [&]() {
+    qa = dot(d, d); qia = 1.0f / qa;
+    idx = 1.0f / d.x; idy = 1.0f / d.y; idz = 1.0f / d.z;
+    odx = o.x * idx; ody = o.y * idy; odz = o.z * idz;
+    best_t = kInf; best_i = kMiss; sp = 0;
+    node = sc.n_nodes > 0 ? 0 : kMiss;
+    state = node == kMiss ? DONE : TRAV;
+  };
+
+  for (;;) {
+    const uint32_t trav_mask = __ballot_sync(0xffffffffu, state == TRAV);
+    const int n_service = 32 - __popc(trav_mask);
+    if (n_service >= SERVICE_MIN || trav_mask == 0u) {
+      // ---- shade lanes whose traversal finished ------------------------------------------------------------
+      if (state == DONE) {
+        trace_big_spheres(sc, o, d, tm, best_t, best_i);
+        ++n_rays;
+        bool ended = false;
+        if (best_i == kMiss) {
+          const F3 c = sky_color(d);
+          accum_add(p.accum, pix, tr * c.x, tg * c.y, tbl * c.z);
+          ended = true;
+        } else if (depth >= p.max_depth) {
+          ended = true;
+        } else {
+          const HitGeom g = hit_geometry(sc, tb.sphA, tb.sphB, o, d, tm, best_t, best_i);
+          const float4 mA = __ldg(&sc.matA[g.material]);
+          const float2 mB = __ldg(&sc.matB[g.material]);
+          const int kind = __float_as_int(mB.y);
+          const uint4 x = philox4x32_10(make_uint4(pix, smp, 2u + static_cast<uint32_t>(depth), 0u), key);
+          const F3 ball = sample_octant_ball(u01(x.x), u01(x.y), u01(x.z));
+          F3 dn;
+          if (scatter_dir(kind, mA.w, mB.x, d, g.n, g.front, ball, u01(x.w), dn)) {
+            o = g.p; d = dn;
+            if (kind != kDielectric) { tr *= mA.x; tg *= mA.y; tbl *= mA.z; }
+            ++depth;
+            start_traversal();
+          } else {
+            ended = true;
+          }
+        }
+        if (ended) {
+          ++n_paths;
+          atomicAdd(p.accum + 4ull * pix + 3, 1ull);
+          state = DEAD;
+        }
+      }
+      // ---- refill dead lanes from the warp's pool ------------------------------------------------------------------
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        const uint32_t need = __ballot_sync(0xffffffffu, state == DEAD);
+        if (need == 0u) break;
+        if (pool_next == pool_end) {
+          if (exhausted) break;
+          unsigned long long u = 0;
+          if (lane == 0) u = atomicAdd(p.counters + kCtrWork, 1ull);
+          u = __shfl_sync(0xffffffffu, u, 0);
+          if (u >= p.n_units) { exhausted = true; break; }
+          grp = static_cast<uint32_t>(u / p.n_chunks);
+          const uint32_t chunk = static_cast<uint32_t>(u - static_cast<unsigned long long>(grp) * p.n_chunks);
+          s0 = p.s_begin + chunk * p.su;
+          const uint32_t ns = min(p.su, p.s_end - s0);
+          pool_next = 0; pool_end = ns * kGroupPixels;
+        }
+        const uint32_t avail = pool_end - pool_next;
+        const uint32_t rank = __popc(need & lt);
+        if (state == DEAD && rank < avail) {
+          const uint32_t within = pool_next + rank;
+          const uint32_t px = grp * kGroupPixels + (within & (kGroupPixels - 1u));
+          const uint32_t sm = s0 + within / kGroupPixels;
+          if (px < p.npix) {
+            const uint4 x0 = philox4x32_10(make_uint4(px, sm, 0u, 0u), key);
+            const uint4 x1 = philox4x32_10(make_uint4(px, sm, 1u, 0u), key);
+            const uint32_t i = px / p.width, j = px - i * p.width;
+            const float u = (static_cast<float>(j) + u01(x0.x)) * p.inv_wm1;
+            const float v = (static_cast<float>(p.height - 1u - i) + u01(x0.y)) * p.inv_hm1;
+            const float2 dk = sample_disk(u01(x0.z), u01(x0.w));
+            camera_ray<float>(sc.cam, u, v, dk.x, dk.y, o, d);
+            tm = fmaf(u01(x1.x), sc.cam.t1 - sc.cam.t0, sc.cam.t0);
+            tr = tg = tbl = 1.0f;
+            pix = px; smp = sm; depth = 0;
+            start_traversal();
+          }
+        }
+        pool_next += min(static_cast<uint32_t>(__popc(need)), avail);
+      }
+      if (!__any_sync(0xffffffffu, state != DEAD)) {
+        if (exhausted) break;
+        continue;
+      }
+    }
+
+    // ---- traversal phase: STEPS node-or-leaf steps per traversing lane ------------------------------------------------
+#pragma unroll 1
+    for (int step = 0; step < STEPS; ++step) {
+      if (state != TRAV) continue;
+      if (node < 0) {  // leaf
+        const uint32_t v = static_cast<uint32_t>(~node);
+        const uint32_t first = v >> 5, cnt = v & 31u;
+        for (uint32_t k = 0; k < cnt; ++k) {
+          const uint32_t ref = ld1<SMEM>(tb.leafRefs, static_cast<int>(first + k));
+          const int i = static_cast<int>(ref & 0x3fffffffu);
+          if (ref >> 30) {
+            if (STATS) ++n_tri;
+            const float4 q0 = ld4<SMEM>(tb.tri, 3 * i), q1 = ld4<SMEM>(tb.tri, 3 * i + 1), q2 = ld4<SMEM>(tb.tri, 3 * i + 2);
+            const float t = triangle_hit<float>(o, d, mk<float>(q0.x, q0.y, q0.z), mk<float>(q1.x, q1.y, q1.z), mk<float>(q2.x, q2.y, q2.z),
+                                                mk<float>(q0.w, q1.w, q2.w), kTMin, best_t);
+            if (t >= 0.0f) { best_t = t; best_i = kHitTri | i; }
+          } else {
+            if (STATS) ++n_tests;
+            const float4 A = ld4<SMEM>(tb.sphA, i), B = ld4<SMEM>(tb.sphB, i);
+            const float t = sphere_hit_t<float>(o, d, qa, qia, mk<float>(fmaf(tm, B.x, A.x), fmaf(tm, B.y, A.y), fmaf(tm, B.z, A.z)), B.w, kTMin,
+                                                best_t);
+            if (t >= 0.0f) { best_t = t; best_i = i; }
+          }
+        }
+        if (sp > 0) node = stack[--sp];
+        else { node = kMiss; state = DONE; }
+      } else {
+        if (STATS) ++n_nodes;
+        const float4 q0 = ld4<SMEM>(tb.nodes, 4 * node), q1 = ld4<SMEM>(tb.nodes, 4 * node + 1), q2 = ld4<SMEM>(tb.nodes, 4 * node + 2),
+                     q3 = ld4<SMEM>(tb.nodes, 4 * node + 3);
+        float t0x = fmaf(q0.x, idx, -odx), t1x = fmaf(q0.w, idx, -odx);
+        float t0y = fmaf(q0.y, idy, -ody), t1y = fmaf(q1.x, idy, -ody);
+        float t0z = fmaf(q0.z, idz, -odz), t1z = fmaf(q1.y, idz, -odz);
+        const float ln = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), kTMin));
+        const float lf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best_t));
+        t0x = fmaf(q1.z, idx, -odx); t1x = fmaf(q2.y, idx, -odx);
+        t0y = fmaf(q1.w, idy, -ody); t1y = fmaf(q2.z, idy, -ody);
+        t0z = fmaf(q2.x, idz, -odz); t1z = fmaf(q2.w, idz, -odz);
+        const float rn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), kTMin));
+        const float rf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best_t));
+        const bool hl = ln <= lf, hr = rn <= rf;
+        const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
+        if (hl && hr) {
+          const bool lfirst = ln <= rn;
+          node = lfirst ? left : right;
+          if (sp < kBvhStack) stack[sp++] = lfirst ? right : left;
+        } else if (hl) {
+          node = left;
+        } else if (hr) {
+          node = right;
+        } else if (sp > 0) {
+          node = stack[--sp];
+        } else {
+          node = kMiss; state = DONE;
+        }
+      }
+    }
+  }
+
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    n_rays += __shfl_xor_sync(0xffffffffu, n_rays, off);
+    n_paths += __shfl_xor_sync(0xffffffffu, n_paths, off);
+    if (STATS) {
+      n_tests += __shfl_xor_sync(0xffffffffu, n_tests, off);
+      n_nodes += __shfl_xor_sync(0xffffffffu, n_nodes, off);
+      n_tri += __shfl_xor_sync(0xffffffffu, n_tri, off);
+    }
+  }
+  if (lane == 0) {
+    atomicAdd(p.counters + kCtrRays, n_rays);
+    atomicAdd(p.counters + kCtrPaths, n_paths);
+    if (STATS) {
+      atomicAdd(p.counters + kCtrSphereTests, n_tests);
+      atomicAdd(p.counters + kCtrNodes, n_nodes);
+      atomicAdd(p.counters + kCtrTriTests, n_tri);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // K3: deterministic primary hits
 // ---------------------------------------------------------------------------------------------------------
 template <int MODE>
@@ -431,7 +747,7 @@ __global__ void __launch_bounds__(kRenderThreads) k_primary_f32(const __grid_con
   if (MODE == 0) {
     const int n = sc.n_static + sc.n_moving;
     float4* a = reinterpret_cast<float4*>(smem_raw + 16);
-    float4* b = a + n;
+    float4* b = a + n + 1;
     stage_spheres(sc, a, b, reinterpret_cast<uint64_t*>(smem_raw));
     sA = a; sB = b;
   }
@@ -462,7 +778,7 @@ __global__ void __launch_bounds__(kRenderThreads) k_primary_f32(const __grid_con
     p.prim_id[px] = -1; p.t[px] = 0.0; p.normal[3 * px] = p.normal[3 * px + 1] = p.normal[3 * px + 2] = 0.0; p.front[px] = 0;
   } else {
     const HitGeom g = hit_geometry(sc, sA, sB, o, d, tm, best_t, best_i);
-    p.prim_id[px] = g.prim_id; p.t[px] = best_t;
+    p.prim_id[px] = g.prim_id; p.t[px] = g.t;
     p.normal[3 * px] = g.n.x; p.normal[3 * px + 1] = g.n.y; p.normal[3 * px + 2] = g.n.z;
     p.front[px] = g.front ? 1 : 0;
   }
@@ -600,22 +916,63 @@ static cudaError_t launch_render_t(const RenderParams& p, int sm_count, size_t s
   return cudaGetLastError();
 }
 
+template <bool SMEM, bool STATS, int STEPS, int SERVICE_MIN>
+static cudaError_t launch_bvh_t(const RenderParams& p, int sm_count, size_t smem, cudaStream_t stream) {
+  auto kern = k_render_bvh<SMEM, STATS, STEPS, SERVICE_MIN>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRenderThreads, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  unsigned long long want = (p.n_units + (kRenderThreads / 32) - 1) / (kRenderThreads / 32);
+  unsigned long long blocks = static_cast<unsigned long long>(sm_count) * per_sm;
+  if (want < blocks) blocks = want < 1 ? 1 : want;
+  kern<<<static_cast<unsigned>(blocks), kRenderThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// bytes of shared memory the BVH kernel needs to stage the whole scene (0 = does not fit, use global memory)
+size_t bvh_smem_bytes(const RenderParams& p) {
+  const size_t nspheres = static_cast<size_t>(p.sc.n_static + p.sc.n_moving);
+  const size_t bytes = 16 + static_cast<size_t>(p.sc.n_nodes) * 64 + ((static_cast<size_t>(p.n_leaf_refs) * 4 + 15) & ~size_t(15)) + nspheres * 32 +
+                       static_cast<size_t>(p.sc.n_tri) * 48;
+  return bytes <= 72 * 1024 ? bytes : 0;
+}
+
 cudaError_t launch_render(const RenderParams& p, int mode, int rays_per_lane, bool stats, int sm_count, cudaStream_t stream) {
-  const size_t smem = mode == 0 ? 16 + static_cast<size_t>(p.sc.n_static + p.sc.n_moving) * 32 : 0;
+  const size_t smem = mode == 0 ? 16 + static_cast<size_t>(p.sc.n_static + p.sc.n_moving + 1) * 32 : 0;
 #define RTW_LAUNCH(R, M)                                                                      \
   return stats ? launch_render_t<R, M, true>(p, sm_count, smem, stream, nullptr)               \
                : launch_render_t<R, M, false>(p, sm_count, smem, stream, nullptr)
   if (mode == 0) {
     if (rays_per_lane == 1) { RTW_LAUNCH(1, 0); }
-    if (rays_per_lane == 2) { RTW_LAUNCH(2, 0); }
-    RTW_LAUNCH(4, 0);
+    if (rays_per_lane == 4) { RTW_LAUNCH(4, 0); }
+    RTW_LAUNCH(2, 0);
   }
-  RTW_LAUNCH(1, 1);
 #undef RTW_LAUNCH
+  // BVH kernel.  rays_per_lane selects tuning variants: 0 default, 100 = first (non-resumable) version,
+  // 1xy = resumable with STEPS/SERVICE_MIN variants, +1000 = force global memory tables
+  const int variant = rays_per_lane % 1000;
+  const size_t bsm = rays_per_lane >= 1000 ? 0 : bvh_smem_bytes(p);
+  if (variant == 100) return stats ? launch_render_t<1, 1, true>(p, sm_count, 0, stream, nullptr) : launch_render_t<1, 1, false>(p, sm_count, 0, stream, nullptr);
+#define RTW_BVH(ST, SV)                                                                                             \
+  return bsm ? (stats ? launch_bvh_t<true, true, ST, SV>(p, sm_count, bsm, stream) : launch_bvh_t<true, false, ST, SV>(p, sm_count, bsm, stream)) \
+             : (stats ? launch_bvh_t<false, true, ST, SV>(p, sm_count, 0, stream) : launch_bvh_t<false, false, ST, SV>(p, sm_count, 0, stream))
+  if (variant == 101) { RTW_BVH(4, 8); }
+  if (variant == 102) { RTW_BVH(4, 16); }
+  if (variant == 103) { RTW_BVH(8, 8); }
+  if (variant == 104) { RTW_BVH(8, 16); }
+  if (variant == 105) { RTW_BVH(2, 8); }
+  if (variant == 106) { RTW_BVH(4, 4); }
+  if (variant == 107) { RTW_BVH(16, 16); }
+  if (variant == 108) { RTW_BVH(8, 24); }
+  RTW_BVH(4, 8);
+#undef RTW_BVH
 }
 
 cudaError_t launch_primary_f32(const PrimaryParams& p, int mode, cudaStream_t stream) {
-  const size_t smem = mode == 0 ? 16 + static_cast<size_t>(p.sc.n_static + p.sc.n_moving) * 32 : 0;
+  const size_t smem = mode == 0 ? 16 + static_cast<size_t>(p.sc.n_static + p.sc.n_moving + 1) * 32 : 0;
   const unsigned blocks = (p.npix + kRenderThreads - 1) / kRenderThreads;
   if (mode == 0) {
     cudaError_t e = cudaFuncSetAttribute(k_primary_f32<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
