@@ -179,6 +179,7 @@ def main() -> int:
     height = rtw.image_height(width, aspect)
     kernel = {"auto": rtw.KERNEL_AUTO, "spheres": rtw.KERNEL_SPHERES_SMEM, "bvh": rtw.KERNEL_BVH}[args.kernel]
     scene = rtw.cover_scene(nsqrt, aspect, moving)
+    scene_has_triangles = bool((scene.prims["kind"] == rtw.RTW_TRIANGLE).any())
     s_begin, s_end = rtw.sample_shard(spp, rank, world)
     ds = rtw.DeviceScene(scene, local_rank)
     npix = width * height
@@ -289,7 +290,10 @@ def main() -> int:
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (k_render) ---------------------------------------------------------------
+    # ---- roofline of the dominant kernel --------------------------------------------------------------------------------
+    # Neither HBM nor tensor cores bound this path (scene tables live in shared memory, HBM traffic is the 66 MB
+    # accumulation buffer): SURVEY 8(d) names the FP32 FMA pipe.  Algorithmic flops use SURVEY's canonical per-test costs
+    # (FMA = 2) times the tests the kernel actually performs, counted by an instrumented pass of the same kernel.
     kinds = scene.prims["kind"]
     radius = np.abs(scene.prims["radius"])
     n_moving = int(((kinds == rtw.RTW_MOVING_SPHERE) & (radius < 100)).sum())
@@ -297,20 +301,53 @@ def main() -> int:
     n_big = int((radius >= 100).sum())
     rays_gpu = rays_total / world  # per launch (per GPU)
     paths_gpu = paths_total / world
-    roofline = None
+    peak_tflops, _ = rtw.fp32_peak(local_rank, 1.0)
+    peak_note = "FFMA micro-benchmark (rtw_fp32_peak) measured in this run; MEASURED_PEAKS.json carries no FP32 figure; nominal %.1f" % NOMINAL_FP32_TFLOPS
+    moving_frac = n_moving / max(n_moving + n_static, 1)
+    test_flop = FLOP_MOVING_TEST * moving_frac + FLOP_STATIC_TEST * (1 - moving_frac)
+
+    def sweep_roofline(ms, rays, paths, label):
+        flop = rays * ((n_static + n_big) * FLOP_STATIC_TEST + n_moving * FLOP_MOVING_TEST + FLOP_SHADE) + (rays - paths) * FLOP_HIT
+        ach = flop / (ms * 1e-3) / 1e12
+        return {"bound": "fp32_fma", "kernel": label, "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
+                "traffic": args.traffic_bytes, "peak_source": peak_note, "algorithmic_flop_per_launch": flop, "kernel_ms": ms,
+                "flop_model": f"rays x (({n_static}+{n_big}) static x 17 + {n_moving} moving x 23 + 80) + hits x 40 (SURVEY 8(d))"}
+
     if kernel_used == rtw.KERNEL_SPHERES_SMEM:
-        flop = rays_gpu * ((n_static + n_big) * FLOP_STATIC_TEST + n_moving * FLOP_MOVING_TEST + FLOP_SHADE) + (rays_gpu - paths_gpu) * FLOP_HIT
-        peak_tflops, implied_mhz = rtw.fp32_peak(local_rank, 1.0)
-        achieved = flop / (kernel_ms * 1e-3) / 1e12
-        roofline = {"bound": "fp32_fma", "kernel": "k_render<R,0> (K1 sphere sweep)", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                    "frac": achieved / peak_tflops, "traffic": args.traffic_bytes,
-                    "peak_source": "FFMA micro-benchmark (rtw_fp32_peak) measured in this run; MEASURED_PEAKS.json has no FP32 figure; nominal %.1f" % NOMINAL_FP32_TFLOPS,
-                    "algorithmic_flop_per_launch": flop, "kernel_ms": kernel_ms,
-                    "flop_model": f"rays x ({n_static}+{n_big} static x 17 + {n_moving} moving x 23 + 80) + hits x 40 (SURVEY 8(d))",
-                    "note": "no tensor cores and ~no HBM traffic on this path: the bounding unit is the FP32 FMA pipe (SURVEY 8(d))"}
+        roofline = sweep_roofline(kernel_ms, rays_gpu, paths_gpu, "k_render<2,0> (K1 shared-memory sphere sweep)")
     else:
-        roofline = {"bound": "latency", "kernel": "k_render<1,1> (K2 BVH)", "achieved": None, "peak": None, "unit": "GB/s", "frac": None,
-                    "traffic": args.traffic_bytes, "kernel_ms": kernel_ms}
+        # per-ray work of the BVH kernel from an instrumented low-spp pass (the averages do not depend on spp)
+        cs = min(8, s_end - s_begin)
+        accum.zero_()
+        sst = ds.render_into(accum, width, height, cs, depth, sample_begin=s_begin, stream_ptr=stream.cuda_stream, seed=0, kernel=kernel,
+                             rays_per_lane=args.rays_per_lane, want_stats=True, stats=True)
+        nodes_pr, tests_pr, tris_pr = sst["node_visits"] / sst["rays"], sst["sphere_tests"] / sst["rays"], sst["tri_tests"] / sst["rays"]
+        flop = rays_gpu * (nodes_pr * 24.0 + tests_pr * test_flop + tris_pr * 36.0 + n_big * FLOP_STATIC_TEST + FLOP_SHADE) + (rays_gpu - paths_gpu) * FLOP_HIT
+        ach = flop / (kernel_ms * 1e-3) / 1e12
+        roofline = {"bound": "fp32_fma", "kernel": "k_render_bvh (K2 resumable BVH traversal, tables in shared memory)", "achieved": ach,
+                    "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops, "traffic": args.traffic_bytes, "peak_source": peak_note,
+                    "algorithmic_flop_per_launch": flop, "kernel_ms": kernel_ms,
+                    "per_ray": {"node_visits": nodes_pr, "sphere_tests": tests_pr, "triangle_tests": tris_pr},
+                    "flop_model": "rays x (nodes x 2 boxes x 12 + sphere tests x 17|23 + triangle tests x 36 + big spheres x 17 + 80) + hits x 40 (SURVEY 8(d))",
+                    "note": "culling removes ~97% of the sweep's flops, so the flop fraction is low by construction; what limits this kernel is "
+                            "instruction issue under divergence (profiles/: ~74% issue-active, ~19 of 32 lanes per instruction)"}
+    # the SURVEY's FP32-roofline target is defined on the brute-force sweep: measure that kernel too (reduced spp, same scene)
+    roofline_sweep = None
+    if world == 1 and kernel_used != rtw.KERNEL_SPHERES_SMEM and not scene_has_triangles:
+        k1_spp = min(128, spp)
+        evs = []
+        for it in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            accum.zero_()
+            a.record(stream)
+            ds.render_into(accum, width, height, k1_spp, depth, sample_begin=0, stream_ptr=stream.cuda_stream, seed=0, kernel=rtw.KERNEL_SPHERES_SMEM)
+            b.record(stream)
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        k1_ms = min(a.elapsed_time(b) for a, b in evs[1:])
+        frac_spp = k1_spp / spp
+        roofline_sweep = sweep_roofline(k1_ms, rays_gpu * frac_spp, paths_gpu * frac_spp, f"k_render<2,0> (K1 shared-memory sphere sweep), {k1_spp} spp")
+        roofline_sweep["mpaths_per_s"] = paths_gpu * frac_spp / (k1_ms * 1e-3) / 1e6
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -321,10 +358,11 @@ def main() -> int:
         "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "width": width, "height": height, "spp": spp, "max_child_rays": depth, "primitives": int(len(scene.prims)),
-                   "parallelism": f"spp-shard x{world}, one int64 NCCL reduce", "kernel": "spheres_smem" if kernel_used == rtw.KERNEL_SPHERES_SMEM else "bvh",
+                   "parallelism": f"spp-shard x{world}, one int64 NCCL reduce", "kernel": "spheres_smem (K1)" if kernel_used == rtw.KERNEL_SPHERES_SMEM else "bvh (K2)",
                    "l2": "256 MB buffer written between timed iterations (scene tables live in shared memory; accumulation buffer 66 MB)"},
         "mrays_per_s": rays_total / (ms_per_step * 1e-3) / 1e6, "rays_per_path": rays_total / paths_total,
-        "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks, "roofline": roofline, "roofline_sphere_sweep": roofline_sweep,
+        "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))
     if world > 1:

@@ -234,16 +234,20 @@ int flatten_and_upload(const rtw_scene_desc* desc, int device, rtw_scene* sc) {
   return 0;
 }
 
-// which kernel a scene gets: the shared-memory sphere sweep needs a pure sphere scene that fits in smem
+// Which kernel a scene gets.  The shared-memory sphere sweep (K1) needs a sphere-only scene whose tables fit in shared
+// memory; it is the faster kernel only for small tables (its cost is linear in the sphere count, the BVH's is
+// logarithmic: measured crossover well below the cover scene's 484 spheres), so AUTO picks it up to kSweepAutoMax.
+constexpr size_t kSweepAutoMax = 64;
 int choose_mode(const rtw_scene* sc, int requested, int* mode) {
   const bool smem_ok = !sc->has_triangles && sc->smem_bytes <= 100 * 1024;
+  const size_t nspheres = static_cast<size_t>(sc->dev.n_static + sc->dev.n_moving);
   if (requested == RTW_KERNEL_SPHERES_SMEM) {
     if (!smem_ok) return fail("RTW_KERNEL_SPHERES_SMEM needs a sphere-only scene whose tables fit in shared memory");
     *mode = 0;
   } else if (requested == RTW_KERNEL_BVH) {
     *mode = 1;
   } else if (requested == RTW_KERNEL_AUTO) {
-    *mode = smem_ok ? 0 : 1;
+    *mode = (smem_ok && nspheres <= kSweepAutoMax) ? 0 : 1;
   } else {
     return fail("unknown kernel selector");
   }

@@ -81,6 +81,9 @@ template <typename T> __host__ __device__ __forceinline__ V3<T> cross(V3<T> a, V
 __device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
 __device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }
 __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+// single-MUFU approximations (<= 2 ulp) for the traversal: box slabs are padded and accepted hits are re-evaluated in fp64
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
 template <typename T> __device__ __forceinline__ V3<T> normalize(V3<T> a) { return a * rsqrt_(dot(a, a)); }
 
@@ -177,6 +180,23 @@ __device__ __forceinline__ T sphere_hit_t(V3<T> o, V3<T> d, T a, T inv_a, V3<T> 
   if (root < tmin || root > tmax) {
     root = (-h + sq) * inv_a;
     if (root < tmin || root > tmax) return T(-1);
+  }
+  return root;
+}
+
+// Same test with the approximate square root, for traversal kernels that refine the accepted hit afterwards.
+__device__ __forceinline__ float sphere_hit_fast(F3 o, F3 d, float a, float inv_a, F3 c, float r, float tmin, float tmax) {
+  const F3 oc = o - c;
+  const float h = dot(oc, d);
+  const float k = h * inv_a;
+  const F3 l = mk<float>(fmaf(-k, d.x, oc.x), fmaf(-k, d.y, oc.y), fmaf(-k, d.z, oc.z));
+  const float disc = fmaf(r, r, -dot(l, l));
+  if (!(disc >= 0.0f)) return -1.0f;
+  const float sq = fast_sqrt(a * disc);
+  float root = (-h - sq) * inv_a;
+  if (root < tmin || root > tmax) {
+    root = (-h + sq) * inv_a;
+    if (root < tmin || root > tmax) return -1.0f;
   }
   return root;
 }
