@@ -32,7 +32,28 @@ WORKLOADS = {
     "cover_1080p_1024spp_depth50": (1920, 1.7777777777777777, 1024, 50, 11, True),   # BASELINE.json configs[1]
     "cover_default_200x133_20spp_depth20": (200, 1.5, 20, 20, 11, True),            # configs[0]
     "cover_4k_4096spp_depth50": (3840, 1.7777777777777777, 4096, 50, 11, True),     # configs[4]
-}
+    # mesh workloads: (width, aspect, spp, max_child_rays, subdivision rounds of suzanne.obj, -)
+    "suzanne_on_ground_1080p_256spp": (1920, 1.7777777777777777, 256, 20, 0, None),  # configs[2]
+    "dragon_standin_1080p_256spp": (1920, 1.7777777777777777, 256, 20, 5, None),     # configs[3]: dragon.obj is missing from the
+}                                                                                    # reference mount; 968*4^5 = 991,232-triangle stand-in
+SUZANNE = ROOT / "tests" / "golden" / "suzanne.obj"
+
+
+def build_scene(rtw, name, wl):
+    """The product's own scene builders (host C++): cover scene, or a mesh standing on the r=1000 ground sphere."""
+    width, aspect, spp, depth, a, b = wl
+    if name.startswith("cover"):
+        return rtw.cover_scene(a, aspect, b)
+    path = str(SUZANNE)
+    if a > 0:
+        import ctypes as C
+        import tempfile
+        path = os.path.join(tempfile.gettempdir(), f"rtw_standin_r{a}.obj")
+        if not os.path.exists(path):
+            n = C.c_longlong(0)
+            if rtw.host().rtwh_make_mesh(str(SUZANNE).encode(), path.encode(), a, 20221018, 0.08, C.byref(n)) != 0:
+                raise RuntimeError(rtw.host().rtwh_last_error().decode())
+    return rtw.mesh_on_ground_scene(path, aspect)
 # canonical FP32 flop costs of SURVEY.md 8(d) (FMA = 2)
 FLOP_STATIC_TEST, FLOP_MOVING_TEST, FLOP_HIT, FLOP_SHADE = 17.0, 23.0, 40.0, 80.0
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
@@ -115,11 +136,40 @@ def cpu_reference_run(width: int, aspect: float, spp_per_thread: int, depth: int
             "sample": f"cover scene {width}x{height}, {spp_per_thread} spp, depth {depth}, oracle port (brute-force closest hit), rows split over {threads} threads"}
 
 
+def cpu_reference_mesh(scene, aspect, depth) -> dict:
+    """Mesh workloads: the reference has no mesh-on-ground scene builder, so its hit/scatter/BVH code (oracle/_ref, or the
+    port) is driven through its public Scene API on a bounded sample, one thread (its render() would share one racy RNG)."""
+    import oracle
+    o = oracle.ref() if oracle.ref_available() else oracle.port()
+    osc = o.scene_custom(scene.prims, scene.mats.view(oracle.MAT_DTYPE), oracle.camera_params(**scene.params))
+    w, h = 160, int(160 / aspect)
+    times = []
+    for q in (1, 3):  # two sample counts: the difference isolates the per-path rate from the (one-off) BVH build
+        t0 = time.perf_counter()
+        osc.render_linear(w, h, q, depth, seed=1, want_sumsq=True)
+        times.append(time.perf_counter() - t0)
+    per_path = max(times[1] - times[0], 1e-9) / (w * h * 2)
+    build = max(times[0] - per_path * w * h, 0.0)
+    return {"value": 1.0 / per_path / 1e6, "unit": "Mpaths/s", "cores": 1, "kind": "reference" if oracle.ref_available() else "port",
+            "seconds": sum(times), "bvh_build_seconds": build,
+            "sample": f"same scene through the reference Scene API, {w}x{h}, 1 and 3 spp, depth {depth}, one thread; rate from the "
+                      f"difference (BVH build of {build:.2f} s excluded)"}
+
+
 def run_reference_arm(args, wl_name, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     width, aspect, spp, depth, _, _ = wl
+    if not wl_name.startswith("cover"):
+        import importlib as _il
+        rtw = _il.import_module("raytracing-one-weekend_b200")
+        r = cpu_reference_mesh(build_scene(rtw, wl_name, wl), aspect, depth)
+        print(json.dumps({"impl": "reference", "metric": "Mpaths/s", "value": r["value"], "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": 1,
+                          "warmup": 0, "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic", "config": {"workload": wl_name, "bounded_sample": r["sample"]}, "cpu_baseline": r,
+                          "e2e": {"value": r["value"], "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return 0
     threads = min(os.cpu_count() or 1, 64)  # all threads share ONE unsynchronised mt19937 (SURVEY Q9): more only adds contention
     # bounded sample: quarter-resolution frame, 1 sample per thread (cost is linear in pixels x spp)
     bw = max(width // 2, 200)
@@ -130,7 +180,7 @@ def run_reference_arm(args, wl_name, wl):
             vals.append(r["value"]); secs.append(r["seconds"])
     value = sum(v * s for v, s in zip(vals, secs)) / sum(secs)
     line = {"impl": "reference", "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": {"workload": wl_name, "bounded_sample": r["sample"]},
             "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -178,7 +228,7 @@ def main() -> int:
         spp = args.spp
     height = rtw.image_height(width, aspect)
     kernel = {"auto": rtw.KERNEL_AUTO, "spheres": rtw.KERNEL_SPHERES_SMEM, "bvh": rtw.KERNEL_BVH}[args.kernel]
-    scene = rtw.cover_scene(nsqrt, aspect, moving)
+    scene = build_scene(rtw, args.workload, wl)
     scene_has_triangles = bool((scene.prims["kind"] == rtw.RTW_TRIANGLE).any())
     s_begin, s_end = rtw.sample_shard(spp, rank, world)
     ds = rtw.DeviceScene(scene, local_rank)
@@ -248,6 +298,7 @@ def main() -> int:
         d2h = npix * 16
         e_steps = max(1, min(args.steps, 2))
         pinned = torch.empty((height, width, 4), dtype=torch.float32).pin_memory()
+        e2e_parts = {}
         def e2e_step():
             if world == 1:
                 cfg = rtw.make_cfg(width, height, spp, depth, kernel=kernel, seed=0, device=local_rank, rays_per_lane=args.rays_per_lane)
@@ -257,6 +308,7 @@ def main() -> int:
                 rc = rtw.lib().rtw_render(C.byref(d), C.byref(cfg), C.c_void_p(pinned.data_ptr()), C.byref(stt))
                 if rc != 0:
                     raise RuntimeError(rtw.lib().rtw_last_error().decode())
+                e2e_parts.update(upload_ms=stt.h2d_ms, kernel_ms=stt.kernel_ms, d2h_ms=stt.d2h_ms, call_ms=stt.total_ms)
             else:
                 ds2 = rtw.DeviceScene(scene, local_rank)  # host arrays -> HBM
                 accum.zero_()
@@ -280,7 +332,8 @@ def main() -> int:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": paths_total / (te.item() * 1e-3) / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": te.item(), "steps": e_steps,
-               "api": "rtw_render (host buffers)" if world == 1 else "rtw_scene_upload + rtw_render_device + NCCL reduce + D2H to pinned memory"}
+               "api": "rtw_render (host buffers)" if world == 1 else "rtw_scene_upload + rtw_render_device + NCCL reduce + D2H to pinned memory",
+               **e2e_parts}
         if rank == 0 and world == 1:
             ref_img = out_f32.cpu()
             assert torch.equal(ref_img, pinned), "host-buffer render and device-resident render disagree"
@@ -350,9 +403,11 @@ def main() -> int:
         roofline_sweep["mpaths_per_s"] = paths_gpu * frac_spp / (k1_ms * 1e-3) / 1e6
 
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not scene_has_triangles:
         threads = min(os.cpu_count() or 1, 64)
         cpu_baseline = cpu_reference_run(max(width // 2, 200), aspect, 1, depth, threads)
+    elif world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_reference_mesh(scene, aspect, depth)
 
     line = {
         "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

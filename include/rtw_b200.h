@@ -16,6 +16,7 @@
  *   rtw_scene_upload                   Scene::get_root_bvh / BVHNode ctor       render.cpp:73-110,131-133
  *   rtw_primary_hits                   BVHNode::hit on camera rays (parity mode; no reference entry point)
  *   rtw_finalize_rgb8                  write_color                             render.cpp:11-20
+ *   rtw_release_cached_buffers         (the reference frees its per-thread images at scope exit, render.cpp:151,176)
  */
 #ifndef RTW_B200_H
 #define RTW_B200_H
@@ -107,6 +108,9 @@ RTW_API void rtw_scene_free(rtw_scene* scene);
 /* One-shot render with HOST buffers: upload, render samples [sample_begin,sample_end), download.
  * accum_rgba: width*height*4 floats, (sum r, sum g, sum b, number of samples) per pixel, row 0 = top. */
 RTW_API int rtw_render(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, float* accum_rgba, rtw_stats* stats);
+
+/* rtw_render keeps its per-device accumulation buffers between calls; this frees them. */
+RTW_API void rtw_release_cached_buffers(void);
 
 /* Device-resident render.  accum_fx: width*height*4 int64 on the scene's device; the kernel ADDS
  * fixed-point radiance (1 unit = 2^-32) per channel and 1 per finished path to channel 3, so shards rendered by

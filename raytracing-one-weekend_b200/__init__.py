@@ -90,6 +90,7 @@ ABI = {
     "rtw_scene_upload": (C.c_int, [C.POINTER(SceneDesc), C.c_int32, C.POINTER(_VP)]),
     "rtw_scene_free": (None, [_VP]),
     "rtw_render": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(RenderCfg), _VP, C.POINTER(Stats)]),
+    "rtw_release_cached_buffers": (None, []),
     "rtw_render_device": (C.c_int, [_VP, C.POINTER(RenderCfg), _VP, _VP, C.POINTER(Stats)]),
     "rtw_accum_to_float": (C.c_int, [_VP, _VP, C.c_int64, C.c_int32, _VP]),
     "rtw_render_multi_gpu": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(RenderCfg), C.c_int32, _VP, C.POINTER(Stats)]),

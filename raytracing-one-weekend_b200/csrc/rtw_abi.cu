@@ -68,16 +68,9 @@ double now_ms() {
 struct rtw_scene {
   int device = 0;
   int sm_count = 0;
-  DevBuf<float4> sphA, sphB;
-  DevBuf<int2> sphId;
-  DevBuf<rtw::BigSphere> big;
-  DevBuf<float4> tri;
-  DevBuf<int2> triId;
-  DevBuf<float4> nodes;
-  DevBuf<uint32_t> leafRefs;
-  DevBuf<float4> matA;
-  DevBuf<float2> matB;
-  DevBuf<unsigned long long> counters;
+  DevBuf<unsigned char> arena;  // every table of the scene in ONE allocation, filled by ONE host-to-device copy
+  unsigned long long* counters = nullptr;
+  size_t n_leaf_refs = 0;
   rtw::DevScene dev{};
   int64_t nprims = 0;
   bool has_triangles = false;
@@ -96,11 +89,12 @@ int flatten_and_upload(const rtw_scene_desc* desc, int device, rtw_scene* sc) {
   if (e != cudaSuccess) return fail_cuda("cudaGetDeviceCount (no CUDA device: this library has no CPU fallback)", e);
   if (device < 0 || device >= ndev) return fail("rtw_scene_upload: device ordinal out of range");
   RTW_CUDA(cudaSetDevice(device));
-  cudaDeviceProp prop{};
-  RTW_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10) return fail(std::string("rtw_b200 kernels are built for sm_100a only; device is ") + prop.name);
+  int cc_major = 0, sm_count = 0;
+  RTW_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+  RTW_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+  if (cc_major < 10) return fail("rtw_b200 kernels are built for sm_100a only; this device has an older compute capability");
   sc->device = device;
-  sc->sm_count = prop.multiProcessorCount;
+  sc->sm_count = sm_count;
   sc->nprims = desc->nprims;
 
   std::vector<float4> sA_static, sB_static, sA_moving, sB_moving;
@@ -201,26 +195,39 @@ int flatten_and_upload(const rtw_scene_desc* desc, int device, rtw_scene* sc) {
     matB[i] = make_float2((float)m.ior, __int_as_float_host(m.kind));
   }
 
-  RTW_CUDA(sc->sphA.upload(sA));
-  RTW_CUDA(sc->sphB.upload(sB));
-  RTW_CUDA(sc->sphId.upload(sId));
-  RTW_CUDA(sc->big.upload(big));
-  RTW_CUDA(sc->tri.upload(tri));
-  RTW_CUDA(sc->triId.upload(triId));
-  RTW_CUDA(sc->nodes.upload(nodes));
-  RTW_CUDA(sc->leafRefs.upload(builder.leaf_refs()));
-  RTW_CUDA(sc->matA.upload(matA));
-  RTW_CUDA(sc->matB.upload(matB));
-  RTW_CUDA(sc->counters.alloc(rtw::kCtrCount));
-  RTW_CUDA(cudaMemsetAsync(sc->counters.p, 0, rtw::kCtrCount * sizeof(unsigned long long)));
+  // ---- one arena, one copy ---------------------------------------------------------------------------------------------
+  std::vector<unsigned char> host;
+  auto put = [&host](const void* src, size_t bytes) {
+    const size_t off = (host.size() + 255) & ~size_t(255);
+    host.resize(off + bytes);
+    if (bytes) std::memcpy(host.data() + off, src, bytes);
+    return off;
+  };
+  const unsigned long long zero_counters[rtw::kCtrCount] = {};
+  const size_t o_sA = put(sA.data(), sA.size() * sizeof(float4)), o_sB = put(sB.data(), sB.size() * sizeof(float4)),
+               o_sId = put(sId.data(), sId.size() * sizeof(int2)), o_big = put(big.data(), big.size() * sizeof(rtw::BigSphere)),
+               o_tri = put(tri.data(), tri.size() * sizeof(float4)), o_triId = put(triId.data(), triId.size() * sizeof(int2)),
+               o_nodes = put(nodes.data(), nodes.size() * sizeof(float4)),
+               o_refs = put(builder.leaf_refs().data(), builder.leaf_refs().size() * sizeof(uint32_t)),
+               o_matA = put(matA.data(), matA.size() * sizeof(float4)), o_matB = put(matB.data(), matB.size() * sizeof(float2)),
+               o_ctr = put(zero_counters, sizeof zero_counters);
+  host.resize((host.size() + 255) & ~size_t(255));
+  RTW_CUDA(sc->arena.alloc(host.size()));
+  RTW_CUDA(cudaMemcpy(sc->arena.p, host.data(), host.size(), cudaMemcpyHostToDevice));
+  unsigned char* base = sc->arena.p;
+  sc->counters = reinterpret_cast<unsigned long long*>(base + o_ctr);
+  sc->n_leaf_refs = builder.leaf_refs().size();
 
   rtw::DevScene& d = sc->dev;
-  d.sphA = sc->sphA.p; d.sphB = sc->sphB.p; d.sphId = sc->sphId.p;
+  d.sphA = reinterpret_cast<const float4*>(base + o_sA); d.sphB = reinterpret_cast<const float4*>(base + o_sB);
+  d.sphId = reinterpret_cast<const int2*>(base + o_sId);
   d.n_static = static_cast<int32_t>(sA_static.size()); d.n_moving = static_cast<int32_t>(sA_moving.size());
-  d.big = sc->big.p; d.n_big = static_cast<int32_t>(big.size());
-  d.tri = sc->tri.p; d.triId = sc->triId.p; d.n_tri = static_cast<int32_t>(triId.size());
-  d.nodes = sc->nodes.p; d.leafRefs = sc->leafRefs.p; d.n_nodes = static_cast<int32_t>(builder.nodes().size());
-  d.matA = sc->matA.p; d.matB = sc->matB.p;
+  d.big = reinterpret_cast<const rtw::BigSphere*>(base + o_big); d.n_big = static_cast<int32_t>(big.size());
+  d.tri = reinterpret_cast<const float4*>(base + o_tri); d.triId = reinterpret_cast<const int2*>(base + o_triId);
+  d.n_tri = static_cast<int32_t>(triId.size());
+  d.nodes = reinterpret_cast<const float4*>(base + o_nodes); d.leafRefs = reinterpret_cast<const uint32_t*>(base + o_refs);
+  d.n_nodes = static_cast<int32_t>(builder.nodes().size());
+  d.matA = reinterpret_cast<const float4*>(base + o_matA); d.matB = reinterpret_cast<const float2*>(base + o_matB);
   const rtw_camera& c = desc->camera;
   for (int k = 0; k < 3; ++k) {
     d.cam.origin[k] = (float)c.origin[k]; d.cam.lower_left[k] = (float)c.lower_left[k];
@@ -230,7 +237,6 @@ int flatten_and_upload(const rtw_scene_desc* desc, int device, rtw_scene* sc) {
   d.cam.lens_radius = (float)c.lens_radius; d.cam.t0 = (float)c.t0; d.cam.t1 = (float)c.t1;
   sc->has_triangles = !triId.empty();
   sc->smem_bytes = 16 + (sA.size() + 1) * 32;
-  RTW_CUDA(cudaStreamSynchronize(nullptr));
   return 0;
 }
 
@@ -261,7 +267,7 @@ int fill_params(const rtw_scene* sc, const rtw_render_cfg* cfg, int mode, unsign
   if (static_cast<long long>(cfg->width) * cfg->height >= (1ll << 31)) return fail("render: image too large");
   p->sc = sc->dev;
   p->accum = accum;
-  p->counters = sc->counters.p;
+  p->counters = sc->counters;
   p->width = static_cast<uint32_t>(cfg->width); p->height = static_cast<uint32_t>(cfg->height);
   p->npix = p->width * p->height;
   p->s_begin = static_cast<uint32_t>(cfg->sample_begin); p->s_end = static_cast<uint32_t>(cfg->sample_end);
@@ -279,7 +285,7 @@ int fill_params(const rtw_scene* sc, const rtw_render_cfg* cfg, int mode, unsign
   p->inv_wm1 = 1.0f / static_cast<float>(cfg->width - 1);
   p->inv_hm1 = 1.0f / static_cast<float>(cfg->height - 1);
   p->seed = cfg->seed;
-  p->n_leaf_refs = static_cast<uint32_t>(sc->leafRefs.n);
+  p->n_leaf_refs = static_cast<uint32_t>(sc->n_leaf_refs);
   (void)mode;
   return 0;
 }
@@ -330,7 +336,7 @@ int rtw_render_device(const rtw_scene* scene, const rtw_render_cfg* cfg, int64_t
   if (int rc = fill_params(scene, cfg, mode, reinterpret_cast<unsigned long long*>(accum_fx), &p)) return rc;
   const int rpl = cfg->rays_per_lane;
   const bool want_stats = (cfg->flags & RTW_FLAG_STATS) != 0;
-  RTW_CUDA(cudaMemsetAsync(scene->counters.p, 0, rtw::kCtrCount * sizeof(unsigned long long), stream));
+  RTW_CUDA(cudaMemsetAsync(scene->counters, 0, rtw::kCtrCount * sizeof(unsigned long long), stream));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (stats) {
     RTW_CUDA(cudaEventCreate(&e0));
@@ -342,7 +348,7 @@ int rtw_render_device(const rtw_scene* scene, const rtw_render_cfg* cfg, int64_t
   if (stats) {
     RTW_CUDA(cudaEventRecord(e1, stream));
     unsigned long long h[rtw::kCtrCount];
-    RTW_CUDA(cudaMemcpyAsync(h, scene->counters.p, sizeof h, cudaMemcpyDeviceToHost, stream));
+    RTW_CUDA(cudaMemcpyAsync(h, scene->counters, sizeof h, cudaMemcpyDeviceToHost, stream));
     RTW_CUDA(cudaStreamSynchronize(stream));
     float ms = 0.f;
     RTW_CUDA(cudaEventElapsedTime(&ms, e0, e1));
@@ -365,25 +371,52 @@ int rtw_accum_to_float(const int64_t* accum_fx, float* accum_rgba, int64_t npixe
   return 0;
 }
 
+// Per-device accumulation buffers of the host-buffer entry point, kept across calls (grow-only) so that a render costs one
+// small arena allocation, one H2D copy, the kernels and one D2H copy.  Released by rtw_release_cached_buffers().
+namespace {
+struct RenderCache {
+  DevBuf<long long> fx;
+  DevBuf<float> out;
+  size_t npix = 0;
+};
+std::mutex g_cache_mutex;
+RenderCache* g_cache[64] = {};
+}  // namespace
+
+void rtw_release_cached_buffers(void) {
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  for (int d = 0; d < 64; ++d) {
+    if (!g_cache[d]) continue;
+    cudaSetDevice(d);
+    delete g_cache[d];
+    g_cache[d] = nullptr;
+  }
+}
+
 int rtw_render(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, float* accum_rgba, rtw_stats* stats) {
   if (!desc || !cfg || !accum_rgba) return fail("rtw_render: null argument");
+  if (cfg->width < 2 || cfg->height < 2) return fail("render: width and height must be >= 2 (pixel mapping divides by W-1, H-1)");
   const double t_start = now_ms();
   rtw_scene* sc = nullptr;
   if (int rc = rtw_scene_upload(desc, cfg->device, &sc)) return rc;
   struct Guard { rtw_scene* s; ~Guard() { rtw_scene_free(s); } } guard{sc};
   const double t_up = now_ms();
   const size_t npix = static_cast<size_t>(cfg->width) * static_cast<size_t>(cfg->height);
-  if (cfg->width < 2 || cfg->height < 2) return fail("render: width and height must be >= 2 (pixel mapping divides by W-1, H-1)");
-  DevBuf<long long> fx;
-  DevBuf<float> out;
-  RTW_CUDA(fx.alloc(npix * 4));
-  RTW_CUDA(out.alloc(npix * 4));
-  RTW_CUDA(cudaMemsetAsync(fx.p, 0, npix * 4 * sizeof(long long)));
+  std::lock_guard<std::mutex> lock(g_cache_mutex);  // also serialises host-buffer renders per process (not re-entrant per device)
+  if (cfg->device >= 64) return fail("rtw_render: device ordinal out of range");
+  if (!g_cache[cfg->device]) g_cache[cfg->device] = new RenderCache();
+  RenderCache& rc_ = *g_cache[cfg->device];
+  if (rc_.npix < npix) {
+    RTW_CUDA(rc_.fx.alloc(npix * 4));
+    RTW_CUDA(rc_.out.alloc(npix * 4));
+    rc_.npix = npix;
+  }
+  RTW_CUDA(cudaMemsetAsync(rc_.fx.p, 0, npix * 4 * sizeof(long long)));
   rtw_stats st{};
-  if (int rc = rtw_render_device(sc, cfg, reinterpret_cast<int64_t*>(fx.p), nullptr, &st)) return rc;
-  if (int rc = rtw_accum_to_float(reinterpret_cast<const int64_t*>(fx.p), out.p, static_cast<int64_t>(npix), cfg->device, nullptr)) return rc;
+  if (int rc = rtw_render_device(sc, cfg, reinterpret_cast<int64_t*>(rc_.fx.p), nullptr, &st)) return rc;
+  if (int rc = rtw_accum_to_float(reinterpret_cast<const int64_t*>(rc_.fx.p), rc_.out.p, static_cast<int64_t>(npix), cfg->device, nullptr)) return rc;
   const double t_d0 = now_ms();
-  RTW_CUDA(cudaMemcpy(accum_rgba, out.p, npix * 4 * sizeof(float), cudaMemcpyDeviceToHost));
+  RTW_CUDA(cudaMemcpy(accum_rgba, rc_.out.p, npix * 4 * sizeof(float), cudaMemcpyDeviceToHost));
   const double t_end = now_ms();
   if (stats) {
     *stats = st;

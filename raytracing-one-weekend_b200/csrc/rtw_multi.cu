@@ -6,6 +6,9 @@
 // NCCL is loaded with dlopen at first use so that processes which already carry their own NCCL (PyTorch) never
 // see a second copy just because they loaded this library.
 #include <dlfcn.h>
+#include <unistd.h>
+
+#include <cstdio>
 
 #include <cstring>
 #include <string>
@@ -86,7 +89,13 @@ extern "C" int rtw_render_multi_gpu(const rtw_scene_desc* desc, const rtw_render
     }
   };
 
+  // NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION/INFO is set; stdout is the image (P3 text) for the
+  // drop-in render(), so route fd 1 to stderr while the communicators are created.
+  std::fflush(stdout);
+  const int saved_stdout = dup(1);
+  if (saved_stdout >= 0) dup2(2, 1);
   int nrc = g_nccl.CommInitAll(comms.data(), ngpus, devs.data());
+  if (saved_stdout >= 0) { std::fflush(stdout); dup2(saved_stdout, 1); close(saved_stdout); }
   if (nrc != 0) { cleanup(); return rtw_set_error_((std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(nrc)).c_str()); }
 
   // one host thread per GPU: upload, zero, render its sample shard

@@ -410,3 +410,25 @@ def test_multi_gpu_in_process(gpu):
     one, _ = gpu.render(scene, 200, 133, 32, 20, seed=8)
     two, st = gpu.render_multi_gpu(scene, 200, 133, 32, 2, 20, seed=8)
     assert np.array_equal(one, two) and st["paths"] == 200 * 133 * 32
+
+
+def test_high_poly_stand_in_mesh(gpu, port, oracle_mod, tmp_path):
+    """Config-4 path (device BVH over a large mesh in global memory) on a 62k-triangle stand-in: 968 * 4^3 triangles made
+    by the product's generator, on the r=1000 ground; ids exact in fp64, knife-edge tolerance in fp32, same-stream image."""
+    import ctypes as C
+    obj = tmp_path / "standin3.obj"
+    n = C.c_longlong(0)
+    assert gpu.host().rtwh_make_mesh(SUZANNE.encode(), str(obj).encode(), 3, 20221018, 0.08, C.byref(n)) == 0 and n.value == 968 * 64
+    scene = gpu.mesh_on_ground_scene(str(obj), 1.7777777777777777)
+    assert len(scene.prims) == 968 * 64 + 1
+    osc = port.scene_custom(scene.prims, scene.mats.view(oracle_mod.MAT_DTYPE), oracle_mod.camera_params(**scene.params))
+    W, H = 128, 72
+    want = osc.primary_hits(W, H, 0.0)
+    check_primary(gpu.primary_hits(scene, W, H, 0.0, 64), want, fp64=True, unit_normals=False)
+    check_primary(gpu.primary_hits(scene, W, H, 0.0, 32), want, fp64=False, unit_normals=False, max_knife_edge=3)
+    acc, st = gpu.render(scene, 64, 36, 4, 20, seed=6, stats=True)
+    ref, _, rays = port.render_philox(osc, 64, 36, 0, 4, 20, seed=6, nthreads=8)
+    assert st["kernel_used"] == gpu.KERNEL_BVH and st["tri_tests"] > 0
+    got = acc[..., :3].astype(np.float64) / 4
+    assert (np.abs(got - ref / 4).max(axis=2) > 1e-3).mean() < 0.03
+    assert abs(st["rays"] - rays) / rays < 0.01
