@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -181,6 +182,7 @@ int flatten_and_upload(const rtw_scene_desc* desc, int device, rtw_scene* sc) {
     refs.push_back((1u << 30) | static_cast<uint32_t>(i));
   }
   rtw::BvhBuilder builder;
+  if (const char* e = std::getenv("RTW_BVH_LEAF")) builder.kMaxLeaf = std::min(std::max(std::atoi(e), 1), 31);  // tuning knob
   builder.build(boxes, refs);
   std::vector<float4> nodes(builder.nodes().size() * 4);
   if (!nodes.empty()) std::memcpy(nodes.data(), builder.nodes().data(), nodes.size() * sizeof(float4));
@@ -227,6 +229,7 @@ int flatten_and_upload(const rtw_scene_desc* desc, int device, rtw_scene* sc) {
   d.n_tri = static_cast<int32_t>(triId.size());
   d.nodes = reinterpret_cast<const float4*>(base + o_nodes); d.leafRefs = reinterpret_cast<const uint32_t*>(base + o_refs);
   d.n_nodes = static_cast<int32_t>(builder.nodes().size());
+  d.leaf_direct = builder.kMaxLeaf == 1 ? 1 : 0;
   d.matA = reinterpret_cast<const float4*>(base + o_matA); d.matB = reinterpret_cast<const float2*>(base + o_matB);
   const rtw_camera& c = desc->camera;
   for (int k = 0; k < 3; ++k) {

@@ -31,8 +31,10 @@ static_assert(sizeof(PackedNode) == 64, "node must be 64 bytes");
 
 class BvhBuilder {
  public:
-  static constexpr int kMaxLeaf = 4;
+  int kMaxLeaf = 1;  // primitives per leaf (<= 31); 1 = primitive reference stored in the child code
   static constexpr int kBins = 16;
+  // references are (kind << 30) | index with index < 2^28; bit 29 marks a direct leaf so that its code ~ref is never -1
+  static constexpr uint32_t kDirectMark = 1u << 29;
 
   // boxes[i] / refs[i]: bounds and encoded reference ((kind << 30) | index) of primitive i
   void build(const std::vector<Box3>& boxes, const std::vector<uint32_t>& refs) {
@@ -55,7 +57,7 @@ class BvhBuilder {
       PackedNode nd{};
       set_child(nd, 0, rb, make_leaf(0, n));
       Box3 e; e.reset();
-      set_child(nd, 1, e, ~0);  // ~0 -> first 0, count 0
+      set_child(nd, 1, e, empty_leaf());
       nodes_.push_back(nd);
       return;
     }
@@ -63,6 +65,8 @@ class BvhBuilder {
     build_node(0, 0, n, rb);
   }
 
+  // a child that is never entered (inverted box); its code must still decode harmlessly
+  int32_t empty_leaf() const { return kMaxLeaf == 1 ? static_cast<int32_t>(~kDirectMark) : ~0; }
   const std::vector<PackedNode>& nodes() const { return nodes_; }
   const std::vector<uint32_t>& leaf_refs() const { return leaf_refs_; }
 
@@ -94,7 +98,10 @@ class BvhBuilder {
       nd.right = code;
     }
   }
+  // leaf child code: ~((first << 5) | count) into leaf_refs, or, with single-primitive leaves (kMaxLeaf == 1),
+  // ~reference itself: no indirection left on the device
   int32_t make_leaf(size_t begin, size_t end) {
+    if (kMaxLeaf == 1 && end - begin == 1) return static_cast<int32_t>(~((*refs_)[order_[begin]] | kDirectMark));
     const uint32_t first = static_cast<uint32_t>(leaf_refs_.size());
     for (size_t i = begin; i < end; ++i) leaf_refs_.push_back((*refs_)[order_[i]]);
     const uint32_t v = (first << 5) | static_cast<uint32_t>(end - begin);

@@ -51,10 +51,12 @@ struct DevScene {
   // BVH over small spheres + triangles: 4 float4 per node
   //   q0 = (lmin.x, lmin.y, lmin.z, lmax.x) q1 = (lmax.y, lmax.z, rmin.x, rmin.y)
   //   q2 = (rmin.z, rmax.x, rmax.y, rmax.z) q3 = (left, right, -, -) as int bits
-  //   child >= 0: inner node index; child < 0: leaf, ~child = (first << 5) | count  into leafRefs
+  //   child >= 0: inner node index; child < 0: leaf, ~child = (first << 5) | count  into leafRefs,
+  //   or (leaf_direct) ~child = the primitive reference itself with bit 29 set (so that the code is never -1 = "no node")
   const float4* nodes;
   const uint32_t* leafRefs;  // (kind << 30) | index, kind 0 = sphere table index, 1 = triangle index
   int32_t n_nodes;
+  int32_t leaf_direct;       // 1: single-primitive leaves, child code = ~reference (leafRefs unused)
   // materials
   const float4* matA;  // (albedo.r, albedo.g, albedo.b, fuzz)
   const float2* matB;  // (ior, kind as int bits)

@@ -239,10 +239,10 @@ __device__ __forceinline__ void trace_bvh(const DevScene& sc, F3 o, F3 d, float 
 
   auto leaf = [&](int code) {
     const uint32_t v = static_cast<uint32_t>(~code);
-    const uint32_t first = v >> 5, cnt = v & 31u;
+    const uint32_t first = v >> 5, cnt = sc.leaf_direct ? 1u : (v & 31u);
     for (uint32_t k = 0; k < cnt; ++k) {
-      const uint32_t ref = __ldg(&sc.leafRefs[first + k]);
-      const int i = static_cast<int>(ref & 0x3fffffffu);
+      const uint32_t ref = sc.leaf_direct ? v : __ldg(&sc.leafRefs[first + k]);
+      const int i = static_cast<int>(ref & 0x1fffffffu);
       if (ref >> 30) {
         if (STATS) ++n_tri;
         const float4 q0 = __ldg(&sc.tri[3 * i]), q1 = __ldg(&sc.tri[3 * i + 1]), q2 = __ldg(&sc.tri[3 * i + 2]);
@@ -504,8 +504,8 @@ __device__ __forceinline__ float4 ld4(const float4* p, int i) { return SMEM ? p[
 template <bool SMEM>
 __device__ __forceinline__ uint32_t ld1(const uint32_t* p, int i) { return SMEM ? p[i] : __ldg(p + i); }
 
-template <bool SMEM, bool STATS, int STEPS, int SERVICE_MIN, int LEAF_MIN>
-__global__ void __launch_bounds__(kRenderThreads, 3) k_render_bvh(const __grid_constant__ RenderParams p) {
+template <bool SMEM, bool STATS, int STEPS, int SERVICE_MIN, int MINB>
+__global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __grid_constant__ RenderParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const DevScene& sc = p.sc;
   BvhTables tb{sc.nodes, sc.leafRefs, sc.sphA, sc.sphB, sc.tri};
@@ -655,17 +655,16 @@ __global__ void __launch_bounds__(kRenderThreads, 3) k_render_bvh(const __grid_c
       }
     }
 
-    if constexpr (LEAF_MIN == 0) {
     // ---- traversal phase: STEPS node-or-leaf steps per traversing lane ------------------------------------------------
 #pragma unroll 1
     for (int step = 0; step < STEPS; ++step) {
       if (state != TRAV) continue;
       if (node < 0) {  // leaf
         const uint32_t v = static_cast<uint32_t>(~node);
-        const uint32_t first = v >> 5, cnt = v & 31u;
+        const uint32_t first = v >> 5, cnt = sc.leaf_direct ? 1u : (v & 31u);
         for (uint32_t k = 0; k < cnt; ++k) {
-          const uint32_t ref = ld1<SMEM>(tb.leafRefs, static_cast<int>(first + k));
-          const int i = static_cast<int>(ref & 0x3fffffffu);
+          const uint32_t ref = sc.leaf_direct ? v : ld1<SMEM>(tb.leafRefs, static_cast<int>(first + k));
+          const int i = static_cast<int>(ref & 0x1fffffffu);
           if (ref >> 30) {
             if (STATS) ++n_tri;
             const float4 q0 = ld4<SMEM>(tb.tri, 3 * i), q1 = ld4<SMEM>(tb.tri, 3 * i + 1), q2 = ld4<SMEM>(tb.tri, 3 * i + 2);
@@ -711,79 +710,6 @@ __global__ void __launch_bounds__(kRenderThreads, 3) k_render_bvh(const __grid_c
           node = kMiss; state = DONE;
         }
       }
-    }
-    } else {
-    // ---- traversal phase ---------------------------------------------------------------------------------------------
-    // Each step: every lane standing on an inner node visits it; lanes standing on a leaf wait until at least LEAF_MIN of
-    // them are (or nobody has inner work left) and then test ONE primitive of their leaf, so both halves run on mostly
-    // full warps instead of a handful of lanes each.
-#pragma unroll 1
-    for (int step = 0; step < STEPS; ++step) {
-      const bool inner = state == TRAV && node >= 0;
-      if (inner) {
-        if (STATS) ++n_nodes;
-        const float4 q0 = ld4<SMEM>(tb.nodes, 4 * node), q1 = ld4<SMEM>(tb.nodes, 4 * node + 1), q2 = ld4<SMEM>(tb.nodes, 4 * node + 2),
-                     q3 = ld4<SMEM>(tb.nodes, 4 * node + 3);
-        float t0x = fmaf(q0.x, idx, -odx), t1x = fmaf(q0.w, idx, -odx);
-        float t0y = fmaf(q0.y, idy, -ody), t1y = fmaf(q1.x, idy, -ody);
-        float t0z = fmaf(q0.z, idz, -odz), t1z = fmaf(q1.y, idz, -odz);
-        const float far_limit = best_t * 1.0000005f;  // slack for the approximate reciprocals
-        const float ln = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), kTMin * 0.999f));
-        const float lf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), far_limit)) * 1.0000005f;
-        t0x = fmaf(q1.z, idx, -odx); t1x = fmaf(q2.y, idx, -odx);
-        t0y = fmaf(q1.w, idy, -ody); t1y = fmaf(q2.z, idy, -ody);
-        t0z = fmaf(q2.x, idz, -odz); t1z = fmaf(q2.w, idz, -odz);
-        const float rn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), kTMin * 0.999f));
-        const float rf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), far_limit)) * 1.0000005f;
-        const bool hl = ln <= lf, hr = rn <= rf;
-        const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
-        if (hl && hr) {
-          const bool lfirst = ln <= rn;
-          node = lfirst ? left : right;
-          if (sp < kBvhStack) stack[sp++] = lfirst ? right : left;
-        } else if (hl) {
-          node = left;
-        } else if (hr) {
-          node = right;
-        } else if (sp > 0) {
-          node = stack[--sp];
-        } else {
-          node = kMiss; state = DONE;
-        }
-      }
-      const bool at_leaf = state == TRAV && node < 0;
-      const uint32_t leaf_mask = __ballot_sync(0xffffffffu, at_leaf);
-      const uint32_t inner_mask = __ballot_sync(0xffffffffu, state == TRAV && node >= 0);
-      if (leaf_mask == 0u && inner_mask == 0u) break;
-      if (__popc(leaf_mask) >= LEAF_MIN || inner_mask == 0u) {
-        if (at_leaf) {
-          uint32_t v = static_cast<uint32_t>(~node);  // (first << 5) | remaining
-          if ((v & 31u) != 0u) {
-            const uint32_t ref = ld1<SMEM>(tb.leafRefs, static_cast<int>(v >> 5));
-            const int i = static_cast<int>(ref & 0x3fffffffu);
-            if (ref >> 30) {
-              if (STATS) ++n_tri;
-              const float4 q0 = ld4<SMEM>(tb.tri, 3 * i), q1 = ld4<SMEM>(tb.tri, 3 * i + 1), q2 = ld4<SMEM>(tb.tri, 3 * i + 2);
-              const float t = triangle_hit<float>(o, d, mk<float>(q0.x, q0.y, q0.z), mk<float>(q1.x, q1.y, q1.z), mk<float>(q2.x, q2.y, q2.z),
-                                                  mk<float>(q0.w, q1.w, q2.w), kTMin, best_t);
-              if (t >= 0.0f) { best_t = t; best_i = kHitTri | i; }
-            } else {
-              if (STATS) ++n_tests;
-              const float4 A = ld4<SMEM>(tb.sphA, i), B = ld4<SMEM>(tb.sphB, i);
-              const float t = sphere_hit_fast(o, d, qa, qia, mk<float>(fmaf(tm, B.x, A.x), fmaf(tm, B.y, A.y), fmaf(tm, B.z, A.z)), B.w, kTMin, best_t);
-              if (t >= 0.0f) { best_t = t; best_i = i; }
-            }
-            v += 31u;  // first + 1, remaining - 1
-          }
-          if ((v & 31u) == 0u) {
-            if (sp > 0) node = stack[--sp];
-            else { node = kMiss; state = DONE; }
-          } else {
-            node = static_cast<int>(~v);
-          }
-        }
-      }
-    }
     }
   }
 
@@ -989,9 +915,9 @@ static cudaError_t launch_render_t(const RenderParams& p, int sm_count, size_t s
   return cudaGetLastError();
 }
 
-template <bool SMEM, bool STATS, int STEPS, int SERVICE_MIN, int LEAF_MIN>
+template <bool SMEM, bool STATS, int STEPS, int SERVICE_MIN, int MINB>
 static cudaError_t launch_bvh_t(const RenderParams& p, int sm_count, size_t smem, cudaStream_t stream) {
-  auto kern = k_render_bvh<SMEM, STATS, STEPS, SERVICE_MIN, LEAF_MIN>;
+  auto kern = k_render_bvh<SMEM, STATS, STEPS, SERVICE_MIN, MINB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
   int per_sm = 0;
@@ -1029,15 +955,14 @@ cudaError_t launch_render(const RenderParams& p, int mode, int rays_per_lane, bo
   const int variant = rays_per_lane % 1000;
   const size_t bsm = rays_per_lane >= 1000 ? 0 : bvh_smem_bytes(p);
   if (variant == 100) return stats ? launch_render_t<1, 1, true>(p, sm_count, 0, stream, nullptr) : launch_render_t<1, 1, false>(p, sm_count, 0, stream, nullptr);
-#define RTW_BVH(ST, SV, LF)                                                                                         \
-  return bsm ? (stats ? launch_bvh_t<true, true, ST, SV, LF>(p, sm_count, bsm, stream) : launch_bvh_t<true, false, ST, SV, LF>(p, sm_count, bsm, stream)) \
-             : (stats ? launch_bvh_t<false, true, ST, SV, LF>(p, sm_count, 0, stream) : launch_bvh_t<false, false, ST, SV, LF>(p, sm_count, 0, stream))
-  if (variant == 101) { RTW_BVH(8, 24, 0); }
-  if (variant == 102) { RTW_BVH(8, 28, 0); }
-  if (variant == 103) { RTW_BVH(16, 24, 0); }
-  if (variant == 104) { RTW_BVH(12, 26, 0); }
-  if (variant == 105) { RTW_BVH(8, 24, 8); }
-  RTW_BVH(8, 24, 0);
+#define RTW_BVH(ST, SV, MB)                                                                                         \
+  return bsm ? (stats ? launch_bvh_t<true, true, ST, SV, MB>(p, sm_count, bsm, stream) : launch_bvh_t<true, false, ST, SV, MB>(p, sm_count, bsm, stream)) \
+             : (stats ? launch_bvh_t<false, true, ST, SV, MB>(p, sm_count, 0, stream) : launch_bvh_t<false, false, ST, SV, MB>(p, sm_count, 0, stream))
+  if (variant == 101) { RTW_BVH(8, 24, 3); }
+  if (variant == 102) { RTW_BVH(12, 24, 4); }
+  if (variant == 103) { RTW_BVH(8, 28, 4); }
+  if (variant == 104) { RTW_BVH(6, 24, 4); }
+  RTW_BVH(8, 24, 4);
 #undef RTW_BVH
 }
 
