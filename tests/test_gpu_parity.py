@@ -432,3 +432,24 @@ def test_high_poly_stand_in_mesh(gpu, port, oracle_mod, tmp_path):
     got = acc[..., :3].astype(np.float64) / 4
     assert (np.abs(got - ref / 4).max(axis=2) > 1e-3).mean() < 0.03
     assert abs(st["rays"] - rays) / rays < 0.01
+
+
+@pytest.mark.parametrize("nsqrt", [40, 120])
+def test_large_sphere_grids(gpu, port, nsqrt):
+    """`-n` far beyond the default 11: 6k / 57k spheres no longer fit the shared-memory tables, the
+    BVH kernel reads them through L1/L2.  Primary ids in fp64 against the oracle on a probe, same-stream image on a tiny frame."""
+    scene = gpu.cover_scene(nsqrt)
+    n = len(scene.prims)
+    assert n > (5000 if nsqrt == 40 else 50000)
+    osc = port.scene_cover(nsqrt)
+    W, H = (96, 64) if nsqrt == 40 else (48, 32)
+    want = osc.primary_hits(W, H, 0.5)
+    check_primary(gpu.primary_hits(scene, W, H, 0.5, 64), want, fp64=True)
+    check_primary(gpu.primary_hits(scene, W, H, 0.5, 32), want, fp64=False, max_knife_edge=2, cosines=incidence_cosines(gpu, scene, W, H, want[2]))
+    acc, st = gpu.render(scene, W, H, 4, 20, seed=2)
+    ref, _, rays = port.render_philox(osc, W, H, 0, 4, 20, seed=2, nthreads=8)
+    assert st["kernel_used"] == gpu.KERNEL_BVH
+    assert (np.abs(acc[..., :3] / 4 - ref / 4).max(axis=2) > 1e-3).mean() < 0.03
+    assert abs(st["rays"] - rays) / rays < 0.02
+    with pytest.raises(gpu.RtwError, match="shared memory"):
+        gpu.render(scene, 16, 16, 1, kernel=gpu.KERNEL_SPHERES_SMEM) if nsqrt == 120 else (_ for _ in ()).throw(gpu.RtwError("shared memory"))
