@@ -4,6 +4,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <future>
 #include <cstdint>
 #include <limits>
 #include <vector>
@@ -42,6 +43,7 @@ class BvhBuilder {
     const size_t n = boxes.size();
     if (n == 0) return;
     boxes_ = &boxes; refs_ = &refs;
+    if (kMaxLeaf == 1 && n >= 2) { build_direct(boxes, refs); return; }
     order_.resize(n);
     cent_.resize(3 * n);
     for (size_t i = 0; i < n; ++i) {
@@ -77,6 +79,128 @@ class BvhBuilder {
   std::vector<float> cent_;
   std::vector<PackedNode> nodes_;
   std::vector<uint32_t> leaf_refs_;
+
+
+  // ---- fast path for single-primitive leaves (the default) -------------------------------------------------------------
+  // A subtree over m primitives has exactly m-1 inner nodes, so node indices can be assigned in preorder up front
+  // (root = base, left subtree = base+1 ..., right subtree after it): deterministic layout, children next to their
+  // parent, and disjoint index ranges that independent threads can fill without synchronisation.
+  struct Item { Box3 box; float c[3]; uint32_t ref; };
+
+  void build_direct(const std::vector<Box3>& boxes, const std::vector<uint32_t>& refs) {
+    const size_t n = boxes.size();
+    items_.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+      items_[i].box = boxes[i];
+      for (int k = 0; k < 3; ++k) items_[i].c[k] = 0.5f * (boxes[i].lo[k] + boxes[i].hi[k]);
+      items_[i].ref = refs[i];
+    }
+    nodes_.assign(n - 1, PackedNode{});
+    leaf_refs_.clear();
+    direct_node(0, 0, n, 0);
+    items_.clear(); items_.shrink_to_fit();
+  }
+
+  int32_t direct_child_code(size_t node_index, size_t begin, size_t end) const {
+    return end - begin == 1 ? static_cast<int32_t>(~(items_[begin].ref | kDirectMark)) : static_cast<int32_t>(node_index);
+  }
+
+  static float area_of(const Box3& b) { return b.half_area(); }
+
+  void direct_node(size_t idx, size_t begin, size_t end, int depth) {
+    const size_t n = end - begin;
+    Item* it = items_.data();
+    size_t mid = begin;
+    Box3 lb, rb;
+    if (n == 2) {
+      mid = begin + 1; lb = it[begin].box; rb = it[begin + 1].box;
+    } else if (n <= 8) {
+      // exact SAH over the sorted order of the widest centroid axis
+      float clo[3] = {1e30f, 1e30f, 1e30f}, chi[3] = {-1e30f, -1e30f, -1e30f};
+      for (size_t i = begin; i < end; ++i)
+        for (int k = 0; k < 3; ++k) { clo[k] = std::min(clo[k], it[i].c[k]); chi[k] = std::max(chi[k], it[i].c[k]); }
+      int ax = 0;
+      if (chi[1] - clo[1] > chi[ax] - clo[ax]) ax = 1;
+      if (chi[2] - clo[2] > chi[ax] - clo[ax]) ax = 2;
+      std::sort(it + begin, it + end, [ax](const Item& a, const Item& b) { return a.c[ax] < b.c[ax]; });
+      Box3 suffix[8];
+      Box3 acc; acc.reset();
+      for (size_t k = n; k-- > 1;) { acc.grow(it[begin + k].box); suffix[k] = acc; }
+      acc.reset();
+      float best = std::numeric_limits<float>::infinity();
+      size_t best_k = 1;
+      for (size_t k = 1; k < n; ++k) {
+        acc.grow(it[begin + k - 1].box);
+        const float cost = area_of(acc) * static_cast<float>(k) + area_of(suffix[k]) * static_cast<float>(n - k);
+        if (cost < best) { best = cost; best_k = k; lb = acc; rb = suffix[k]; }
+      }
+      mid = begin + best_k;
+    } else {
+      // binned SAH, all three axes in one pass over the range
+      float clo[3] = {1e30f, 1e30f, 1e30f}, chi[3] = {-1e30f, -1e30f, -1e30f};
+      for (size_t i = begin; i < end; ++i)
+        for (int k = 0; k < 3; ++k) { clo[k] = std::min(clo[k], it[i].c[k]); chi[k] = std::max(chi[k], it[i].c[k]); }
+      Box3 bb[3][kBins]; uint32_t cnt[3][kBins];
+      float scale[3];
+      for (int ax = 0; ax < 3; ++ax) {
+        const float ext = chi[ax] - clo[ax];
+        scale[ax] = ext > 0.0f ? kBins / ext : 0.0f;
+        for (int b = 0; b < kBins; ++b) { bb[ax][b].reset(); cnt[ax][b] = 0; }
+      }
+      for (size_t i = begin; i < end; ++i) {
+        for (int ax = 0; ax < 3; ++ax) {
+          int b = static_cast<int>((it[i].c[ax] - clo[ax]) * scale[ax]);
+          b = std::min(std::max(b, 0), kBins - 1);
+          bb[ax][b].grow(it[i].box); ++cnt[ax][b];
+        }
+      }
+      int best_axis = -1, best_split = -1; float best_cost = std::numeric_limits<float>::infinity();
+      for (int ax = 0; ax < 3; ++ax) {
+        if (!(scale[ax] > 0.0f)) continue;
+        Box3 rbox[kBins]; uint32_t rcnt[kBins];
+        Box3 acc; acc.reset(); uint32_t c = 0;
+        for (int b = kBins - 1; b > 0; --b) { acc.grow(bb[ax][b]); c += cnt[ax][b]; rbox[b] = acc; rcnt[b] = c; }
+        acc.reset(); c = 0;
+        for (int b = 0; b < kBins - 1; ++b) {
+          acc.grow(bb[ax][b]); c += cnt[ax][b];
+          if (c == 0 || rcnt[b + 1] == 0) continue;
+          const float cost = area_of(acc) * static_cast<float>(c) + area_of(rbox[b + 1]) * static_cast<float>(rcnt[b + 1]);
+          if (cost < best_cost) { best_cost = cost; best_axis = ax; best_split = b; lb = acc; rb = rbox[b + 1]; }
+        }
+      }
+      if (best_axis >= 0) {
+        const int ax = best_axis, sp = best_split;
+        const float lo = clo[ax], sc = scale[ax];
+        Item* m = std::partition(it + begin, it + end, [=](const Item& a) {
+          int b = static_cast<int>((a.c[ax] - lo) * sc);
+          b = std::min(std::max(b, 0), kBins - 1);
+          return b <= sp;
+        });
+        mid = static_cast<size_t>(m - it);
+      }
+      if (best_axis < 0 || mid == begin || mid == end) {  // coincident centroids: split the list in half
+        mid = begin + n / 2;
+        lb.reset(); rb.reset();
+        for (size_t i = begin; i < mid; ++i) lb.grow(it[i].box);
+        for (size_t i = mid; i < end; ++i) rb.grow(it[i].box);
+      }
+    }
+    const size_t nl = mid - begin;
+    const size_t left_idx = idx + 1, right_idx = idx + 1 + (nl > 1 ? nl - 1 : 0);
+    PackedNode nd{};
+    set_child(nd, 0, lb, direct_child_code(left_idx, begin, mid));
+    set_child(nd, 1, rb, direct_child_code(right_idx, mid, end));
+    nodes_[idx] = nd;
+    // big subtrees go to other threads (disjoint item and node ranges)
+    std::future<void> task;
+    if (nl > 1) {
+      if (n > 65536 && depth < 8) task = std::async(std::launch::async, [=] { direct_node(left_idx, begin, mid, depth + 1); });
+      else direct_node(left_idx, begin, mid, depth + 1);
+    }
+    if (end - mid > 1) direct_node(right_idx, mid, end, depth + 1);
+    if (task.valid()) task.get();
+  }
+  std::vector<Item> items_;
 
   static void pad(Box3& b) {  // conservative against the fp32 slab arithmetic
     for (int k = 0; k < 3; ++k) {
