@@ -149,6 +149,16 @@ RTW_API int rtw_debug_scatter(int32_t device, int64_t n, const rtw_material* mat
                       uint8_t* scattered);
 RTW_API int rtw_debug_samples(int32_t device, int64_t n, uint64_t seed, float* ball, float* disk, float* u01);
 
+/* Host-only view of what rtw_scene_upload builds (no CUDA call): table sizes, BVH shape and build time.  Lets CPU-only
+ * tests check the flattening of the primitive list (north_star item 1) and the tree invariants. */
+typedef struct rtw_flatten_report {
+  int32_t n_static_spheres, n_moving_spheres, n_big_spheres, n_triangles;
+  int32_t n_bvh_nodes, bvh_max_depth, leaf_direct, reserved;
+  int64_t arena_bytes, bvh_errors; /* bvh_errors: primitives missing from / duplicated in the tree (must be 0) */
+  double flatten_ms, bvh_build_ms;
+} rtw_flatten_report;
+RTW_API int rtw_flatten_info(const rtw_scene_desc* desc, rtw_flatten_report* out);
+
 /* FP32 FFMA micro-benchmark: sustained TFLOP/s (2 flop per FMA) and the SM clock seen, the denominator of the
  * sphere-scene roofline (MEASURED_PEAKS.json carries only HBM and bf16 figures). */
 RTW_API int rtw_fp32_peak(int32_t device, double seconds, double* tflops, double* sm_mhz);

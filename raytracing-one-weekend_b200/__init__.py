@@ -65,6 +65,15 @@ class RenderCfg(C.Structure):
                 ("flags", C.c_int32), ("rays_per_lane", C.c_int32), ("reserved", C.c_int32)]
 
 
+class FlattenReport(C.Structure):
+    _fields_ = [("n_static_spheres", C.c_int32), ("n_moving_spheres", C.c_int32), ("n_big_spheres", C.c_int32), ("n_triangles", C.c_int32),
+                ("n_bvh_nodes", C.c_int32), ("bvh_max_depth", C.c_int32), ("leaf_direct", C.c_int32), ("reserved", C.c_int32),
+                ("arena_bytes", C.c_int64), ("bvh_errors", C.c_int64), ("flatten_ms", C.c_double), ("bvh_build_ms", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 class Stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("sphere_tests", C.c_uint64),
                 ("sphere_candidates", C.c_uint64), ("tri_tests", C.c_uint64), ("node_visits", C.c_uint64),
@@ -99,6 +108,7 @@ ABI = {
                                    C.c_int32, _VP, _VP, _VP, _VP]),
     "rtw_debug_scatter": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(Material), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "rtw_debug_samples": (C.c_int, [C.c_int32, C.c_int64, C.c_uint64, _VP, _VP, _VP]),
+    "rtw_flatten_info": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(FlattenReport)]),
     "rtw_fp32_peak": (C.c_int, [C.c_int32, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
@@ -343,6 +353,14 @@ def debug_samples(n: int, seed: int = 0, device: int = 0):
     _check(lib().rtw_debug_samples(device, n, seed, ball.ctypes.data_as(_VP), disk.ctypes.data_as(_VP),
                                    u.ctypes.data_as(_VP)), "rtw_debug_samples")
     return ball, disk, u
+
+
+def flatten_info(scene: "Scene") -> dict:
+    """rtw_flatten_info: the host-side flatten + BVH build of rtw_scene_upload, without touching a GPU."""
+    d = scene.desc()
+    r = FlattenReport()
+    _check(lib().rtw_flatten_info(C.byref(d), C.byref(r)), "rtw_flatten_info")
+    return r.as_dict()
 
 
 def fp32_peak(device: int = 0, seconds: float = 1.0):

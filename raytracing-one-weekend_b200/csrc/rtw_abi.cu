@@ -70,6 +70,7 @@ struct rtw_scene {
   int device = 0;
   int sm_count = 0;
   DevBuf<unsigned char> arena;  // every table of the scene in ONE allocation, filled by ONE host-to-device copy
+  unsigned char* arena_ptr = nullptr;  // = arena.p, or memory borrowed from rtw_render's per-device cache
   unsigned long long* counters = nullptr;
   size_t n_leaf_refs = 0;
   rtw::DevScene dev{};
@@ -80,24 +81,20 @@ struct rtw_scene {
 
 namespace {
 
-// Flatten (north_star item 1): variant/virtual primitive list -> device SoA.
-int flatten_and_upload(const rtw_scene_desc* desc, int device, rtw_scene* sc) {
+// Flatten (north_star item 1): variant/virtual primitive list -> SoA tables, BVH, materials, all in one host arena whose
+// layout is the device layout.  Pure host code: no CUDA call in here (rtw_flatten_info exposes it to CPU-only tests).
+struct HostFlat {
+  std::vector<unsigned char> host;
+  size_t o_sA = 0, o_sB = 0, o_sId = 0, o_big = 0, o_tri = 0, o_triId = 0, o_nodes = 0, o_refs = 0, o_matA = 0, o_matB = 0, o_ctr = 0;
+  int32_t n_static = 0, n_moving = 0, n_big = 0, n_tri = 0, n_nodes = 0, leaf_direct = 0;
+  size_t n_leaf_refs = 0;
+  double bvh_ms = 0.0;
+};
+
+int flatten_host(const rtw_scene_desc* desc, HostFlat* hf) {
   if (!desc || desc->nprims < 0 || desc->nmats < 0 || (desc->nprims > 0 && !desc->prims) || (desc->nmats > 0 && !desc->mats))
     return fail("rtw_scene_upload: invalid scene description");
   if (desc->nprims >= (1ll << 28)) return fail("rtw_scene_upload: too many primitives");
-  int ndev = 0;
-  cudaError_t e = cudaGetDeviceCount(&ndev);
-  if (e != cudaSuccess) return fail_cuda("cudaGetDeviceCount (no CUDA device: this library has no CPU fallback)", e);
-  if (device < 0 || device >= ndev) return fail("rtw_scene_upload: device ordinal out of range");
-  RTW_CUDA(cudaSetDevice(device));
-  int cc_major = 0, sm_count = 0;
-  RTW_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
-  RTW_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
-  if (cc_major < 10) return fail("rtw_b200 kernels are built for sm_100a only; this device has an older compute capability");
-  sc->device = device;
-  sc->sm_count = sm_count;
-  sc->nprims = desc->nprims;
-
   std::vector<float4> sA_static, sB_static, sA_moving, sB_moving;
   std::vector<int2> id_static, id_moving;
   std::vector<rtw::BigSphere> big;
@@ -183,7 +180,9 @@ int flatten_and_upload(const rtw_scene_desc* desc, int device, rtw_scene* sc) {
   }
   rtw::BvhBuilder builder;
   if (const char* e = std::getenv("RTW_BVH_LEAF")) builder.kMaxLeaf = std::min(std::max(std::atoi(e), 1), 31);  // tuning knob
+  const double t_bvh = now_ms();
   builder.build(boxes, refs);
+  hf->bvh_ms = now_ms() - t_bvh;
   std::vector<float4> nodes(builder.nodes().size() * 4);
   if (!nodes.empty()) std::memcpy(nodes.data(), builder.nodes().data(), nodes.size() * sizeof(float4));
 
@@ -198,7 +197,8 @@ int flatten_and_upload(const rtw_scene_desc* desc, int device, rtw_scene* sc) {
   }
 
   // ---- one arena, one copy ---------------------------------------------------------------------------------------------
-  std::vector<unsigned char> host;
+  std::vector<unsigned char>& host = hf->host;
+  host.clear();
   auto put = [&host](const void* src, size_t bytes) {
     const size_t off = (host.size() + 255) & ~size_t(255);
     host.resize(off + bytes);
@@ -214,22 +214,56 @@ int flatten_and_upload(const rtw_scene_desc* desc, int device, rtw_scene* sc) {
                o_matA = put(matA.data(), matA.size() * sizeof(float4)), o_matB = put(matB.data(), matB.size() * sizeof(float2)),
                o_ctr = put(zero_counters, sizeof zero_counters);
   host.resize((host.size() + 255) & ~size_t(255));
-  RTW_CUDA(sc->arena.alloc(host.size()));
-  RTW_CUDA(cudaMemcpy(sc->arena.p, host.data(), host.size(), cudaMemcpyHostToDevice));
-  unsigned char* base = sc->arena.p;
+  hf->o_sA = o_sA; hf->o_sB = o_sB; hf->o_sId = o_sId; hf->o_big = o_big; hf->o_tri = o_tri; hf->o_triId = o_triId; hf->o_nodes = o_nodes;
+  hf->o_refs = o_refs; hf->o_matA = o_matA; hf->o_matB = o_matB; hf->o_ctr = o_ctr;
+  hf->n_static = static_cast<int32_t>(sA_static.size()); hf->n_moving = static_cast<int32_t>(sA_moving.size());
+  hf->n_big = static_cast<int32_t>(big.size()); hf->n_tri = static_cast<int32_t>(triId.size());
+  hf->n_nodes = static_cast<int32_t>(builder.nodes().size()); hf->leaf_direct = builder.kMaxLeaf == 1 ? 1 : 0;
+  hf->n_leaf_refs = builder.leaf_refs().size();
+  return 0;
+}
+
+int flatten_and_upload(const rtw_scene_desc* desc, int device, rtw_scene* sc, DevBuf<unsigned char>* borrowed = nullptr) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess) return fail_cuda("cudaGetDeviceCount (no CUDA device: this library has no CPU fallback)", e);
+  if (device < 0 || device >= ndev) return fail("rtw_scene_upload: device ordinal out of range");
+  RTW_CUDA(cudaSetDevice(device));
+  int cc_major = 0, sm_count = 0;
+  RTW_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+  RTW_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+  if (cc_major < 10) return fail("rtw_b200 kernels are built for sm_100a only; this device has an older compute capability");
+  sc->device = device;
+  sc->sm_count = sm_count;
+
+  sc->nprims = desc ? desc->nprims : 0;
+  HostFlat hf;
+  if (int rc = flatten_host(desc, &hf)) return rc;
+  const std::vector<unsigned char>& host = hf.host;
+  const size_t o_sA = hf.o_sA, o_sB = hf.o_sB, o_sId = hf.o_sId, o_big = hf.o_big, o_tri = hf.o_tri, o_triId = hf.o_triId, o_nodes = hf.o_nodes,
+               o_refs = hf.o_refs, o_matA = hf.o_matA, o_matB = hf.o_matB, o_ctr = hf.o_ctr;
+  if (borrowed) {  // grow-only buffer owned by the caller (rtw_render's cache): no allocation in the steady state
+    if (borrowed->n < host.size()) RTW_CUDA(borrowed->alloc(host.size() + host.size() / 8));
+    sc->arena_ptr = borrowed->p;
+  } else {
+    RTW_CUDA(sc->arena.alloc(host.size()));
+    sc->arena_ptr = sc->arena.p;
+  }
+  RTW_CUDA(cudaMemcpy(sc->arena_ptr, host.data(), host.size(), cudaMemcpyHostToDevice));
+  unsigned char* base = sc->arena_ptr;
   sc->counters = reinterpret_cast<unsigned long long*>(base + o_ctr);
-  sc->n_leaf_refs = builder.leaf_refs().size();
+  sc->n_leaf_refs = hf.n_leaf_refs;
 
   rtw::DevScene& d = sc->dev;
   d.sphA = reinterpret_cast<const float4*>(base + o_sA); d.sphB = reinterpret_cast<const float4*>(base + o_sB);
   d.sphId = reinterpret_cast<const int2*>(base + o_sId);
-  d.n_static = static_cast<int32_t>(sA_static.size()); d.n_moving = static_cast<int32_t>(sA_moving.size());
-  d.big = reinterpret_cast<const rtw::BigSphere*>(base + o_big); d.n_big = static_cast<int32_t>(big.size());
+  d.n_static = hf.n_static; d.n_moving = hf.n_moving;
+  d.big = reinterpret_cast<const rtw::BigSphere*>(base + o_big); d.n_big = hf.n_big;
   d.tri = reinterpret_cast<const float4*>(base + o_tri); d.triId = reinterpret_cast<const int2*>(base + o_triId);
-  d.n_tri = static_cast<int32_t>(triId.size());
+  d.n_tri = hf.n_tri;
   d.nodes = reinterpret_cast<const float4*>(base + o_nodes); d.leafRefs = reinterpret_cast<const uint32_t*>(base + o_refs);
-  d.n_nodes = static_cast<int32_t>(builder.nodes().size());
-  d.leaf_direct = builder.kMaxLeaf == 1 ? 1 : 0;
+  d.n_nodes = hf.n_nodes;
+  d.leaf_direct = hf.leaf_direct;
   d.matA = reinterpret_cast<const float4*>(base + o_matA); d.matB = reinterpret_cast<const float2*>(base + o_matB);
   const rtw_camera& c = desc->camera;
   for (int k = 0; k < 3; ++k) {
@@ -238,8 +272,8 @@ int flatten_and_upload(const rtw_scene_desc* desc, int device, rtw_scene* sc) {
     d.cam.u[k] = (float)c.u[k]; d.cam.v[k] = (float)c.v[k];
   }
   d.cam.lens_radius = (float)c.lens_radius; d.cam.t0 = (float)c.t0; d.cam.t1 = (float)c.t1;
-  sc->has_triangles = !triId.empty();
-  sc->smem_bytes = 16 + (sA.size() + 1) * 32;
+  sc->has_triangles = hf.n_tri > 0;
+  sc->smem_bytes = 16 + (static_cast<size_t>(hf.n_static + hf.n_moving) + 1) * 32;
   return 0;
 }
 
@@ -313,6 +347,45 @@ int rtw_device_count(int* count) {
   return 0;
 }
 
+int rtw_flatten_info(const rtw_scene_desc* desc, rtw_flatten_report* out) {
+  if (!out) return fail("rtw_flatten_info: null output");
+  HostFlat hf;
+  const double t0 = now_ms();
+  if (int rc = flatten_host(desc, &hf)) return rc;
+  out->n_static_spheres = hf.n_static; out->n_moving_spheres = hf.n_moving; out->n_big_spheres = hf.n_big; out->n_triangles = hf.n_tri;
+  out->n_bvh_nodes = hf.n_nodes; out->leaf_direct = hf.leaf_direct; out->arena_bytes = static_cast<int64_t>(hf.host.size());
+  out->flatten_ms = now_ms() - t0; out->bvh_build_ms = hf.bvh_ms;
+  // structural self-check of the tree: every primitive referenced exactly once, child boxes inside the parent box
+  const rtw::PackedNode* nodes = reinterpret_cast<const rtw::PackedNode*>(hf.host.data() + hf.o_nodes);
+  const uint32_t* refs = reinterpret_cast<const uint32_t*>(hf.host.data() + hf.o_refs);
+  std::vector<uint8_t> seen(static_cast<size_t>(hf.n_static + hf.n_moving) + static_cast<size_t>(hf.n_tri), 0);
+  int64_t dup = 0, depth_max = 0;
+  std::vector<std::pair<int32_t, int>> todo;
+  if (hf.n_nodes > 0) todo.push_back({0, 1});
+  auto visit_ref = [&](uint32_t ref) {
+    const size_t idx = (ref >> 30) ? static_cast<size_t>(hf.n_static + hf.n_moving) + (ref & 0x1fffffffu) : (ref & 0x1fffffffu);
+    if (idx >= seen.size() || seen[idx]++) ++dup;
+  };
+  while (!todo.empty()) {
+    auto [n, dpt] = todo.back(); todo.pop_back();
+    depth_max = std::max<int64_t>(depth_max, dpt);
+    for (int which = 0; which < 2; ++which) {
+      const int32_t code = which == 0 ? nodes[n].left : nodes[n].right;
+      if (code >= 0) { todo.push_back({code, dpt + 1}); continue; }
+      if (which == 1 && seen.size() <= static_cast<size_t>(hf.leaf_direct ? 1 : 31) && hf.n_nodes == 1 && nodes[n].rmin_z > nodes[n].rmax[2])
+        continue;  // the never-entered filler child of a single-leaf tree (inverted box)
+      const uint32_t v = static_cast<uint32_t>(~code);
+      if (hf.leaf_direct) visit_ref(v);
+      else for (uint32_t k = 0; k < (v & 31u); ++k) visit_ref(refs[(v >> 5) + k]);
+    }
+  }
+  int64_t missing = 0;
+  for (uint8_t c : seen) if (!c) ++missing;
+  out->bvh_max_depth = static_cast<int32_t>(depth_max);
+  out->bvh_errors = dup + missing;
+  return 0;
+}
+
 int rtw_scene_upload(const rtw_scene_desc* desc, int32_t device, rtw_scene** out) {
   if (!out) return fail("rtw_scene_upload: null output");
   *out = nullptr;
@@ -380,6 +453,7 @@ namespace {
 struct RenderCache {
   DevBuf<long long> fx;
   DevBuf<float> out;
+  DevBuf<unsigned char> arena;
   size_t npix = 0;
 };
 std::mutex g_cache_mutex;
@@ -400,15 +474,15 @@ int rtw_render(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, float* acc
   if (!desc || !cfg || !accum_rgba) return fail("rtw_render: null argument");
   if (cfg->width < 2 || cfg->height < 2) return fail("render: width and height must be >= 2 (pixel mapping divides by W-1, H-1)");
   const double t_start = now_ms();
-  rtw_scene* sc = nullptr;
-  if (int rc = rtw_scene_upload(desc, cfg->device, &sc)) return rc;
-  struct Guard { rtw_scene* s; ~Guard() { rtw_scene_free(s); } } guard{sc};
-  const double t_up = now_ms();
-  const size_t npix = static_cast<size_t>(cfg->width) * static_cast<size_t>(cfg->height);
   std::lock_guard<std::mutex> lock(g_cache_mutex);  // also serialises host-buffer renders per process (not re-entrant per device)
-  if (cfg->device >= 64) return fail("rtw_render: device ordinal out of range");
+  if (cfg->device < 0 || cfg->device >= 64) return fail("rtw_render: device ordinal out of range");
   if (!g_cache[cfg->device]) g_cache[cfg->device] = new RenderCache();
   RenderCache& rc_ = *g_cache[cfg->device];
+  rtw_scene scene_obj;
+  rtw_scene* sc = &scene_obj;
+  if (int rc = flatten_and_upload(desc, cfg->device, sc, &rc_.arena)) return rc;
+  const double t_up = now_ms();
+  const size_t npix = static_cast<size_t>(cfg->width) * static_cast<size_t>(cfg->height);
   if (rc_.npix < npix) {
     RTW_CUDA(rc_.fx.alloc(npix * 4));
     RTW_CUDA(rc_.out.alloc(npix * 4));

@@ -510,14 +510,15 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
   const DevScene& sc = p.sc;
   BvhTables tb{sc.nodes, sc.leafRefs, sc.sphA, sc.sphB, sc.tri};
   if (SMEM) {
-    // segment sizes (bytes, multiples of 16) in the order nodes, leafRefs, sphA, sphB, tri
+    // nodes, leafRefs, sphA, sphB, tri back to back (every size a multiple of 16 bytes), one mbarrier for all copies
     const uint32_t nspheres = static_cast<uint32_t>(sc.n_static + sc.n_moving);
-    const uint32_t bytes[5] = {static_cast<uint32_t>(sc.n_nodes) * 64u, (static_cast<uint32_t>(p.n_leaf_refs) * 4u + 15u) & ~15u, nspheres * 16u,
-                               nspheres * 16u, static_cast<uint32_t>(sc.n_tri) * 48u};
-    const void* src[5] = {sc.nodes, sc.leafRefs, sc.sphA, sc.sphB, sc.tri};
-    unsigned char* dst[5];
-    unsigned char* cur = smem_raw + 16;
-    for (int k = 0; k < 5; ++k) { dst[k] = cur; cur += bytes[k]; }
+    const uint32_t b_nodes = static_cast<uint32_t>(sc.n_nodes) * 64u, b_refs = (p.n_leaf_refs * 4u + 15u) & ~15u, b_sph = nspheres * 16u,
+                   b_tri = static_cast<uint32_t>(sc.n_tri) * 48u;
+    unsigned char* d_nodes = smem_raw + 16;
+    unsigned char* d_refs = d_nodes + b_nodes;
+    unsigned char* d_sa = d_refs + b_refs;
+    unsigned char* d_sb = d_sa + b_sph;
+    unsigned char* d_tri = d_sb + b_sph;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     if (threadIdx.x == 0) {
       mbar_init(bar, 1);
@@ -525,23 +526,24 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      uint32_t total = 0;
-      for (int k = 0; k < 5; ++k) total += bytes[k];
-      mbar_expect_tx(bar, total);
-      constexpr uint32_t kChunk = 32768u;
-      for (int k = 0; k < 5; ++k)
-        for (uint32_t off = 0; off < bytes[k]; off += kChunk)
-          tma_bulk_g2s(dst[k] + off, static_cast<const unsigned char*>(src[k]) + off, min(kChunk, bytes[k] - off), bar);
+      mbar_expect_tx(bar, b_nodes + b_refs + 2u * b_sph + b_tri);
+      auto copy = [&](unsigned char* dst, const void* src, uint32_t bytes) {
+        constexpr uint32_t kChunk = 32768u;
+        for (uint32_t off = 0; off < bytes; off += kChunk)
+          tma_bulk_g2s(dst + off, static_cast<const unsigned char*>(src) + off, min(kChunk, bytes - off), bar);
+      };
+      copy(d_nodes, sc.nodes, b_nodes); copy(d_refs, sc.leafRefs, b_refs); copy(d_sa, sc.sphA, b_sph); copy(d_sb, sc.sphB, b_sph);
+      copy(d_tri, sc.tri, b_tri);
     }
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, 0)) {
       if (++spins > (1u << 26)) __trap();
     }
-    tb.nodes = reinterpret_cast<const float4*>(dst[0]);
-    tb.leafRefs = reinterpret_cast<const uint32_t*>(dst[1]);
-    tb.sphA = reinterpret_cast<const float4*>(dst[2]);
-    tb.sphB = reinterpret_cast<const float4*>(dst[3]);
-    tb.tri = reinterpret_cast<const float4*>(dst[4]);
+    tb.nodes = reinterpret_cast<const float4*>(d_nodes);
+    tb.leafRefs = reinterpret_cast<const uint32_t*>(d_refs);
+    tb.sphA = reinterpret_cast<const float4*>(d_sa);
+    tb.sphB = reinterpret_cast<const float4*>(d_sb);
+    tb.tri = reinterpret_cast<const float4*>(d_tri);
   }
 
   const uint32_t lane = threadIdx.x & 31u;

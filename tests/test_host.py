@@ -175,3 +175,51 @@ def test_sample_shard(rtw):
     assert [rtw.sample_shard(12, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 12)]
     with pytest.raises(ValueError):
         rtw.sample_shard(20, 0, 8)
+
+
+def test_flatten_tables_and_bvh_invariants(rtw, tmp_path):
+    """north_star item 1 on the CPU: the primitive list flattened into sphere / big-sphere / triangle tables and a BVH in
+    which every primitive appears exactly once (rtw_flatten_info runs the host half of rtw_scene_upload, no GPU)."""
+    r = rtw.flatten_info(rtw.cover_scene())
+    assert (r["n_static_spheres"], r["n_moving_spheres"], r["n_big_spheres"], r["n_triangles"]) == (95, 389, 1, 0)
+    assert r["n_bvh_nodes"] == 483 and r["leaf_direct"] == 1 and r["bvh_errors"] == 0 and r["bvh_max_depth"] <= 16
+    r = rtw.flatten_info(rtw.cover_scene(11, 1.5, False))
+    assert (r["n_static_spheres"], r["n_moving_spheres"], r["n_big_spheres"]) == (484, 0, 1)
+    r = rtw.flatten_info(rtw.obj_scene(SUZANNE))
+    assert r["n_triangles"] == 968 and r["n_bvh_nodes"] == 967 and r["bvh_errors"] == 0
+    r = rtw.flatten_info(rtw.mesh_on_ground_scene(SUZANNE))
+    assert r["n_triangles"] == 968 and r["n_big_spheres"] == 1 and r["bvh_errors"] == 0
+    cam = dict(lookfrom=(0, 0, 0), lookat=(0, 0, -1), vup=(0, 1, 0), vfov=60.0, aspect=1.0, aperture=0.0, focus_dist=1.0)
+    mats = np.zeros(1, rtw.MAT_DTYPE)
+    for n in (0, 1, 2, 3, 9, 100):
+        prims = np.zeros(n, rtw.PRIM_DTYPE)
+        prims["a"] = prims["b"] = np.random.default_rng(n).uniform(-5, 5, (n, 3))
+        prims["radius"] = 0.3
+        prims["kind"][: n // 2] = rtw.RTW_MOVING_SPHERE
+        prims["b"][: n // 2] += 0.5
+        r = rtw.flatten_info(rtw.custom_scene(prims, mats, **cam))
+        assert r["bvh_errors"] == 0 and r["n_bvh_nodes"] == max(n - 1, 1 if n else 0)
+        assert r["n_static_spheres"] + r["n_moving_spheres"] == n and r["n_moving_spheres"] == n // 2
+    # coincident primitives (all centroids equal) must still build a finite tree
+    prims = np.zeros(50, rtw.PRIM_DTYPE); prims["radius"] = 1.0
+    r = rtw.flatten_info(rtw.custom_scene(prims, mats, **cam))
+    assert r["bvh_errors"] == 0 and r["bvh_max_depth"] <= 50
+    # the multi-primitive leaf layout (tuning knob) keeps the same invariants
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent(f"""
+        import importlib, sys
+        sys.path.insert(0, {str(ROOT)!r})
+        rtw = importlib.import_module("raytracing-one-weekend_b200")
+        r = rtw.flatten_info(rtw.cover_scene())
+        assert r["leaf_direct"] == 0 and r["bvh_errors"] == 0 and r["n_bvh_nodes"] < 300, r
+    """)
+    subprocess.run([sys.executable, "-c", code], check=True, env={**os.environ, "RTW_BVH_LEAF": "4"})
+    # errors
+    bad = rtw.cover_scene(1)
+    bad.prims["material"][0] = 99
+    with pytest.raises(rtw.RtwError, match="material"):
+        rtw.flatten_info(bad)
+    bad = rtw.cover_scene(1)
+    bad.prims["kind"][0] = 7
+    with pytest.raises(rtw.RtwError, match="primitive kind"):
+        rtw.flatten_info(bad)
