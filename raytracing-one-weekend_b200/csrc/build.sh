@@ -11,9 +11,10 @@ for f in rtw_kernels.cu rtw_abi.cu rtw_multi.cu rtw_device.cuh rtw_internal.h rt
 done
 if [ "$newer" = 0 ] && [ "${1:-}" != "-f" ]; then echo "librtw_b200.so up to date"; exit 0; fi
 mkdir -p ../build
-$NVCC $FLAGS ${RTW_PTXAS_V:+-Xptxas -v} -c rtw_kernels.cu -o ../build/rtw_kernels.o &
-$NVCC $FLAGS -c rtw_abi.cu -o ../build/rtw_abi.o &
-$NVCC $FLAGS -c rtw_multi.cu -o ../build/rtw_multi.o &
-wait
+rm -f ../build/rtw_kernels.o ../build/rtw_abi.o ../build/rtw_multi.o
+$NVCC $FLAGS ${RTW_PTXAS_V:+-Xptxas -v} -c rtw_kernels.cu -o ../build/rtw_kernels.o & p1=$!
+$NVCC $FLAGS -c rtw_abi.cu -o ../build/rtw_abi.o & p2=$!
+$NVCC $FLAGS -c rtw_multi.cu -o ../build/rtw_multi.o & p3=$!
+wait $p1; wait $p2; wait $p3   # each wait returns that compiler's status; set -e stops on the first failure
 $NVCC -shared -o $OUT ../build/rtw_kernels.o ../build/rtw_abi.o ../build/rtw_multi.o -lcudart_static -ldl -lpthread -lrt
 echo "built $OUT"

@@ -6,8 +6,12 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <array>
 #include <cstring>
+#include <future>
+#include <memory>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -83,143 +87,185 @@ namespace {
 
 // Flatten (north_star item 1): variant/virtual primitive list -> SoA tables, BVH, materials, all in one host arena whose
 // layout is the device layout.  Pure host code: no CUDA call in here (rtw_flatten_info exposes it to CPU-only tests).
+// Two passes over the primitive list, both split over host threads for large scenes: (1) classify + count + scene bound,
+// (2) write every table entry and BVH build record straight into its final place (insertion order is kept per table).
 struct HostFlat {
-  std::vector<unsigned char> host;
+  std::unique_ptr<unsigned char[]> host;
+  size_t bytes = 0;
   size_t o_sA = 0, o_sB = 0, o_sId = 0, o_big = 0, o_tri = 0, o_triId = 0, o_nodes = 0, o_refs = 0, o_matA = 0, o_matB = 0, o_ctr = 0;
   int32_t n_static = 0, n_moving = 0, n_big = 0, n_tri = 0, n_nodes = 0, leaf_direct = 0;
   size_t n_leaf_refs = 0;
   double bvh_ms = 0.0;
 };
 
+enum : uint8_t { kClsStatic = 0, kClsMoving = 1, kClsBig = 2, kClsTri = 3, kClsBadKind = 4, kClsBadMaterial = 5 };
+
+template <typename F>
+void parallel_chunks(int64_t n, int nchunks, F&& fn) {  // fn(chunk, begin, end)
+  if (nchunks <= 1) { fn(0, int64_t(0), n); return; }
+  std::vector<std::future<void>> tasks;
+  for (int c = 1; c < nchunks; ++c) tasks.push_back(std::async(std::launch::async, [&fn, c, n, nchunks] { fn(c, n * c / nchunks, n * (c + 1) / nchunks); }));
+  fn(0, int64_t(0), n / nchunks);
+  for (auto& t : tasks) t.get();
+}
+
 int flatten_host(const rtw_scene_desc* desc, HostFlat* hf) {
   if (!desc || desc->nprims < 0 || desc->nmats < 0 || (desc->nprims > 0 && !desc->prims) || (desc->nmats > 0 && !desc->mats))
     return fail("rtw_scene_upload: invalid scene description");
   if (desc->nprims >= (1ll << 28)) return fail("rtw_scene_upload: too many primitives");
-  std::vector<float4> sA_static, sB_static, sA_moving, sB_moving;
-  std::vector<int2> id_static, id_moving;
-  std::vector<rtw::BigSphere> big;
-  std::vector<float4> tri;
-  std::vector<int2> triId;
+  const int64_t n = desc->nprims;
+  const int hw = static_cast<int>(std::max(1u, std::thread::hardware_concurrency()));
+  const int nchunks = n >= 65536 ? std::min(hw, 32) : 1;
 
-  // scene bound for the conservative slack of the reject test (see rtw_kernels.cu trace_spheres)
+  // ---- pass 1: classify, count per chunk, bound of the small primitives (slack of the sweep's reject test) -------------------
+  std::vector<uint8_t> cls(static_cast<size_t>(n));
+  struct ChunkInfo { int64_t cnt[4] = {0, 0, 0, 0}; double bound = 0.0; int bad = 0; };
+  std::vector<ChunkInfo> info(static_cast<size_t>(nchunks));
+  parallel_chunks(n, nchunks, [&](int c, int64_t begin, int64_t end) {
+    ChunkInfo ci;
+    for (int64_t i = begin; i < end; ++i) {
+      const rtw_primitive& P = desc->prims[i];
+      uint8_t k;
+      if (P.material < 0 || P.material >= desc->nmats) { k = kClsBadMaterial; ci.bad = std::max(ci.bad, 2); }
+      else if (P.kind == RTW_TRIANGLE) {
+        k = kClsTri;
+        for (int q = 0; q < 3; ++q) ci.bound = std::max({ci.bound, std::fabs(P.a[q]), std::fabs(P.b[q]), std::fabs(P.c[q])});
+      } else if (P.kind == RTW_SPHERE || P.kind == RTW_MOVING_SPHERE) {
+        if (std::fabs(P.radius) >= rtw::kBigRadius) k = kClsBig;
+        else {
+          const bool moving = P.kind == RTW_MOVING_SPHERE && (P.a[0] != P.b[0] || P.a[1] != P.b[1] || P.a[2] != P.b[2]);
+          k = moving ? kClsMoving : kClsStatic;
+          for (int q = 0; q < 3; ++q) {
+            ci.bound = std::max(ci.bound, std::fabs(P.a[q]) + std::fabs(P.radius));
+            if (moving) ci.bound = std::max(ci.bound, std::fabs(P.b[q]) + std::fabs(P.radius));
+          }
+        }
+      } else { k = kClsBadKind; ci.bad = std::max(ci.bad, 1); }
+      cls[static_cast<size_t>(i)] = k;
+      if (k < 4) ++ci.cnt[k];
+    }
+    info[static_cast<size_t>(c)] = ci;
+  });
   double bound = 0.0;
   for (int k = 0; k < 3; ++k) bound = std::max(bound, std::fabs(desc->camera.origin[k]));
-  for (int64_t i = 0; i < desc->nprims; ++i) {
-    const rtw_primitive& P = desc->prims[i];
-    if (P.material < 0 || P.material >= desc->nmats) return fail("rtw_scene_upload: primitive references a missing material");
-    if (P.kind == RTW_TRIANGLE) {
-      for (int k = 0; k < 3; ++k) bound = std::max({bound, std::fabs(P.a[k]), std::fabs(P.b[k]), std::fabs(P.c[k])});
-    } else if (P.kind == RTW_SPHERE || P.kind == RTW_MOVING_SPHERE) {
-      if (std::fabs(P.radius) >= rtw::kBigRadius) continue;
-      for (int k = 0; k < 3; ++k) {
-        bound = std::max(bound, std::fabs(P.a[k]) + std::fabs(P.radius));
-        if (P.kind == RTW_MOVING_SPHERE) bound = std::max(bound, std::fabs(P.b[k]) + std::fabs(P.radius));
-      }
-    } else {
-      return fail("rtw_scene_upload: unknown primitive kind");
-    }
+  int64_t total[4] = {0, 0, 0, 0};
+  std::vector<std::array<int64_t, 4>> start(static_cast<size_t>(nchunks));
+  for (int c = 0; c < nchunks; ++c) {
+    const ChunkInfo& ci = info[static_cast<size_t>(c)];
+    if (ci.bad == 2) return fail("rtw_scene_upload: primitive references a missing material");
+    if (ci.bad == 1) return fail("rtw_scene_upload: unknown primitive kind");
+    bound = std::max(bound, ci.bound);
+    for (int k = 0; k < 4; ++k) { start[static_cast<size_t>(c)][static_cast<size_t>(k)] = total[k]; total[k] += ci.cnt[k]; }
   }
+  for (int64_t i = 0; i < desc->nmats; ++i)
+    if (desc->mats[i].kind < RTW_LAMBERTIAN || desc->mats[i].kind > RTW_DIELECTRIC) return fail("rtw_scene_upload: unknown material kind");
   const double E = 24.0 * 1.1920929e-7 * bound;
+  const size_t n_static = static_cast<size_t>(total[kClsStatic]), n_moving = static_cast<size_t>(total[kClsMoving]),
+               n_big = static_cast<size_t>(total[kClsBig]), n_tri = static_cast<size_t>(total[kClsTri]);
+  const size_t n_small = n_static + n_moving, n_items = n_small + n_tri;
 
-  for (int64_t i = 0; i < desc->nprims; ++i) {
-    const rtw_primitive& P = desc->prims[i];
-    const int id = static_cast<int>(i);
-    if (P.kind == RTW_TRIANGLE) {
-      const double e1[3] = {P.b[0] - P.a[0], P.b[1] - P.a[1], P.b[2] - P.a[2]};
-      const double e2[3] = {P.c[0] - P.a[0], P.c[1] - P.a[1], P.c[2] - P.a[2]};
-      const double n[3] = {e1[1] * e2[2] - e2[1] * e1[2], e1[2] * e2[0] - e2[2] * e1[0], e1[0] * e2[1] - e2[0] * e1[1]};
-      tri.push_back(make_float4((float)P.a[0], (float)P.a[1], (float)P.a[2], (float)n[0]));
-      tri.push_back(make_float4((float)e1[0], (float)e1[1], (float)e1[2], (float)n[1]));
-      tri.push_back(make_float4((float)e2[0], (float)e2[1], (float)e2[2], (float)n[2]));
-      triId.push_back(make_int2(id, P.material));
-      continue;
-    }
-    const bool moving = P.kind == RTW_MOVING_SPHERE && (P.a[0] != P.b[0] || P.a[1] != P.b[1] || P.a[2] != P.b[2]);
-    const double dc[3] = {moving ? P.b[0] - P.a[0] : 0.0, moving ? P.b[1] - P.a[1] : 0.0, moving ? P.b[2] - P.a[2] : 0.0};
-    if (std::fabs(P.radius) >= rtw::kBigRadius) {
-      rtw::BigSphere b{};
-      for (int k = 0; k < 3; ++k) { b.c0[k] = P.a[k]; b.dc[k] = dc[k]; }
-      b.r = P.radius; b.prim_id = id; b.material = P.material;
-      big.push_back(b);
-      continue;
-    }
-    const double r = std::fabs(P.radius);
-    const float r2c = static_cast<float>((r * r + 3.0 * r * E + E * E) * (1.0 + 4e-7));
-    const float4 A = make_float4((float)P.a[0], (float)P.a[1], (float)P.a[2], r2c);
-    const float4 B = make_float4((float)dc[0], (float)dc[1], (float)dc[2], (float)P.radius);
-    if (moving) { sA_moving.push_back(A); sB_moving.push_back(B); id_moving.push_back(make_int2(id, P.material)); }
-    else { sA_static.push_back(A); sB_static.push_back(B); id_static.push_back(make_int2(id, P.material)); }
-  }
-  std::vector<float4> sA(sA_static), sB(sB_static);
-  std::vector<int2> sId(id_static);
-  sA.insert(sA.end(), sA_moving.begin(), sA_moving.end());
-  sB.insert(sB.end(), sB_moving.begin(), sB_moving.end());
-  sId.insert(sId.end(), id_moving.begin(), id_moving.end());
-
-  // BVH over small spheres (swept bounds for moving ones, common-model.cpp:197-207) and triangles
-  std::vector<rtw::Box3> boxes;
-  std::vector<uint32_t> refs;
-  boxes.reserve(sA.size() + triId.size());
-  for (size_t i = 0; i < sA.size(); ++i) {
-    const float r = std::fabs(sB[i].w);
-    const float c0[3] = {sA[i].x, sA[i].y, sA[i].z};
-    const float c1[3] = {sA[i].x + sB[i].x, sA[i].y + sB[i].y, sA[i].z + sB[i].z};
-    rtw::Box3 b;
-    for (int k = 0; k < 3; ++k) { b.lo[k] = std::min(c0[k], c1[k]) - r; b.hi[k] = std::max(c0[k], c1[k]) + r; }
-    boxes.push_back(b);
-    refs.push_back(static_cast<uint32_t>(i));
-  }
-  for (size_t i = 0; i < triId.size(); ++i) {
-    const float4 q0 = tri[3 * i], q1 = tri[3 * i + 1], q2 = tri[3 * i + 2];
-    const float a[3] = {q0.x, q0.y, q0.z};
-    const float b1[3] = {q0.x + q1.x, q0.y + q1.y, q0.z + q1.z};
-    const float c1[3] = {q0.x + q2.x, q0.y + q2.y, q0.z + q2.z};
-    rtw::Box3 b; b.reset(); b.grow(a); b.grow(b1); b.grow(c1);
-    boxes.push_back(b);
-    refs.push_back((1u << 30) | static_cast<uint32_t>(i));
-  }
   rtw::BvhBuilder builder;
   if (const char* e = std::getenv("RTW_BVH_LEAF")) builder.kMaxLeaf = std::min(std::max(std::atoi(e), 1), 31);  // tuning knob
-  const double t_bvh = now_ms();
-  builder.build(boxes, refs);
-  hf->bvh_ms = now_ms() - t_bvh;
-  std::vector<float4> nodes(builder.nodes().size() * 4);
-  if (!nodes.empty()) std::memcpy(nodes.data(), builder.nodes().data(), nodes.size() * sizeof(float4));
+  const bool direct = builder.kMaxLeaf == 1;
+  const size_t node_cap = std::max<size_t>(n_items, 1), ref_cap = direct ? 0 : n_items;
 
-  std::vector<float4> matA(static_cast<size_t>(desc->nmats));
-  std::vector<float2> matB(static_cast<size_t>(desc->nmats));
+  // ---- arena layout ----------------------------------------------------------------------------------------------------------------
+  size_t cursor = 0;
+  auto reserve = [&cursor](size_t bytes) { const size_t off = (cursor + 255) & ~size_t(255); cursor = off + bytes; return off; };
+  hf->o_sA = reserve(n_small * sizeof(float4)); hf->o_sB = reserve(n_small * sizeof(float4)); hf->o_sId = reserve(n_small * sizeof(int2));
+  hf->o_big = reserve(n_big * sizeof(rtw::BigSphere));
+  hf->o_tri = reserve(n_tri * 3 * sizeof(float4)); hf->o_triId = reserve(n_tri * sizeof(int2));
+  hf->o_nodes = reserve(node_cap * sizeof(rtw::PackedNode)); hf->o_refs = reserve(ref_cap * sizeof(uint32_t));
+  hf->o_matA = reserve(static_cast<size_t>(desc->nmats) * sizeof(float4)); hf->o_matB = reserve(static_cast<size_t>(desc->nmats) * sizeof(float2));
+  hf->o_ctr = reserve(rtw::kCtrCount * sizeof(unsigned long long));
+  hf->bytes = (cursor + 255) & ~size_t(255);
+  hf->host.reset(new unsigned char[hf->bytes]);
+  unsigned char* base = hf->host.get();
+  float4* sA = reinterpret_cast<float4*>(base + hf->o_sA);
+  float4* sB = reinterpret_cast<float4*>(base + hf->o_sB);
+  int2* sId = reinterpret_cast<int2*>(base + hf->o_sId);
+  rtw::BigSphere* big = reinterpret_cast<rtw::BigSphere*>(base + hf->o_big);
+  float4* tri = reinterpret_cast<float4*>(base + hf->o_tri);
+  int2* triId = reinterpret_cast<int2*>(base + hf->o_triId);
+  std::memset(base + hf->o_ctr, 0, rtw::kCtrCount * sizeof(unsigned long long));
+
+  // ---- pass 2: table entries and BVH build records (small spheres: swept bounds, common-model.cpp:197-207) ----------------------
+  std::vector<rtw::BvhBuilder::Item> items(n_items);
+  parallel_chunks(n, nchunks, [&](int c, int64_t begin, int64_t end) {
+    std::array<int64_t, 4> at = start[static_cast<size_t>(c)];
+    for (int64_t i = begin; i < end; ++i) {
+      const rtw_primitive& P = desc->prims[i];
+      const int id = static_cast<int>(i);
+      const uint8_t k = cls[static_cast<size_t>(i)];
+      if (k == kClsTri) {
+        const size_t t = static_cast<size_t>(at[kClsTri]++);
+        const double e1[3] = {P.b[0] - P.a[0], P.b[1] - P.a[1], P.b[2] - P.a[2]};
+        const double e2[3] = {P.c[0] - P.a[0], P.c[1] - P.a[1], P.c[2] - P.a[2]};
+        const double nn[3] = {e1[1] * e2[2] - e2[1] * e1[2], e1[2] * e2[0] - e2[2] * e1[0], e1[0] * e2[1] - e2[0] * e1[1]};
+        const float4 q0 = make_float4((float)P.a[0], (float)P.a[1], (float)P.a[2], (float)nn[0]);
+        const float4 q1 = make_float4((float)e1[0], (float)e1[1], (float)e1[2], (float)nn[1]);
+        const float4 q2 = make_float4((float)e2[0], (float)e2[1], (float)e2[2], (float)nn[2]);
+        tri[3 * t] = q0; tri[3 * t + 1] = q1; tri[3 * t + 2] = q2;
+        triId[t] = make_int2(id, P.material);
+        rtw::BvhBuilder::Item& it = items[n_small + t];
+        const float va[3] = {q0.x, q0.y, q0.z}, vb[3] = {q0.x + q1.x, q0.y + q1.y, q0.z + q1.z}, vc[3] = {q0.x + q2.x, q0.y + q2.y, q0.z + q2.z};
+        it.box.reset(); it.box.grow(va); it.box.grow(vb); it.box.grow(vc);
+        it.ref = (1u << 30) | static_cast<uint32_t>(t);
+        continue;
+      }
+      const bool moving = k == kClsMoving;
+      const double dc[3] = {P.kind == RTW_MOVING_SPHERE ? P.b[0] - P.a[0] : 0.0, P.kind == RTW_MOVING_SPHERE ? P.b[1] - P.a[1] : 0.0,
+                            P.kind == RTW_MOVING_SPHERE ? P.b[2] - P.a[2] : 0.0};
+      if (k == kClsBig) {
+        rtw::BigSphere bsp{};
+        for (int q = 0; q < 3; ++q) { bsp.c0[q] = P.a[q]; bsp.dc[q] = dc[q]; }
+        bsp.r = P.radius; bsp.prim_id = id; bsp.material = P.material;
+        big[static_cast<size_t>(at[kClsBig]++)] = bsp;
+        continue;
+      }
+      const size_t t = moving ? n_static + static_cast<size_t>(at[kClsMoving]++) : static_cast<size_t>(at[kClsStatic]++);
+      const double r = std::fabs(P.radius);
+      const float r2c = static_cast<float>((r * r + 3.0 * r * E + E * E) * (1.0 + 4e-7));
+      const float4 A = make_float4((float)P.a[0], (float)P.a[1], (float)P.a[2], r2c);
+      const float4 B = make_float4(moving ? (float)dc[0] : 0.0f, moving ? (float)dc[1] : 0.0f, moving ? (float)dc[2] : 0.0f, (float)P.radius);
+      sA[t] = A; sB[t] = B; sId[t] = make_int2(id, P.material);
+      rtw::BvhBuilder::Item& it = items[t];
+      const float rf = std::fabs(B.w);
+      const float c0[3] = {A.x, A.y, A.z}, c1[3] = {A.x + B.x, A.y + B.y, A.z + B.z};
+      for (int q = 0; q < 3; ++q) { it.box.lo[q] = std::min(c0[q], c1[q]) - rf; it.box.hi[q] = std::max(c0[q], c1[q]) + rf; }
+      it.ref = static_cast<uint32_t>(t);
+    }
+  });
+
+  // ---- BVH ---------------------------------------------------------------------------------------------------------------------------
+  const double t_bvh = now_ms();
+  rtw::PackedNode* nodes_out = reinterpret_cast<rtw::PackedNode*>(base + hf->o_nodes);
+  size_t n_nodes = 0, n_refs = 0;
+  if (direct) {
+    n_nodes = builder.build_items_direct(items, nodes_out);
+  } else {
+    std::vector<rtw::Box3> boxes(n_items);
+    std::vector<uint32_t> refs(n_items);
+    for (size_t i = 0; i < n_items; ++i) { boxes[i] = items[i].box; refs[i] = items[i].ref; }
+    builder.build(boxes, refs);
+    n_nodes = builder.nodes().size(); n_refs = builder.leaf_refs().size();
+    if (n_nodes) std::memcpy(nodes_out, builder.nodes().data(), n_nodes * sizeof(rtw::PackedNode));
+    if (n_refs) std::memcpy(base + hf->o_refs, builder.leaf_refs().data(), n_refs * sizeof(uint32_t));
+  }
+  hf->bvh_ms = now_ms() - t_bvh;
+
+  float4* matA = reinterpret_cast<float4*>(base + hf->o_matA);
+  float2* matB = reinterpret_cast<float2*>(base + hf->o_matB);
   for (int64_t i = 0; i < desc->nmats; ++i) {
     const rtw_material& m = desc->mats[i];
-    if (m.kind < RTW_LAMBERTIAN || m.kind > RTW_DIELECTRIC) return fail("rtw_scene_upload: unknown material kind");
     const double fuzz = std::min(std::max(m.fuzz, 0.0), 1.0);  // common-model.h:132-133,143-144
     matA[i] = make_float4((float)m.albedo[0], (float)m.albedo[1], (float)m.albedo[2], (float)fuzz);
     matB[i] = make_float2((float)m.ior, __int_as_float_host(m.kind));
   }
-
-  // ---- one arena, one copy ---------------------------------------------------------------------------------------------
-  std::vector<unsigned char>& host = hf->host;
-  host.clear();
-  auto put = [&host](const void* src, size_t bytes) {
-    const size_t off = (host.size() + 255) & ~size_t(255);
-    host.resize(off + bytes);
-    if (bytes) std::memcpy(host.data() + off, src, bytes);
-    return off;
-  };
-  const unsigned long long zero_counters[rtw::kCtrCount] = {};
-  const size_t o_sA = put(sA.data(), sA.size() * sizeof(float4)), o_sB = put(sB.data(), sB.size() * sizeof(float4)),
-               o_sId = put(sId.data(), sId.size() * sizeof(int2)), o_big = put(big.data(), big.size() * sizeof(rtw::BigSphere)),
-               o_tri = put(tri.data(), tri.size() * sizeof(float4)), o_triId = put(triId.data(), triId.size() * sizeof(int2)),
-               o_nodes = put(nodes.data(), nodes.size() * sizeof(float4)),
-               o_refs = put(builder.leaf_refs().data(), builder.leaf_refs().size() * sizeof(uint32_t)),
-               o_matA = put(matA.data(), matA.size() * sizeof(float4)), o_matB = put(matB.data(), matB.size() * sizeof(float2)),
-               o_ctr = put(zero_counters, sizeof zero_counters);
-  host.resize((host.size() + 255) & ~size_t(255));
-  hf->o_sA = o_sA; hf->o_sB = o_sB; hf->o_sId = o_sId; hf->o_big = o_big; hf->o_tri = o_tri; hf->o_triId = o_triId; hf->o_nodes = o_nodes;
-  hf->o_refs = o_refs; hf->o_matA = o_matA; hf->o_matB = o_matB; hf->o_ctr = o_ctr;
-  hf->n_static = static_cast<int32_t>(sA_static.size()); hf->n_moving = static_cast<int32_t>(sA_moving.size());
-  hf->n_big = static_cast<int32_t>(big.size()); hf->n_tri = static_cast<int32_t>(triId.size());
-  hf->n_nodes = static_cast<int32_t>(builder.nodes().size()); hf->leaf_direct = builder.kMaxLeaf == 1 ? 1 : 0;
-  hf->n_leaf_refs = builder.leaf_refs().size();
+  hf->n_static = static_cast<int32_t>(n_static); hf->n_moving = static_cast<int32_t>(n_moving);
+  hf->n_big = static_cast<int32_t>(n_big); hf->n_tri = static_cast<int32_t>(n_tri);
+  hf->n_nodes = static_cast<int32_t>(n_nodes); hf->leaf_direct = direct ? 1 : 0;
+  hf->n_leaf_refs = n_refs;
   return 0;
 }
 
@@ -239,17 +285,16 @@ int flatten_and_upload(const rtw_scene_desc* desc, int device, rtw_scene* sc, De
   sc->nprims = desc ? desc->nprims : 0;
   HostFlat hf;
   if (int rc = flatten_host(desc, &hf)) return rc;
-  const std::vector<unsigned char>& host = hf.host;
   const size_t o_sA = hf.o_sA, o_sB = hf.o_sB, o_sId = hf.o_sId, o_big = hf.o_big, o_tri = hf.o_tri, o_triId = hf.o_triId, o_nodes = hf.o_nodes,
                o_refs = hf.o_refs, o_matA = hf.o_matA, o_matB = hf.o_matB, o_ctr = hf.o_ctr;
   if (borrowed) {  // grow-only buffer owned by the caller (rtw_render's cache): no allocation in the steady state
-    if (borrowed->n < host.size()) RTW_CUDA(borrowed->alloc(host.size() + host.size() / 8));
+    if (borrowed->n < hf.bytes) RTW_CUDA(borrowed->alloc(hf.bytes + hf.bytes / 8));
     sc->arena_ptr = borrowed->p;
   } else {
-    RTW_CUDA(sc->arena.alloc(host.size()));
+    RTW_CUDA(sc->arena.alloc(hf.bytes));
     sc->arena_ptr = sc->arena.p;
   }
-  RTW_CUDA(cudaMemcpy(sc->arena_ptr, host.data(), host.size(), cudaMemcpyHostToDevice));
+  RTW_CUDA(cudaMemcpy(sc->arena_ptr, hf.host.get(), hf.bytes, cudaMemcpyHostToDevice));
   unsigned char* base = sc->arena_ptr;
   sc->counters = reinterpret_cast<unsigned long long*>(base + o_ctr);
   sc->n_leaf_refs = hf.n_leaf_refs;
@@ -353,11 +398,11 @@ int rtw_flatten_info(const rtw_scene_desc* desc, rtw_flatten_report* out) {
   const double t0 = now_ms();
   if (int rc = flatten_host(desc, &hf)) return rc;
   out->n_static_spheres = hf.n_static; out->n_moving_spheres = hf.n_moving; out->n_big_spheres = hf.n_big; out->n_triangles = hf.n_tri;
-  out->n_bvh_nodes = hf.n_nodes; out->leaf_direct = hf.leaf_direct; out->arena_bytes = static_cast<int64_t>(hf.host.size());
+  out->n_bvh_nodes = hf.n_nodes; out->leaf_direct = hf.leaf_direct; out->arena_bytes = static_cast<int64_t>(hf.bytes);
   out->flatten_ms = now_ms() - t0; out->bvh_build_ms = hf.bvh_ms;
   // structural self-check of the tree: every primitive referenced exactly once, child boxes inside the parent box
-  const rtw::PackedNode* nodes = reinterpret_cast<const rtw::PackedNode*>(hf.host.data() + hf.o_nodes);
-  const uint32_t* refs = reinterpret_cast<const uint32_t*>(hf.host.data() + hf.o_refs);
+  const rtw::PackedNode* nodes = reinterpret_cast<const rtw::PackedNode*>(hf.host.get() + hf.o_nodes);
+  const uint32_t* refs = reinterpret_cast<const uint32_t*>(hf.host.get() + hf.o_refs);
   std::vector<uint8_t> seen(static_cast<size_t>(hf.n_static + hf.n_moving) + static_cast<size_t>(hf.n_tri), 0);
   int64_t dup = 0, depth_max = 0;
   std::vector<std::pair<int32_t, int>> todo;

@@ -32,6 +32,7 @@ static_assert(sizeof(PackedNode) == 64, "node must be 64 bytes");
 
 class BvhBuilder {
  public:
+  struct Item { Box3 box; float c[3]; uint32_t ref; };  // one primitive: bounds, centroid, encoded reference
   int kMaxLeaf = 1;  // primitives per leaf (<= 31); 1 = primitive reference stored in the child code
   static constexpr int kBins = 16;
   // references are (kind << 30) | index with index < 2^28; bit 29 marks a direct leaf so that its code ~ref is never -1
@@ -69,6 +70,29 @@ class BvhBuilder {
 
   // a child that is never entered (inverted box); its code must still decode harmlessly
   int32_t empty_leaf() const { return kMaxLeaf == 1 ? static_cast<int32_t>(~kDirectMark) : ~0; }
+  // Same, for a caller that already holds the records and the destination of the nodes (max(n - 1, 1) entries):
+  // single-primitive leaves only.  `items` is reordered.  Returns the number of nodes written.
+  size_t build_items_direct(std::vector<Item>& items, PackedNode* out) {
+    const size_t n = items.size();
+    if (n == 0) return 0;
+    for (Item& it : items)
+      for (int k = 0; k < 3; ++k) it.c[k] = 0.5f * (it.box.lo[k] + it.box.hi[k]);
+    if (n == 1) {
+      PackedNode nd{};
+      set_child(nd, 0, items[0].box, static_cast<int32_t>(~(items[0].ref | kDirectMark)));
+      Box3 e; e.reset();
+      set_child(nd, 1, e, static_cast<int32_t>(~kDirectMark));
+      out[0] = nd;
+      return 1;
+    }
+    items_.swap(items);
+    ext_nodes_ = out;
+    direct_node(0, 0, n, 0);
+    ext_nodes_ = nullptr;
+    items_.swap(items);
+    return n - 1;
+  }
+
   const std::vector<PackedNode>& nodes() const { return nodes_; }
   const std::vector<uint32_t>& leaf_refs() const { return leaf_refs_; }
 
@@ -85,8 +109,6 @@ class BvhBuilder {
   // A subtree over m primitives has exactly m-1 inner nodes, so node indices can be assigned in preorder up front
   // (root = base, left subtree = base+1 ..., right subtree after it): deterministic layout, children next to their
   // parent, and disjoint index ranges that independent threads can fill without synchronisation.
-  struct Item { Box3 box; float c[3]; uint32_t ref; };
-
   void build_direct(const std::vector<Box3>& boxes, const std::vector<uint32_t>& refs) {
     const size_t n = boxes.size();
     items_.resize(n);
@@ -190,7 +212,7 @@ class BvhBuilder {
     PackedNode nd{};
     set_child(nd, 0, lb, direct_child_code(left_idx, begin, mid));
     set_child(nd, 1, rb, direct_child_code(right_idx, mid, end));
-    nodes_[idx] = nd;
+    (ext_nodes_ ? ext_nodes_ : nodes_.data())[idx] = nd;
     // big subtrees go to other threads (disjoint item and node ranges)
     std::future<void> task;
     if (nl > 1) {
@@ -201,6 +223,7 @@ class BvhBuilder {
     if (task.valid()) task.get();
   }
   std::vector<Item> items_;
+  PackedNode* ext_nodes_ = nullptr;
 
   static void pad(Box3& b) {  // conservative against the fp32 slab arithmetic
     for (int k = 0; k < 3; ++k) {
