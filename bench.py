@@ -54,6 +54,10 @@ def build_scene(rtw, name, wl):
             if rtw.host().rtwh_make_mesh(str(SUZANNE).encode(), path.encode(), a, 20221018, 0.08, C.byref(n)) != 0:
                 raise RuntimeError(rtw.host().rtwh_last_error().decode())
     return rtw.mesh_on_ground_scene(path, aspect)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the `ncu --set full` captures summarised
+# under profiles/ (r01_prof_k2_final.txt, r01_prof_k1_final.txt, r01_prof_k2_dragon.txt).  The traffic is the accumulation
+# buffer (66 MB at 1080p) being read after the memset and partly written back, plus the scene once: it does not scale with spp.
+NCU_TRAFFIC_BYTES = {("cover", "bvh"): 66.46e6 + 17.33e6, ("cover", "sweep"): 66.45e6 + 20.74e6, ("dragon", "bvh"): 286.38e6 + 70.87e6}
 # canonical FP32 flop costs of SURVEY.md 8(d) (FMA = 2)
 FLOP_STATIC_TEST, FLOP_MOVING_TEST, FLOP_HIT, FLOP_SHADE = 17.0, 23.0, 40.0, 80.0
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
@@ -200,7 +204,7 @@ def main() -> int:
     ap.add_argument("--rays-per-lane", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--traffic-bytes", type=float, default=None, help="dram bytes per launch of the render kernel from an ncu --set full capture")
+    ap.add_argument("--traffic-bytes", type=float, default=None, help="override: dram bytes per launch of the render kernel from an ncu --set full capture")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -356,6 +360,12 @@ def main() -> int:
     paths_gpu = paths_total / world
     peak_tflops, _ = rtw.fp32_peak(local_rank, 1.0)
     peak_note = "FFMA micro-benchmark (rtw_fp32_peak) measured in this run; MEASURED_PEAKS.json carries no FP32 figure; nominal %.1f" % NOMINAL_FP32_TFLOPS
+    def traffic(kernel_key):
+        if args.traffic_bytes is not None:
+            return args.traffic_bytes
+        fam = "cover" if args.workload.startswith("cover_1080p") else ("dragon" if args.workload.startswith("dragon") else None)
+        return NCU_TRAFFIC_BYTES.get((fam, kernel_key))
+
     moving_frac = n_moving / max(n_moving + n_static, 1)
     test_flop = FLOP_MOVING_TEST * moving_frac + FLOP_STATIC_TEST * (1 - moving_frac)
 
@@ -363,11 +373,11 @@ def main() -> int:
         flop = rays * ((n_static + n_big) * FLOP_STATIC_TEST + n_moving * FLOP_MOVING_TEST + FLOP_SHADE) + (rays - paths) * FLOP_HIT
         ach = flop / (ms * 1e-3) / 1e12
         return {"bound": "fp32_fma", "kernel": label, "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
-                "traffic": args.traffic_bytes, "peak_source": peak_note, "algorithmic_flop_per_launch": flop, "kernel_ms": ms,
+                "traffic": traffic("sweep"), "peak_source": peak_note, "algorithmic_flop_per_launch": flop, "kernel_ms": ms,
                 "flop_model": f"rays x (({n_static}+{n_big}) static x 17 + {n_moving} moving x 23 + 80) + hits x 40 (SURVEY 8(d))"}
 
     if kernel_used == rtw.KERNEL_SPHERES_SMEM:
-        roofline = sweep_roofline(kernel_ms, rays_gpu, paths_gpu, "k_render<2,0> (K1 shared-memory sphere sweep)")
+        roofline = sweep_roofline(kernel_ms, rays_gpu, paths_gpu, "k_render_sweep<2> (K1 shared-memory sphere sweep)")
     else:
         # per-ray work of the BVH kernel from an instrumented low-spp pass (the averages do not depend on spp)
         cs = min(8, s_end - s_begin)
@@ -378,12 +388,13 @@ def main() -> int:
         flop = rays_gpu * (nodes_pr * 24.0 + tests_pr * test_flop + tris_pr * 36.0 + n_big * FLOP_STATIC_TEST + FLOP_SHADE) + (rays_gpu - paths_gpu) * FLOP_HIT
         ach = flop / (kernel_ms * 1e-3) / 1e12
         roofline = {"bound": "fp32_fma", "kernel": "k_render_bvh (K2 resumable BVH traversal, tables in shared memory)", "achieved": ach,
-                    "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops, "traffic": args.traffic_bytes, "peak_source": peak_note,
+                    "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops, "traffic": traffic("bvh"), "peak_source": peak_note,
                     "algorithmic_flop_per_launch": flop, "kernel_ms": kernel_ms,
                     "per_ray": {"node_visits": nodes_pr, "sphere_tests": tests_pr, "triangle_tests": tris_pr},
                     "flop_model": "rays x (nodes x 2 boxes x 12 + sphere tests x 17|23 + triangle tests x 36 + big spheres x 17 + 80) + hits x 40 (SURVEY 8(d))",
                     "note": "culling removes ~97% of the sweep's flops, so the flop fraction is low by construction; what limits this kernel is "
-                            "instruction issue under divergence (profiles/: ~74% issue-active, ~19 of 32 lanes per instruction)"}
+                            "instruction issue under divergence (profiles/r01_prof_k2_final.txt: 82% issue-active, 17.5 of 32 lanes per "
+                            "instruction = 45% of the thread-instruction peak; HBM 0.3% of peak)"}
     # the SURVEY's FP32-roofline target is defined on the brute-force sweep: measure that kernel too (reduced spp, same scene)
     roofline_sweep = None
     if world == 1 and kernel_used != rtw.KERNEL_SPHERES_SMEM and not scene_has_triangles:
@@ -399,7 +410,7 @@ def main() -> int:
         torch.cuda.synchronize()
         k1_ms = min(a.elapsed_time(b) for a, b in evs[1:])
         frac_spp = k1_spp / spp
-        roofline_sweep = sweep_roofline(k1_ms, rays_gpu * frac_spp, paths_gpu * frac_spp, f"k_render<2,0> (K1 shared-memory sphere sweep), {k1_spp} spp")
+        roofline_sweep = sweep_roofline(k1_ms, rays_gpu * frac_spp, paths_gpu * frac_spp, f"k_render_sweep<2> (K1 shared-memory sphere sweep), {k1_spp} spp")
         roofline_sweep["mpaths_per_s"] = paths_gpu * frac_spp / (k1_ms * 1e-3) / 1e6
 
     cpu_baseline = None

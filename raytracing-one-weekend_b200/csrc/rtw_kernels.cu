@@ -1,15 +1,13 @@
 // rtw_kernels.cu -- sm_100a kernels of the B200 path tracer and their launchers.
 //
-//   k_render<R, MODE>   the per-pixel / per-sample loop of render.cpp:150-167 with ray_color (render.cpp:112-129)
-//                       turned into an iterative bounce loop.  Persistent warps pull units of (128 pixels x SU
-//                       samples) from a global atomic counter; inside a warp every lane keeps R paths in flight
-//                       and a finished path is replaced at once from the warp's pool (ballot + popc ranking), so
-//                       the uniform sphere sweep always runs on full warps regardless of path length.
-//       MODE 0 (K1)     sphere scenes: the whole sphere table is staged in shared memory with TMA bulk copies
-//                       (cp.async.bulk + mbarrier) and swept brute force: per (ray, sphere) 8 FMA for the
-//                       line-distance reject test (+3 for the centre lerp of moving spheres); survivors go through
-//                       the exact reference-rule root selection.
-//       MODE 1 (K2)     meshes / mixed scenes: SAH BVH in 64-byte two-child nodes, per-thread stack.
+//   Both render kernels are the per-pixel / per-sample loop of render.cpp:150-167 with ray_color (render.cpp:112-129) turned
+//   into an iterative bounce loop.  Persistent warps pull units of (128 pixels x SU samples) from a global atomic counter; a
+//   finished path is replaced at once from the warp's pool (ballot + popc ranking).
+//   k_render_bvh (K2)   the default: SAH BVH (64-byte two-child nodes, single-primitive leaves), resumable per-lane
+//                       traversal, tables staged in shared memory with TMA bulk copies when they fit.
+//   k_render_sweep<R> (K1)  small sphere scenes: the whole sphere table staged in shared memory (cp.async.bulk + mbarrier)
+//                       and swept brute force, R paths per lane: per (ray, sphere) 8 FMA for the line-distance reject test
+//                       (+3 for the centre lerp of moving spheres); survivors go through the exact reference-rule root selection.
 //   k_primary_f32       K3: deterministic primary hits through the SAME tracing routines (parity mode)
 //   k_primary_f64       K3 in double: reference formulas verbatim, brute force over the raw primitive list
 //   k_accum_to_float, k_finalize_rgb8   render.cpp:11-20,176-186 on the device
@@ -311,20 +309,14 @@ __device__ __forceinline__ void accum_add(unsigned long long* accum, uint32_t pi
   atomicAdd(px + 2, static_cast<unsigned long long>(__float2ll_rn(b * 4294967296.0f)));
 }
 
-template <int R, int MODE, bool STATS>
-__global__ void __launch_bounds__(kRenderThreads, (MODE == 0 ? (R >= 4 ? 2 : (R == 2 ? 3 : 4)) : 3))
-k_render(const __grid_constant__ RenderParams p) {
+template <int R, bool STATS>
+__global__ void __launch_bounds__(kRenderThreads, (R >= 4 ? 2 : (R == 2 ? 3 : 4))) k_render_sweep(const __grid_constant__ RenderParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const DevScene& sc = p.sc;
-  const float4* sA = sc.sphA;
-  const float4* sB = sc.sphB;
-  if (MODE == 0) {
-    const int n = sc.n_static + sc.n_moving;
-    float4* a = reinterpret_cast<float4*>(smem_raw + 16);
-    float4* b = a + n + 1;
-    stage_spheres(sc, a, b, reinterpret_cast<uint64_t*>(smem_raw));
-    sA = a; sB = b;
-  }
+  const int n_table = sc.n_static + sc.n_moving;
+  float4* sA = reinterpret_cast<float4*>(smem_raw + 16);
+  float4* sB = sA + n_table + 1;
+  stage_spheres(sc, sA, sB, reinterpret_cast<uint64_t*>(smem_raw));
 
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t lt = (1u << lane) - 1u;
@@ -343,7 +335,7 @@ k_render(const __grid_constant__ RenderParams p) {
   }
   uint32_t pool_next = 0, pool_end = 0, grp = 0, s0 = 0;
   bool exhausted = false;
-  unsigned long long n_rays = 0, n_paths = 0, n_tests = 0, n_cand = 0, n_nodes = 0, n_tri = 0;
+  unsigned long long n_rays = 0, n_paths = 0, n_tests = 0, n_cand = 0;
 
   for (;;) {
     // ---- refill: every dead slot takes the next (pixel, sample) of the warp's pool --------------------------
@@ -403,20 +395,10 @@ k_render(const __grid_constant__ RenderParams p) {
     // ---- trace ---------------------------------------------------------------------------------------------
     float best_t[R];
     int best_i[R];
-    if (MODE == 0) {
-      trace_spheres<R, STATS>(sc, sA, sB, ray, alive, best_t, best_i, n_cand);
-      if (STATS) {
+    trace_spheres<R, STATS>(sc, sA, sB, ray, alive, best_t, best_i, n_cand);
+    if (STATS) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) if (alive[r]) n_tests += static_cast<unsigned long long>(sc.n_static + sc.n_moving);
-      }
-    } else {
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        best_t[r] = kInf; best_i[r] = kMiss;
-        if (alive[r])
-          trace_bvh<STATS>(sc, mk<float>(ray.ox[r], ray.oy[r], ray.oz[r]), mk<float>(ray.dx[r], ray.dy[r], ray.dz[r]), ray.tm[r],
-                           best_t[r], best_i[r], n_nodes, n_tests, n_tri);
-      }
+      for (int r = 0; r < R; ++r) if (alive[r]) n_tests += static_cast<unsigned long long>(sc.n_static + sc.n_moving);
     }
 
     // ---- shade: ray_color, render.cpp:112-129, one bounce ------------------------------------------------
@@ -463,8 +445,6 @@ k_render(const __grid_constant__ RenderParams p) {
     if (STATS) {
       n_tests += __shfl_xor_sync(0xffffffffu, n_tests, off);
       n_cand += __shfl_xor_sync(0xffffffffu, n_cand, off);
-      n_nodes += __shfl_xor_sync(0xffffffffu, n_nodes, off);
-      n_tri += __shfl_xor_sync(0xffffffffu, n_tri, off);
     }
   }
   if (lane == 0) {
@@ -473,8 +453,6 @@ k_render(const __grid_constant__ RenderParams p) {
     if (STATS) {
       atomicAdd(p.counters + kCtrSphereTests, n_tests);
       atomicAdd(p.counters + kCtrCandidates, n_cand);
-      atomicAdd(p.counters + kCtrNodes, n_nodes);
-      atomicAdd(p.counters + kCtrTriTests, n_tri);
     }
   }
 }
@@ -899,9 +877,9 @@ __global__ void __launch_bounds__(256) k_ffma_peak(float* out, int iters, float 
 // ---------------------------------------------------------------------------------------------------------
 // Launchers (host)
 // ---------------------------------------------------------------------------------------------------------
-template <int R, int MODE, bool STATS>
-static cudaError_t launch_render_t(const RenderParams& p, int sm_count, size_t smem, cudaStream_t stream, int* blocks_out) {
-  auto kern = k_render<R, MODE, STATS>;
+template <int R, bool STATS>
+static cudaError_t launch_sweep_t(const RenderParams& p, int sm_count, size_t smem, cudaStream_t stream, int* blocks_out) {
+  auto kern = k_render_sweep<R, STATS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
   int per_sm = 0;
@@ -943,27 +921,17 @@ size_t bvh_smem_bytes(const RenderParams& p) {
 
 cudaError_t launch_render(const RenderParams& p, int mode, int rays_per_lane, bool stats, int sm_count, cudaStream_t stream) {
   const size_t smem = mode == 0 ? 16 + static_cast<size_t>(p.sc.n_static + p.sc.n_moving + 1) * 32 : 0;
-#define RTW_LAUNCH(R, M)                                                                      \
-  return stats ? launch_render_t<R, M, true>(p, sm_count, smem, stream, nullptr)               \
-               : launch_render_t<R, M, false>(p, sm_count, smem, stream, nullptr)
   if (mode == 0) {
-    if (rays_per_lane == 1) { RTW_LAUNCH(1, 0); }
-    if (rays_per_lane == 4) { RTW_LAUNCH(4, 0); }
-    RTW_LAUNCH(2, 0);
+    // rays_per_lane: paths in flight per lane (1, 2 or 4); 2 measured fastest
+    if (rays_per_lane == 1) return stats ? launch_sweep_t<1, true>(p, sm_count, smem, stream, nullptr) : launch_sweep_t<1, false>(p, sm_count, smem, stream, nullptr);
+    if (rays_per_lane == 4) return stats ? launch_sweep_t<4, true>(p, sm_count, smem, stream, nullptr) : launch_sweep_t<4, false>(p, sm_count, smem, stream, nullptr);
+    return stats ? launch_sweep_t<2, true>(p, sm_count, smem, stream, nullptr) : launch_sweep_t<2, false>(p, sm_count, smem, stream, nullptr);
   }
-#undef RTW_LAUNCH
-  // BVH kernel.  rays_per_lane selects tuning variants: 0 default, 100 = first (non-resumable) version,
-  // 1xy = resumable with STEPS/SERVICE_MIN variants, +1000 = force global memory tables
-  const int variant = rays_per_lane % 1000;
-  const size_t bsm = rays_per_lane >= 1000 ? 0 : bvh_smem_bytes(p);
-  if (variant == 100) return stats ? launch_render_t<1, 1, true>(p, sm_count, 0, stream, nullptr) : launch_render_t<1, 1, false>(p, sm_count, 0, stream, nullptr);
+  // BVH kernel: 8 traversal steps between service checks, service once 24 lanes need it, 4 CTAs/SM (tuning record in DESIGN.md)
+  const size_t bsm = bvh_smem_bytes(p);
 #define RTW_BVH(ST, SV, MB)                                                                                         \
   return bsm ? (stats ? launch_bvh_t<true, true, ST, SV, MB>(p, sm_count, bsm, stream) : launch_bvh_t<true, false, ST, SV, MB>(p, sm_count, bsm, stream)) \
              : (stats ? launch_bvh_t<false, true, ST, SV, MB>(p, sm_count, 0, stream) : launch_bvh_t<false, false, ST, SV, MB>(p, sm_count, 0, stream))
-  if (variant == 101) { RTW_BVH(8, 24, 3); }
-  if (variant == 102) { RTW_BVH(12, 24, 4); }
-  if (variant == 103) { RTW_BVH(8, 28, 4); }
-  if (variant == 104) { RTW_BVH(6, 24, 4); }
   RTW_BVH(8, 24, 4);
 #undef RTW_BVH
 }

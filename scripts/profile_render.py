@@ -11,7 +11,7 @@ rtw = importlib.import_module("raytracing-one-weekend_b200")
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--kernel", default="auto", choices=["auto", "spheres", "bvh"])
-ap.add_argument("--rays-per-lane", type=int, default=0)
+ap.add_argument("--rays-per-lane", type=int, default=0, help="sphere sweep only: 1, 2 or 4 paths per lane")
 ap.add_argument("--spp", type=int, default=16)
 ap.add_argument("--width", type=int, default=1920)
 ap.add_argument("--depth", type=int, default=50)
