@@ -635,32 +635,11 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
       }
     }
 
-    // ---- traversal phase: STEPS node-or-leaf steps per traversing lane ------------------------------------------------
+    // ---- traversal phase: STEPS steps; in each, lanes on an inner node visit it, then lanes on a leaf test its primitive(s)
+    // at once.  (Holding leaves back until 4..16 lanes stand on one was measured twice and lost 3-8 %: DESIGN.md.)
 #pragma unroll 1
     for (int step = 0; step < STEPS; ++step) {
-      if (state != TRAV) continue;
-      if (node < 0) {  // leaf
-        const uint32_t v = static_cast<uint32_t>(~node);
-        const uint32_t first = v >> 5, cnt = sc.leaf_direct ? 1u : (v & 31u);
-        for (uint32_t k = 0; k < cnt; ++k) {
-          const uint32_t ref = sc.leaf_direct ? v : ld1<SMEM>(tb.leafRefs, static_cast<int>(first + k));
-          const int i = static_cast<int>(ref & 0x1fffffffu);
-          if (ref >> 30) {
-            if (STATS) ++n_tri;
-            const float4 q0 = ld4<SMEM>(tb.tri, 3 * i), q1 = ld4<SMEM>(tb.tri, 3 * i + 1), q2 = ld4<SMEM>(tb.tri, 3 * i + 2);
-            const float t = triangle_hit<float>(o, d, mk<float>(q0.x, q0.y, q0.z), mk<float>(q1.x, q1.y, q1.z), mk<float>(q2.x, q2.y, q2.z),
-                                                mk<float>(q0.w, q1.w, q2.w), kTMin, best_t);
-            if (t >= 0.0f) { best_t = t; best_i = kHitTri | i; }
-          } else {
-            if (STATS) ++n_tests;
-            const float4 A = ld4<SMEM>(tb.sphA, i), B = ld4<SMEM>(tb.sphB, i);
-            const float t = sphere_hit_fast(o, d, qa, qia, mk<float>(fmaf(tm, B.x, A.x), fmaf(tm, B.y, A.y), fmaf(tm, B.z, A.z)), B.w, kTMin, best_t);
-            if (t >= 0.0f) { best_t = t; best_i = i; }
-          }
-        }
-        if (sp > 0) node = stack[--sp];
-        else { node = kMiss; state = DONE; }
-      } else {
+      if (state == TRAV && node >= 0) {
         if (STATS) ++n_nodes;
         const float4 q0 = ld4<SMEM>(tb.nodes, 4 * node), q1 = ld4<SMEM>(tb.nodes, 4 * node + 1), q2 = ld4<SMEM>(tb.nodes, 4 * node + 2),
                      q3 = ld4<SMEM>(tb.nodes, 4 * node + 3);
@@ -689,6 +668,28 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
         } else {
           node = kMiss; state = DONE;
         }
+      }
+      if (state == TRAV && node < 0) {
+        const uint32_t v = static_cast<uint32_t>(~node);
+        const uint32_t first = v >> 5, cnt = sc.leaf_direct ? 1u : (v & 31u);
+        for (uint32_t k = 0; k < cnt; ++k) {
+          const uint32_t ref = sc.leaf_direct ? v : ld1<SMEM>(tb.leafRefs, static_cast<int>(first + k));
+          const int i = static_cast<int>(ref & 0x1fffffffu);
+          if (ref >> 30) {
+            if (STATS) ++n_tri;
+            const float4 q0 = ld4<SMEM>(tb.tri, 3 * i), q1 = ld4<SMEM>(tb.tri, 3 * i + 1), q2 = ld4<SMEM>(tb.tri, 3 * i + 2);
+            const float t = triangle_hit<float>(o, d, mk<float>(q0.x, q0.y, q0.z), mk<float>(q1.x, q1.y, q1.z), mk<float>(q2.x, q2.y, q2.z),
+                                                mk<float>(q0.w, q1.w, q2.w), kTMin, best_t);
+            if (t >= 0.0f) { best_t = t; best_i = kHitTri | i; }
+          } else {
+            if (STATS) ++n_tests;
+            const float4 A = ld4<SMEM>(tb.sphA, i), B = ld4<SMEM>(tb.sphB, i);
+            const float t = sphere_hit_fast(o, d, qa, qia, mk<float>(fmaf(tm, B.x, A.x), fmaf(tm, B.y, A.y), fmaf(tm, B.z, A.z)), B.w, kTMin, best_t);
+            if (t >= 0.0f) { best_t = t; best_i = i; }
+          }
+        }
+        if (sp > 0) node = stack[--sp];
+        else { node = kMiss; state = DONE; }
       }
     }
   }

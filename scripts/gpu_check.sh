@@ -1,4 +1,5 @@
 #!/bin/bash
+# One GPU: parity suite, smoke, headline bench line, reference arm.   gpurun --timeout 2400 -- 'bash scripts/gpu_check.sh'
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -4 gpurun_out/pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()"
