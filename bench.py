@@ -57,7 +57,7 @@ def build_scene(rtw, name, wl):
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the `ncu --set full` captures summarised
 # under profiles/ (r01_prof_k2_final.txt, r01_prof_k1_final.txt, r01_prof_k2_dragon.txt).  The traffic is the accumulation
 # buffer (66 MB at 1080p) being read after the memset and partly written back, plus the scene once: it does not scale with spp.
-NCU_TRAFFIC_BYTES = {("cover", "bvh"): 66.46e6 + 17.33e6, ("cover", "sweep"): 66.45e6 + 20.74e6, ("dragon", "bvh"): 286.38e6 + 70.87e6}
+NCU_TRAFFIC_BYTES = {("cover", "bvh"): 66.46e6 + 17.97e6, ("cover", "sweep"): 66.45e6 + 19.11e6, ("dragon", "bvh"): 284.46e6 + 71.33e6}
 # canonical FP32 flop costs of SURVEY.md 8(d) (FMA = 2)
 FLOP_STATIC_TEST, FLOP_MOVING_TEST, FLOP_HIT, FLOP_SHADE = 17.0, 23.0, 40.0, 80.0
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
@@ -393,8 +393,8 @@ def main() -> int:
                     "per_ray": {"node_visits": nodes_pr, "sphere_tests": tests_pr, "triangle_tests": tris_pr},
                     "flop_model": "rays x (nodes x 2 boxes x 12 + sphere tests x 17|23 + triangle tests x 36 + big spheres x 17 + 80) + hits x 40 (SURVEY 8(d))",
                     "note": "culling removes ~97% of the sweep's flops, so the flop fraction is low by construction; what limits this kernel is "
-                            "instruction issue under divergence (profiles/r01_prof_k2_final.txt: 82% issue-active, 17.5 of 32 lanes per "
-                            "instruction = 45% of the thread-instruction peak; HBM 0.3% of peak)"}
+                            "instruction issue under divergence (profiles/r01_prof_k2_final.txt: 81% issue-active, 18.7 of 32 lanes per "
+                            "instruction = 47% of the thread-instruction peak; HBM 0.3% of peak)"}
     # the SURVEY's FP32-roofline target is defined on the brute-force sweep: measure that kernel too (reduced spp, same scene)
     roofline_sweep = None
     if world == 1 and kernel_used != rtw.KERNEL_SPHERES_SMEM and not scene_has_triangles:
