@@ -606,14 +606,20 @@ static void* philox_worker(void* arg) {
       for (int q = jb->s0; q < jb->s1; ++q) {
         rsrc rs; rs.philox = 1; rs.key[0] = (uint32_t)jb->seed; rs.key[1] = (uint32_t)(jb->seed >> 32);
         rs.pixel = (uint32_t)k; rs.sample = (uint32_t)q; rs.scatter_index = 0;
-        double x0[4], x1[4];
-        philox_dim(&rs, 0u, x0);
-        philox_dim(&rs, 1u, x1);
+        /* dimension 0 carries five 24-bit uniforms: the top 24 bits of the four words, and a fifth one assembled from the
+         * low bytes of words 0..2 (shutter time); dimension 1 is unused */
+        double x0[4], x_time;
+        {
+          uint32_t ctr[4] = {rs.pixel, rs.sample, 0u, 0u}, o[4];
+          rtwo_philox4x32_10(ctr, rs.key, o);
+          for (int m = 0; m < 4; ++m) x0[m] = u01(o[m]);
+          x_time = (double)(((o[0] & 0xffu) << 16) | ((o[1] & 0xffu) << 8) | (o[2] & 0xffu)) * (1.0 / 16777216.0);
+        }
         double u = (j + x0[0]) / (jb->width - 1);
         double v = (from_top_i + x0[1]) / (jb->height - 1);
         double rr = sqrt(x0[2]), ph = 6.283185307179586 * x0[3];
         v3 disk = V(rr * cos(ph), rr * sin(ph), 0.0);
-        double when = s->cam.t0 + x1[0] * (s->cam.t1 - s->cam.t0);
+        double when = s->cam.t0 + x_time * (s->cam.t1 - s->cam.t0);
         ray r = camera_ray(&s->cam, u, v, disk, when);
         v3 c = ray_color(s, &r, jb->depth, &rs, &jb->nrays);
         jb->sum[3 * k] += c.x; jb->sum[3 * k + 1] += c.y; jb->sum[3 * k + 2] += c.z;

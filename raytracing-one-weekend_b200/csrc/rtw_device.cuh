@@ -108,8 +108,9 @@ __device__ __forceinline__ double sqrt_nr(double x) { return x > 1e-35 ? x * rsq
 
 // ---------------------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11): counter = (pixel, sample, dimension, 0), key = seed.
-//   dimension 0: (pixel jitter x, pixel jitter y, lens radius, lens azimuth)
-//   dimension 1: (shutter time, -, -, -)
+//   dimension 0: (pixel jitter x, pixel jitter y, lens radius, lens azimuth) from the top 24 bits of the four words, and the
+//                shutter time from the low bytes of words 0..2 (u01_low): one block per primary ray
+//   dimension 1: unused
 //   dimension 2+k: k-th scatter of the path: (ball z, ball azimuth, ball radius, Schlick coin)
 // ---------------------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
@@ -131,6 +132,10 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 __host__ __device__ __forceinline__ float u01(uint32_t x) { return static_cast<float>(x >> 8) * 5.9604644775390625e-8f; }
+// A fifth 24-bit uniform from the low bytes u01() leaves unused in the x, y, z words of one Philox block.
+__host__ __device__ __forceinline__ float u01_low(uint4 x) {
+  return static_cast<float>(((x.x & 0xffu) << 16) | ((x.y & 0xffu) << 8) | (x.z & 0xffu)) * 5.9604644775390625e-8f;
+}
 
 // Uniform point of the unit ball restricted to the positive octant, NOT normalised: the distribution the
 // reference's random_unit_vector() actually has (random-utils.cpp:23-33), by direct inversion:
@@ -319,61 +324,58 @@ struct HitGeom {
   int material, prim_id;
 };
 
+// Accepted sphere hit: the reference formula (common-model.cpp:70-88) is re-evaluated once in double from the fp32 ray and the
+// table entry, keeping the root the fp32 tracer selected.  The tracer only has to FIND the hit; point and normal then carry
+// fp32 rounding of the result instead of fp32 cancellation (|o-c| ~ 13 against r = 0.2 in the cover scene).  Small and big
+// spheres share ONE double-precision path (only the table reads differ) so that ground hits and small-sphere hits sitting in
+// neighbouring lanes of a shading batch do not diverge.
 __device__ __forceinline__ HitGeom hit_geometry(const DevScene& sc, const float4* sphA, const float4* sphB, F3 o, F3 d,
-                                                float tm, float t, int hit) {
+                                                  float tm, float t, int hit) {
   HitGeom g;
   if (hit & kHitTri) {
     const int i = hit & ~kHitTri;
     const float4 q0 = __ldg(&sc.tri[3 * i]), q1 = __ldg(&sc.tri[3 * i + 1]), q2 = __ldg(&sc.tri[3 * i + 2]);
     g.p = o + d * t;
     g.t = t;
-    g.n = mk<float>(q0.w, q1.w, q2.w);  // un-normalised geometric normal, front_facing always true (Q7)
+    g.n = mk<float>(q0.w, q1.w, q2.w);
     g.front = true;
     const int2 id = __ldg(&sc.triId[i]);
     g.prim_id = id.x; g.material = id.y;
-  } else if (hit & kHitBig) {
+    return g;
+  }
+  const double time = tm;
+  D3 c;
+  double rr;
+  if (hit & kHitBig) {
     const BigSphere& b = sc.big[hit & ~kHitBig];
-    const double time = tm, td = t;
-    const D3 c = mk<double>(b.c0[0] + time * b.dc[0], b.c0[1] + time * b.dc[1], b.c0[2] + time * b.dc[2]);
-    const D3 p = mk<double>(o.x + td * d.x, o.y + td * d.y, o.z + td * d.z);
-    const D3 pc = p - c;
-    const D3 n = pc * rsqrt_nr(dot(pc, pc));
-    const bool front = ((d.x * n.x + d.y * n.y + d.z * n.z) < 0.0) != (b.r < 0.0);
-    g.p = mk<float>(static_cast<float>(p.x), static_cast<float>(p.y), static_cast<float>(p.z));
-    g.n = front ? mk<float>(static_cast<float>(n.x), static_cast<float>(n.y), static_cast<float>(n.z))
-                : mk<float>(static_cast<float>(-n.x), static_cast<float>(-n.y), static_cast<float>(-n.z));
-    g.front = front;
-    g.t = t;
+    c = mk<double>(b.c0[0] + time * b.dc[0], b.c0[1] + time * b.dc[1], b.c0[2] + time * b.dc[2]);
+    rr = b.r;
     g.prim_id = b.prim_id; g.material = b.material;
   } else {
-    // Accepted small-sphere hit: re-evaluate the reference formula (common-model.cpp:70-88) once in double from
-    // the fp32 ray and table entries, keeping the root the fp32 sweep selected.  The sweep only has to FIND the
-    // hit; point and normal then carry fp32 rounding of the result instead of fp32 cancellation (|o-c| ~ 13
-    // against r = 0.2 in the cover scene).  ~40 DP operations per bounce against ~5000 FP32 ones for the sweep.
     const float4 A = sphA[hit], B = sphB[hit];
-    const double time = tm;
-    const D3 c = mk<double>(A.x + time * B.x, A.y + time * B.y, A.z + time * B.z);
-    const D3 od = mk<double>(o.x, o.y, o.z), dd = mk<double>(d.x, d.y, d.z);
-    const D3 oc = od - c;
-    const double rr = B.w;
-    const double a = dot(dd, dd), h = dot(oc, dd), cc = dot(oc, oc) - rr * rr;
-    const double disc = h * h - a * cc;
-    const double sq = sqrt_nr(disc), ia = rcp_nr(a);
-    const double r1 = (-h - sq) * ia, r2 = (-h + sq) * ia;
-    const double td = (fabs(r1 - static_cast<double>(t)) <= fabs(r2 - static_cast<double>(t))) ? r1 : r2;
-    const D3 p = od + dd * td;
-    const D3 pc = p - c;
-    const D3 n = pc * rsqrt_nr(dot(pc, pc));
-    const bool front = (dot(dd, n) < 0.0) != (rr < 0.0);  // common-model.cpp:88
-    g.p = mk<float>(static_cast<float>(p.x), static_cast<float>(p.y), static_cast<float>(p.z));
-    g.n = front ? mk<float>(static_cast<float>(n.x), static_cast<float>(n.y), static_cast<float>(n.z))
-                : mk<float>(static_cast<float>(-n.x), static_cast<float>(-n.y), static_cast<float>(-n.z));
-    g.front = front;
-    g.t = static_cast<float>(td);
+    c = mk<double>(A.x + time * B.x, A.y + time * B.y, A.z + time * B.z);
+    rr = B.w;
     const int2 id = __ldg(&sc.sphId[hit]);
     g.prim_id = id.x; g.material = id.y;
   }
+  const D3 od = mk<double>(o.x, o.y, o.z), dd = mk<double>(d.x, d.y, d.z);
+  const D3 oc = od - c;
+  const double a = dot(dd, dd), h = dot(oc, dd), cc = dot(oc, oc) - rr * rr;
+  const double disc = h * h - a * cc;
+  const double sq = sqrt_nr(disc), ia = rcp_nr(a);
+  const double r1 = (-h - sq) * ia, r2 = (-h + sq) * ia;
+  const double td = (fabs(r1 - static_cast<double>(t)) <= fabs(r2 - static_cast<double>(t))) ? r1 : r2;
+  const D3 p = od + dd * td;
+  const D3 pc = p - c;
+  const D3 n = pc * rsqrt_nr(dot(pc, pc));
+  const bool front = (dot(dd, n) < 0.0) != (rr < 0.0);
+  g.p = mk<float>(static_cast<float>(p.x), static_cast<float>(p.y), static_cast<float>(p.z));
+  g.n = front ? mk<float>(static_cast<float>(n.x), static_cast<float>(n.y), static_cast<float>(n.z))
+              : mk<float>(static_cast<float>(-n.x), static_cast<float>(-n.y), static_cast<float>(-n.z));
+  g.front = front;
+  g.t = static_cast<float>(td);
   return g;
 }
+
 
 }  // namespace rtw

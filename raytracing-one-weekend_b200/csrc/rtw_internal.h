@@ -14,6 +14,11 @@ constexpr double kBigRadius = 100.0;    // |r| >= this: sphere leaves the fp32 t
 
 enum : int { kCtrWork = 0, kCtrRays = 1, kCtrPaths = 2, kCtrSphereTests = 3, kCtrCandidates = 4, kCtrNodes = 5, kCtrTriTests = 6, kCtrCount = 8 };
 
+struct SmemLayout {  // byte offsets into dynamic shared memory and sizes of the staged tables (filled by launch_render)
+  uint32_t nodes, refs, sa, sb, tri, records;
+  uint32_t b_nodes, b_refs, b_sph, b_tri;
+};
+
 struct RenderParams {
   DevScene sc;
   unsigned long long* accum;     // [npix][4] int64 fixed point (2^-32) + finished-path count
@@ -27,6 +32,7 @@ struct RenderParams {
   float inv_wm1, inv_hm1;
   uint64_t seed;
   uint32_t n_leaf_refs;
+  SmemLayout so;
 };
 
 struct PrimaryParams {

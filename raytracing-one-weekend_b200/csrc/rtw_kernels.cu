@@ -369,7 +369,6 @@ __global__ void __launch_bounds__(kRenderThreads, (R >= 4 ? 2 : (R == 2 ? 3 : 4)
           if (px < p.npix) {
             // primary ray: render.cpp:158-160 with the pixel mapping of SURVEY Q12
             const uint4 x0 = philox4x32_10(make_uint4(px, sm, 0u, 0u), key);
-            const uint4 x1 = philox4x32_10(make_uint4(px, sm, 1u, 0u), key);
             const uint32_t i = px / p.width, j = px - i * p.width;
             const float u = (static_cast<float>(j) + u01(x0.x)) * p.inv_wm1;
             const float v = (static_cast<float>(p.height - 1u - i) + u01(x0.y)) * p.inv_hm1;
@@ -378,7 +377,7 @@ __global__ void __launch_bounds__(kRenderThreads, (R >= 4 ? 2 : (R == 2 ? 3 : 4)
             camera_ray<float>(sc.cam, u, v, dk.x, dk.y, o, d);
             ray.ox[r] = o.x; ray.oy[r] = o.y; ray.oz[r] = o.z;
             ray.dx[r] = d.x; ray.dy[r] = d.y; ray.dz[r] = d.z;
-            ray.tm[r] = fmaf(u01(x1.x), sc.cam.t1 - sc.cam.t0, sc.cam.t0);
+            ray.tm[r] = fmaf(u01_low(x0), sc.cam.t1 - sc.cam.t0, sc.cam.t0);
             tr[r] = tg[r] = tb[r] = 1.0f;
             pix[r] = px; smp[r] = sm; depth[r] = 0;
             alive[r] = true;
@@ -472,6 +471,8 @@ __global__ void __launch_bounds__(kRenderThreads, (R >= 4 ? 2 : (R == 2 ? 3 : 4)
 //   this kernel at 15 of 32 active lanes per instruction.  With SMEM the nodes, leaf references, sphere tables and
 //   triangles are staged into shared memory with TMA bulk copies when they fit.
 // ---------------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr uint32_t wf_warp_bytes(int P) { return static_cast<uint32_t>((P * (48 + 8 + 4) + 3 * P + 15) & ~15); }
+
 struct BvhTables {
   const float4* nodes;
   const uint32_t* leafRefs;
@@ -618,13 +619,12 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
           const uint32_t sm = s0 + within / kGroupPixels;
           if (px < p.npix) {
             const uint4 x0 = philox4x32_10(make_uint4(px, sm, 0u, 0u), key);
-            const uint4 x1 = philox4x32_10(make_uint4(px, sm, 1u, 0u), key);
             const uint32_t i = px / p.width, j = px - i * p.width;
             const float u = (static_cast<float>(j) + u01(x0.x)) * p.inv_wm1;
             const float v = (static_cast<float>(p.height - 1u - i) + u01(x0.y)) * p.inv_hm1;
             const float2 dk = sample_disk(u01(x0.z), u01(x0.w));
             camera_ray<float>(sc.cam, u, v, dk.x, dk.y, o, d);
-            tm = fmaf(u01(x1.x), sc.cam.t1 - sc.cam.t0, sc.cam.t0);
+            tm = fmaf(u01_low(x0), sc.cam.t1 - sc.cam.t0, sc.cam.t0);
             tr = tg = tbl = 1.0f;
             pix = px; smp = sm; depth = 0;
             start_traversal();
@@ -714,6 +714,344 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
       atomicAdd(p.counters + kCtrSphereTests, n_tests);
       atomicAdd(p.counters + kCtrNodes, n_nodes);
       atomicAdd(p.counters + kCtrTriTests, n_tri);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2w render kernel: the same BVH traversal, with the paths of a warp kept as RECORDS in shared memory instead of in
+// the lanes' registers ("wavefront per warp").
+//   Every warp owns P path records (ray, closest hit so far, throughput, pixel, sample, depth) and three index stacks:
+//     ready -- rays waiting to be traversed          hit -- traversal found a hit: scatter next
+//     miss  -- traversal missed / path ended / record is fresh: add the sky term, start a new path in the record
+//   A lane only ever holds the traversal state of ONE ray.  When its traversal finishes it files the record under hit or
+//   miss and takes the next ready ray, so the traversal phase runs with (nearly) all lanes busy.  Shading runs as BATCHES
+//   of up to 32 records of ONE kind, lane l shading the l-th record of the stack: Philox, sampling, the big-sphere test of
+//   the new ray and the record traffic are then convergent across the warp.  With P >= 32 + 2 * BATCH a full batch of one
+//   kind is always available when the ready stack runs dry.
+//   The big spheres (fp64) are tested when a ray is CREATED (inside the batch), and the result seeds best_t of the tree
+//   walk, which also prunes it.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kFresh = -2;   // record holds no path yet
+constexpr int kEnded = -3;   // path ended without a sky term (depth cut / absorbed)
+
+template <bool SMEM, bool STATS, int NW, int P, int STEPS, int BATCH>
+__global__ void __launch_bounds__(NW * 32, 1) k_render_wf(const __grid_constant__ RenderParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const DevScene& sc = p.sc;
+  BvhTables tb{sc.nodes, sc.leafRefs, sc.sphA, sc.sphB, sc.tri};
+  if (SMEM) {
+    // shared-memory offsets of the tables come precomputed from the host (p.so): the compiler re-materialises these
+    // addresses inside the loops instead of holding them in registers, so they must be one constant-bank load away
+    const SmemLayout& so = p.so;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, so.b_nodes + so.b_refs + 2u * so.b_sph + so.b_tri);
+      auto copy = [&](unsigned char* dst, const void* src, uint32_t bytes) {
+        constexpr uint32_t kChunk = 32768u;
+        for (uint32_t off = 0; off < bytes; off += kChunk)
+          tma_bulk_g2s(dst + off, static_cast<const unsigned char*>(src) + off, min(kChunk, bytes - off), bar);
+      };
+      copy(smem_raw + so.nodes, sc.nodes, so.b_nodes); copy(smem_raw + so.refs, sc.leafRefs, so.b_refs);
+      copy(smem_raw + so.sa, sc.sphA, so.b_sph); copy(smem_raw + so.sb, sc.sphB, so.b_sph);
+      copy(smem_raw + so.tri, sc.tri, so.b_tri);
+    }
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, 0)) {
+      if (++spins > (1u << 26)) __trap();
+    }
+    tb.nodes = reinterpret_cast<const float4*>(smem_raw + so.nodes);
+    tb.leafRefs = reinterpret_cast<const uint32_t*>(smem_raw + so.refs);
+    tb.sphA = reinterpret_cast<const float4*>(smem_raw + so.sa);
+    tb.sphB = reinterpret_cast<const float4*>(smem_raw + so.sb);
+    tb.tri = reinterpret_cast<const float4*>(smem_raw + so.tri);
+  }
+  unsigned char* wbase = smem_raw + p.so.records;
+
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint2 key = make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32));
+
+  // ---- this warp's records and index stacks ------------------------------------------------------------------------
+  constexpr uint32_t kWarpBytes = wf_warp_bytes(P);
+  unsigned char* wb = wbase + warp * kWarpBytes;
+  float4* recO = reinterpret_cast<float4*>(wb);      // (o.xyz, time)
+  float4* recD = recO + P;                           // (d.xyz, best_t)
+  float4* recT = recD + P;                           // (throughput.rgb, best_i as int bits)
+  uint2* recI = reinterpret_cast<uint2*>(recT + P);  // (pixel, sample)
+  int* recZ = reinterpret_cast<int*>(recI + P);      // depth
+  uint8_t* q_ready = reinterpret_cast<uint8_t*>(recZ + P);
+  uint8_t* q_hit = q_ready + P;
+  uint8_t* q_miss = q_hit + P;
+  for (uint32_t i = lane; i < static_cast<uint32_t>(P); i += 32u) {
+    recT[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(kFresh));
+    q_miss[i] = static_cast<uint8_t>(i);
+  }
+  __syncwarp();
+  uint32_t n_ready = 0, n_hit = 0, n_miss = P;   // warp-uniform
+
+  enum : int { IDLE = 0, TRAV = 1, FIN = 2 };
+  int state = IDLE;
+  uint32_t rec = 0;
+  F3 o = mk<float>(0.f, 0.f, 0.f), d = mk<float>(0.f, 0.f, 1.f);
+  float tm = 0.f;
+  float idx = 0.f, idy = 0.f, idz = 0.f, odx = 0.f, ody = 0.f, odz = 0.f, qa = 1.f, qia = 1.f, best_t = kInf;
+  int best_i = kMiss, node = kMiss, sp = 0;
+  int stack[kBvhStack];
+
+  uint32_t pool_next = 0, pool_end = 0, grp = 0, s0 = 0;
+  bool exhausted = false;
+  uint32_t n_rays = 0, n_paths = 0, n_tests = 0, n_nodes = 0, n_tri = 0;
+
+  for (;;) {
+    // ---- (1) lanes whose traversal finished file their record under hit / miss --------------------------------------
+    const uint32_t fin = __ballot_sync(0xffffffffu, state == FIN);
+    if (fin != 0u) {
+      const bool is_fin = state == FIN;
+      const bool is_hit = is_fin && best_i != kMiss;
+      const uint32_t mh = __ballot_sync(0xffffffffu, is_hit), mm = fin & ~mh;
+      if (is_fin) {
+        recD[rec].w = best_t;
+        recT[rec].w = __int_as_float(best_i);
+        if (is_hit) q_hit[n_hit + __popc(mh & lt)] = static_cast<uint8_t>(rec);
+        else q_miss[n_miss + __popc(mm & lt)] = static_cast<uint8_t>(rec);
+        ++n_rays;
+        state = IDLE;
+      }
+      n_hit += __popc(mh); n_miss += __popc(mm);
+      __syncwarp();
+    }
+    // ---- (2) idle lanes take ready rays ---------------------------------------------------------------------------------
+    uint32_t idle = __ballot_sync(0xffffffffu, state == IDLE);
+    if (idle != 0u && n_ready != 0u) {
+      const uint32_t rank = __popc(idle & lt);
+      if (state == IDLE && rank < n_ready) {
+        rec = q_ready[n_ready - 1u - rank];
+        const float4 a = recO[rec], b = recD[rec];
+        o = mk<float>(a.x, a.y, a.z); tm = a.w;
+        d = mk<float>(b.x, b.y, b.z); best_t = b.w;
+        best_i = __float_as_int(recT[rec].w);
+        qa = dot(d, d); qia = fast_rcp(qa);
+        idx = fast_rcp(d.x); idy = fast_rcp(d.y); idz = fast_rcp(d.z);
+        odx = o.x * idx; ody = o.y * idy; odz = o.z * idz;
+        sp = 0;
+        node = sc.n_nodes > 0 ? 0 : kMiss;
+        state = node == kMiss ? FIN : TRAV;
+      }
+      const uint32_t took = min(static_cast<uint32_t>(__popc(idle)), n_ready);
+      n_ready -= took;
+      idle = __ballot_sync(0xffffffffu, state == IDLE);
+      __syncwarp();
+    }
+    // ---- (3) shading batches ----------------------------------------------------------------------------------------------
+    const uint32_t n_idle = __popc(idle);
+    const bool starving = n_ready == 0u && n_idle >= 8u;  // cannot happen before the work runs out when P >= 32 + 2 * BATCH
+    const bool run_hit = n_hit >= static_cast<uint32_t>(BATCH) || (starving && n_hit > 0u && n_hit >= n_miss);
+    const bool run_miss = !run_hit && (n_miss >= static_cast<uint32_t>(BATCH) || (starving && n_miss > 0u));
+    if (run_hit) {
+      // scatter: hit geometry, material, next ray (common-model.cpp:13-62), big-sphere pre-test of the new ray
+      const uint32_t take = min(32u, n_hit);
+      const bool act = lane < take;
+      uint32_t r2 = 0;
+      if (act) r2 = q_hit[n_hit - 1u - lane];
+      n_hit -= take;
+      __syncwarp();
+      bool to_ready = false, to_miss = false;
+      if (act) {
+        const float4 a = recO[r2], b = recD[r2], c = recT[r2];
+        const int dep = recZ[r2];
+        const F3 o2 = mk<float>(a.x, a.y, a.z), d2 = mk<float>(b.x, b.y, b.z);
+        if (dep >= p.max_depth) {
+          recT[r2].w = __int_as_float(kEnded);   // hit at depth 0 of the recursion: black
+          to_miss = true;
+        } else {
+          const HitGeom g = hit_geometry(sc, tb.sphA, tb.sphB, o2, d2, a.w, b.w, __float_as_int(c.w));
+          const float4 mA = __ldg(&sc.matA[g.material]);
+          const float2 mB = __ldg(&sc.matB[g.material]);
+          const int kind = __float_as_int(mB.y);
+          const uint2 ps = recI[r2];
+          const uint4 x = philox4x32_10(make_uint4(ps.x, ps.y, 2u + static_cast<uint32_t>(dep), 0u), key);
+          const F3 ball = sample_octant_ball(u01(x.x), u01(x.y), u01(x.z));
+          F3 dn;
+          if (scatter_dir(kind, mA.w, mB.x, d2, g.n, g.front, ball, u01(x.w), dn)) {
+            float bt = kInf; int bi = kMiss;
+            trace_big_spheres(sc, g.p, dn, a.w, bt, bi);
+            recO[r2] = make_float4(g.p.x, g.p.y, g.p.z, a.w);
+            recD[r2] = make_float4(dn.x, dn.y, dn.z, bt);
+            const bool die = kind == kDielectric;
+            recT[r2] = make_float4(die ? c.x : c.x * mA.x, die ? c.y : c.y * mA.y, die ? c.z : c.z * mA.z, __int_as_float(bi));
+            recZ[r2] = dep + 1;
+            to_ready = true;
+          } else {
+            recT[r2].w = __int_as_float(kEnded);
+            to_miss = true;
+          }
+        }
+      }
+      const uint32_t mr = __ballot_sync(0xffffffffu, to_ready), mm = __ballot_sync(0xffffffffu, to_miss);
+      if (to_ready) q_ready[n_ready + __popc(mr & lt)] = static_cast<uint8_t>(r2);
+      if (to_miss) q_miss[n_miss + __popc(mm & lt)] = static_cast<uint8_t>(r2);
+      n_ready += __popc(mr); n_miss += __popc(mm);
+      __syncwarp();
+      continue;
+    }
+    if (run_miss) {
+      // end of path: sky term (render.cpp:125-128), then a new path in the same record (render.cpp:158-160)
+      const uint32_t take = min(32u, n_miss);
+      const bool act = lane < take;
+      uint32_t r2 = 0;
+      if (act) r2 = q_miss[n_miss - 1u - lane];
+      n_miss -= take;
+      __syncwarp();
+      if (act) {
+        const float4 c = recT[r2];
+        const int code = __float_as_int(c.w);
+        if (code != kFresh) {
+          const uint32_t px = recI[r2].x;
+          if (code == kMiss) {
+            const float4 b = recD[r2];
+            const F3 s = sky_color(mk<float>(b.x, b.y, b.z));
+            accum_add(p.accum, px, c.x * s.x, c.y * s.y, c.z * s.z);
+          }
+          ++n_paths;
+          atomicAdd(p.accum + 4ull * px + 3, 1ull);
+        }
+      }
+      bool got = false, retry = false;
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        const uint32_t need = __ballot_sync(0xffffffffu, act && !got);
+        if (need == 0u) break;
+        if (pool_next == pool_end) {
+          if (exhausted) break;
+          unsigned long long u = 0;
+          if (lane == 0) u = atomicAdd(p.counters + kCtrWork, 1ull);
+          u = __shfl_sync(0xffffffffu, u, 0);
+          if (u >= p.n_units) { exhausted = true; break; }
+          grp = static_cast<uint32_t>(u / p.n_chunks);
+          const uint32_t chunk = static_cast<uint32_t>(u - static_cast<unsigned long long>(grp) * p.n_chunks);
+          s0 = p.s_begin + chunk * p.su;
+          const uint32_t ns = min(p.su, p.s_end - s0);
+          pool_next = 0; pool_end = ns * kGroupPixels;
+        }
+        const uint32_t avail = pool_end - pool_next;
+        const uint32_t rank = __popc(need & lt);
+        if (act && !got && rank < avail) {
+          const uint32_t within = pool_next + rank;
+          const uint32_t px = grp * kGroupPixels + (within & (kGroupPixels - 1u));
+          const uint32_t sm = s0 + within / kGroupPixels;
+          if (px < p.npix) {
+            const uint4 x0 = philox4x32_10(make_uint4(px, sm, 0u, 0u), key);
+            const uint32_t i = px / p.width, j = px - i * p.width;
+            const float u = (static_cast<float>(j) + u01(x0.x)) * p.inv_wm1;
+            const float v = (static_cast<float>(p.height - 1u - i) + u01(x0.y)) * p.inv_hm1;
+            const float2 dk = sample_disk(u01(x0.z), u01(x0.w));
+            F3 o2, d2;
+            camera_ray<float>(sc.cam, u, v, dk.x, dk.y, o2, d2);
+            const float t2 = fmaf(u01_low(x0), sc.cam.t1 - sc.cam.t0, sc.cam.t0);
+            float bt = kInf; int bi = kMiss;
+            trace_big_spheres(sc, o2, d2, t2, bt, bi);
+            recO[r2] = make_float4(o2.x, o2.y, o2.z, t2);
+            recD[r2] = make_float4(d2.x, d2.y, d2.z, bt);
+            recT[r2] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(bi));
+            recI[r2] = make_uint2(px, sm);
+            recZ[r2] = 0;
+            got = true;
+          }
+        }
+        pool_next += min(static_cast<uint32_t>(__popc(need)), avail);
+      }
+      // a record that found no pixel this time (tail of the last group) is tried again unless the work is exhausted
+      if (act && !got && !exhausted) { recT[r2].w = __int_as_float(kFresh); retry = true; }
+      const uint32_t mr = __ballot_sync(0xffffffffu, got), mm = __ballot_sync(0xffffffffu, retry);
+      if (got) q_ready[n_ready + __popc(mr & lt)] = static_cast<uint8_t>(r2);
+      if (retry) q_miss[n_miss + __popc(mm & lt)] = static_cast<uint8_t>(r2);
+      n_ready += __popc(mr); n_miss += __popc(mm);
+      __syncwarp();
+      continue;
+    }
+    if (idle == 0xffffffffu && n_ready == 0u) break;   // nothing in flight, nothing queued (hit/miss would have run)
+
+    // ---- (4) traversal: STEPS node-or-leaf steps for every lane holding a ray --------------------------------------------
+#pragma unroll 1
+    for (int step = 0; step < STEPS; ++step) {
+      if (state == TRAV && node >= 0) {
+        if (STATS) ++n_nodes;
+        const float4 q0 = ld4<SMEM>(tb.nodes, 4 * node), q1 = ld4<SMEM>(tb.nodes, 4 * node + 1), q2 = ld4<SMEM>(tb.nodes, 4 * node + 2),
+                     q3 = ld4<SMEM>(tb.nodes, 4 * node + 3);
+        float t0x = fmaf(q0.x, idx, -odx), t1x = fmaf(q0.w, idx, -odx);
+        float t0y = fmaf(q0.y, idy, -ody), t1y = fmaf(q1.x, idy, -ody);
+        float t0z = fmaf(q0.z, idz, -odz), t1z = fmaf(q1.y, idz, -odz);
+        const float ln = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), kTMin));
+        const float lf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best_t));
+        t0x = fmaf(q1.z, idx, -odx); t1x = fmaf(q2.y, idx, -odx);
+        t0y = fmaf(q1.w, idy, -ody); t1y = fmaf(q2.z, idy, -ody);
+        t0z = fmaf(q2.x, idz, -odz); t1z = fmaf(q2.w, idz, -odz);
+        const float rn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), kTMin));
+        const float rf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best_t));
+        const bool hl = ln <= lf, hr = rn <= rf;
+        const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
+        if (hl && hr) {
+          const bool lfirst = ln <= rn;
+          node = lfirst ? left : right;
+          if (sp < kBvhStack) stack[sp++] = lfirst ? right : left;
+        } else if (hl) {
+          node = left;
+        } else if (hr) {
+          node = right;
+        } else if (sp > 0) {
+          node = stack[--sp];
+        } else {
+          node = kMiss; state = FIN;
+        }
+      }
+      if (state == TRAV && node < 0) {
+        const uint32_t v = static_cast<uint32_t>(~node);
+        auto test_ref = [&](uint32_t ref) {
+          const int i = static_cast<int>(ref & 0x1fffffffu);
+          if (ref >> 30) {
+            if (STATS) ++n_tri;
+            const float4 q0 = ld4<SMEM>(tb.tri, 3 * i), q1 = ld4<SMEM>(tb.tri, 3 * i + 1), q2 = ld4<SMEM>(tb.tri, 3 * i + 2);
+            const float t = triangle_hit<float>(o, d, mk<float>(q0.x, q0.y, q0.z), mk<float>(q1.x, q1.y, q1.z), mk<float>(q2.x, q2.y, q2.z),
+                                                mk<float>(q0.w, q1.w, q2.w), kTMin, best_t);
+            if (t >= 0.0f) { best_t = t; best_i = kHitTri | i; }
+          } else {
+            if (STATS) ++n_tests;
+            const float4 A = ld4<SMEM>(tb.sphA, i), B = ld4<SMEM>(tb.sphB, i);
+            const float t = sphere_hit_fast(o, d, qa, qia, mk<float>(fmaf(tm, B.x, A.x), fmaf(tm, B.y, A.y), fmaf(tm, B.z, A.z)), B.w, kTMin, best_t);
+            if (t >= 0.0f) { best_t = t; best_i = i; }
+          }
+        };
+        test_ref(v);   // single-primitive leaves only: the child code is the primitive reference (launch_render checks leaf_direct)
+        if (sp > 0) node = stack[--sp];
+        else { node = kMiss; state = FIN; }
+      }
+    }
+  }
+
+  unsigned long long c_rays = n_rays, c_paths = n_paths, c_tests = n_tests, c_nodes = n_nodes, c_tri = n_tri;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    c_rays += __shfl_xor_sync(0xffffffffu, c_rays, off);
+    c_paths += __shfl_xor_sync(0xffffffffu, c_paths, off);
+    if (STATS) {
+      c_tests += __shfl_xor_sync(0xffffffffu, c_tests, off);
+      c_nodes += __shfl_xor_sync(0xffffffffu, c_nodes, off);
+      c_tri += __shfl_xor_sync(0xffffffffu, c_tri, off);
+    }
+  }
+  if (lane == 0) {
+    atomicAdd(p.counters + kCtrRays, c_rays);
+    atomicAdd(p.counters + kCtrPaths, c_paths);
+    if (STATS) {
+      atomicAdd(p.counters + kCtrSphereTests, c_tests);
+      atomicAdd(p.counters + kCtrNodes, c_nodes);
+      atomicAdd(p.counters + kCtrTriTests, c_tri);
     }
   }
 }
@@ -919,6 +1257,22 @@ static cudaError_t launch_bvh_t(const RenderParams& p, int sm_count, size_t smem
   return cudaGetLastError();
 }
 
+template <bool SMEM, bool STATS, int NW, int P, int STEPS, int BATCH>
+static cudaError_t launch_wf_t(const RenderParams& p, int sm_count, size_t smem, cudaStream_t stream) {
+  auto kern = k_render_wf<SMEM, STATS, NW, P, STEPS, BATCH>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  unsigned long long want = (p.n_units + NW - 1) / NW;
+  unsigned long long blocks = static_cast<unsigned long long>(sm_count) * per_sm;
+  if (want < blocks) blocks = want < 1 ? 1 : want;
+  kern<<<static_cast<unsigned>(blocks), NW * 32, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
 // bytes of shared memory the BVH kernel needs to stage the whole scene (0 = does not fit, use global memory)
 size_t bvh_smem_bytes(const RenderParams& p) {
   const size_t nspheres = static_cast<size_t>(p.sc.n_static + p.sc.n_moving);
@@ -927,7 +1281,20 @@ size_t bvh_smem_bytes(const RenderParams& p) {
   return bytes <= 72 * 1024 ? bytes : 0;
 }
 
-cudaError_t launch_render(const RenderParams& p, int mode, int rays_per_lane, bool stats, int sm_count, cudaStream_t stream) {
+// shared-memory layout of the staged BVH tables: [16 B mbarrier][nodes][leaf refs][sphA][sphB][triangles][per-warp records]
+static SmemLayout smem_layout(const RenderParams& p) {
+  SmemLayout so{};
+  const uint32_t nspheres = static_cast<uint32_t>(p.sc.n_static + p.sc.n_moving);
+  so.b_nodes = static_cast<uint32_t>(p.sc.n_nodes) * 64u; so.b_refs = (p.n_leaf_refs * 4u + 15u) & ~15u; so.b_sph = nspheres * 16u;
+  so.b_tri = static_cast<uint32_t>(p.sc.n_tri) * 48u;
+  so.nodes = 16u; so.refs = so.nodes + so.b_nodes; so.sa = so.refs + so.b_refs; so.sb = so.sa + so.b_sph; so.tri = so.sb + so.b_sph;
+  so.records = so.tri + so.b_tri;
+  return so;
+}
+
+cudaError_t launch_render(const RenderParams& p_in, int mode, int rays_per_lane, bool stats, int sm_count, cudaStream_t stream) {
+  RenderParams p = p_in;
+  p.so = smem_layout(p);
   const size_t smem = mode == 0 ? 16 + static_cast<size_t>(p.sc.n_static + p.sc.n_moving + 1) * 32 : 0;
   if (mode == 0) {
     // rays_per_lane: paths in flight per lane (1, 2 or 4); 2 measured fastest
@@ -937,6 +1304,13 @@ cudaError_t launch_render(const RenderParams& p, int mode, int rays_per_lane, bo
   }
   // BVH kernel: 8 traversal steps between service checks, service once 24 lanes need it, 4 CTAs/SM (tuning record in DESIGN.md)
   const size_t bsm = bvh_smem_bytes(p);
+  // sphere scenes whose tables leave room for the per-warp path records: wavefront-per-warp kernel, 28 warps per SM (72 registers),
+  // 96 records per warp, 16 traversal steps between exchanges, shading batches of 32 (tuning record in DESIGN.md)
+  constexpr int kWfWarps = 28, kWfRecords = 96;
+  const size_t wf_smem = p.so.records + static_cast<size_t>(kWfWarps) * wf_warp_bytes(kWfRecords);
+  if (bsm && p.sc.leaf_direct && wf_smem <= 227u * 1024u && rays_per_lane != 100)
+    return stats ? launch_wf_t<true, true, kWfWarps, kWfRecords, 16, 32>(p, sm_count, wf_smem, stream)
+                 : launch_wf_t<true, false, kWfWarps, kWfRecords, 16, 32>(p, sm_count, wf_smem, stream);
 #define RTW_BVH(ST, SV, MB)                                                                                         \
   return bsm ? (stats ? launch_bvh_t<true, true, ST, SV, MB>(p, sm_count, bsm, stream) : launch_bvh_t<true, false, ST, SV, MB>(p, sm_count, bsm, stream)) \
              : (stats ? launch_bvh_t<false, true, ST, SV, MB>(p, sm_count, 0, stream) : launch_bvh_t<false, false, ST, SV, MB>(p, sm_count, 0, stream))
