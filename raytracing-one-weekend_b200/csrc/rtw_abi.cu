@@ -417,7 +417,7 @@ int rtw_flatten_info(const rtw_scene_desc* desc, rtw_flatten_report* out) {
     for (int which = 0; which < 2; ++which) {
       const int32_t code = which == 0 ? nodes[n].left : nodes[n].right;
       if (code >= 0) { todo.push_back({code, dpt + 1}); continue; }
-      if (which == 1 && seen.size() <= static_cast<size_t>(hf.leaf_direct ? 1 : 31) && hf.n_nodes == 1 && nodes[n].rmin_z > nodes[n].rmax[2])
+      if (which == 1 && seen.size() <= static_cast<size_t>(hf.leaf_direct ? 1 : 31) && hf.n_nodes == 1 && nodes[n].rc_z >= 1.0e38f)
         continue;  // the never-entered filler child of a single-leaf tree (inverted box)
       const uint32_t v = static_cast<uint32_t>(~code);
       if (hf.leaf_direct) visit_ref(v);

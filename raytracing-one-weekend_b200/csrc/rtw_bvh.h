@@ -22,12 +22,13 @@ struct Box3 {
   }
 };
 
-struct PackedNode {  // 4 x float4, see DevScene::nodes
-  float lmin[3], lmax_x;
-  float lmax_yz[2], rmin_xy[2];
-  float rmin_z, rmax[3];
+struct PackedNode {  // 4 x float4, see DevScene::nodes: each child box as centre + half-extent
+  float lc[3], le_x;
+  float le_yz[2], rc_xy[2];
+  float rc_z, re[3];
   int32_t left, right, pad0, pad1;
 };
+constexpr float kEmptyChildCentre = 3.0e38f;  // centre of a never-entered filler child (half-extent 0)
 static_assert(sizeof(PackedNode) == 64, "node must be 64 bytes");
 
 class BvhBuilder {
@@ -225,23 +226,31 @@ class BvhBuilder {
   std::vector<Item> items_;
   PackedNode* ext_nodes_ = nullptr;
 
-  static void pad(Box3& b) {  // conservative against the fp32 slab arithmetic
+  // Child boxes are stored as centre c and half-extent e (node_slabs on the device: t = (c -+ e) / d - o / d costs FMA-pipe
+  // operations instead of min/max ALU operations).  e is rounded up so that [c - e, c + e] contains the exact box plus four ulps of
+  // its largest coordinate: conservative against the fp32 slab arithmetic.
+  static void centre_extent(const Box3& b, float c[3], float e[3]) {
     for (int k = 0; k < 3; ++k) {
-      if (!(b.lo[k] <= b.hi[k])) continue;
-      const float m = std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k]));
-      const float e = 4.0f * 1.1920929e-7f * m + 1e-30f;
-      b.lo[k] -= e; b.hi[k] += e;
+      if (!(b.lo[k] <= b.hi[k])) { c[k] = kEmptyChildCentre; e[k] = 0.0f; continue; }
+      const double lo = b.lo[k], hi = b.hi[k];
+      c[k] = static_cast<float>(0.5 * (lo + hi));
+      const double m = std::max(std::fabs(lo), std::fabs(hi));
+      const double need = std::max(hi - static_cast<double>(c[k]), static_cast<double>(c[k]) - lo) + 4.0 * 1.1920929e-7 * m + 1e-30;
+      float ef = static_cast<float>(need);
+      if (static_cast<double>(ef) < need) ef = std::nextafter(ef, std::numeric_limits<float>::infinity());
+      e[k] = ef;
     }
   }
-  static void set_child(PackedNode& nd, int which, Box3 b, int32_t code) {
-    pad(b);
+  static void set_child(PackedNode& nd, int which, const Box3& b, int32_t code) {
+    float c[3], e[3];
+    centre_extent(b, c, e);
     if (which == 0) {
-      nd.lmin[0] = b.lo[0]; nd.lmin[1] = b.lo[1]; nd.lmin[2] = b.lo[2];
-      nd.lmax_x = b.hi[0]; nd.lmax_yz[0] = b.hi[1]; nd.lmax_yz[1] = b.hi[2];
+      nd.lc[0] = c[0]; nd.lc[1] = c[1]; nd.lc[2] = c[2];
+      nd.le_x = e[0]; nd.le_yz[0] = e[1]; nd.le_yz[1] = e[2];
       nd.left = code;
     } else {
-      nd.rmin_xy[0] = b.lo[0]; nd.rmin_xy[1] = b.lo[1]; nd.rmin_z = b.lo[2];
-      nd.rmax[0] = b.hi[0]; nd.rmax[1] = b.hi[1]; nd.rmax[2] = b.hi[2];
+      nd.rc_xy[0] = c[0]; nd.rc_xy[1] = c[1]; nd.rc_z = c[2];
+      nd.re[0] = e[0]; nd.re[1] = e[1]; nd.re[2] = e[2];
       nd.right = code;
     }
   }

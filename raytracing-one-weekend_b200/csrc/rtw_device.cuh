@@ -48,9 +48,9 @@ struct DevScene {
   const float4* tri;
   const int2* triId;
   int32_t n_tri;
-  // BVH over small spheres + triangles: 4 float4 per node
-  //   q0 = (lmin.x, lmin.y, lmin.z, lmax.x) q1 = (lmax.y, lmax.z, rmin.x, rmin.y)
-  //   q2 = (rmin.z, rmax.x, rmax.y, rmax.z) q3 = (left, right, -, -) as int bits
+  // BVH over small spheres + triangles: 4 float4 per node, each child box as centre c and half-extent e
+  //   q0 = (lc.x, lc.y, lc.z, le.x) q1 = (le.y, le.z, rc.x, rc.y)
+  //   q2 = (rc.z, re.x, re.y, re.z) q3 = (left, right, -, -) as int bits
   //   child >= 0: inner node index; child < 0: leaf, ~child = (first << 5) | count  into leafRefs,
   //   or (leaf_direct) ~child = the primitive reference itself with bit 29 set (so that the code is never -1 = "no node")
   const float4* nodes;
@@ -172,6 +172,22 @@ __device__ __forceinline__ void camera_ray(const Cam& cam, T s, T t, T diskx, T 
 // ---------------------------------------------------------------------------------------------------------
 // Intersection
 // ---------------------------------------------------------------------------------------------------------
+// Slab test of both children of a BVH node (Aabb::hit, common-model.h:71-84) against [kTMin, tmax].  With the box stored as
+// centre c and half-extent e >= 0 the entry/exit parameters along one axis are (c -+ e) * (1/d) - o/d = tc -+ |e * (1/d)|:
+// one FFMA, one FMUL and two FADD (with the |.| operand modifier) on the FMA pipe, and no per-axis min/max on the ALU pipe,
+// which is the busiest pipe of the traversal kernels (profiles/).
+__device__ __forceinline__ void node_slabs(const float4 q0, const float4 q1, const float4 q2, float idx, float idy, float idz, float odx,
+                                           float ody, float odz, float tmax, float& ln, float& lf, float& rn, float& rf) {
+  float cx = fmaf(q0.x, idx, -odx), cy = fmaf(q0.y, idy, -ody), cz = fmaf(q0.z, idz, -odz);
+  float wx = fabsf(q0.w * idx), wy = fabsf(q1.x * idy), wz = fabsf(q1.y * idz);
+  ln = fmaxf(fmaxf(cx - wx, cy - wy), fmaxf(cz - wz, kTMin));
+  lf = fminf(fminf(cx + wx, cy + wy), fminf(cz + wz, tmax));
+  cx = fmaf(q1.z, idx, -odx); cy = fmaf(q1.w, idy, -ody); cz = fmaf(q2.x, idz, -odz);
+  wx = fabsf(q2.y * idx); wy = fabsf(q2.z * idy); wz = fabsf(q2.w * idz);
+  rn = fmaxf(fmaxf(cx - wx, cy - wy), fmaxf(cz - wz, kTMin));
+  rf = fminf(fminf(cx + wx, cy + wy), fminf(cz + wz, tmax));
+}
+
 // sphere_hit_helper (common-model.cpp:64-91).  Same roots and the same accept rule (nearer root if inside
 // [tmin,tmax], else the farther one), but the discriminant is evaluated as a*(r^2 - |oc - (h/a) d|^2), which is
 // algebraically h^2 - a*c and does not cancel in fp32 (Haines et al., "Precision improvements for ray/sphere

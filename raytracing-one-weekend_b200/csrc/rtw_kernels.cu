@@ -270,16 +270,8 @@ __device__ __forceinline__ void trace_bvh(const DevScene& sc, F3 o, F3 d, float 
     const float4 q0 = __ldg(&sc.nodes[4 * node]), q1 = __ldg(&sc.nodes[4 * node + 1]), q2 = __ldg(&sc.nodes[4 * node + 2]),
                  q3 = __ldg(&sc.nodes[4 * node + 3]);
     // slab test of both children against [tmin, best_t]
-    float t0x = fmaf(q0.x, idx, -odx), t1x = fmaf(q0.w, idx, -odx);
-    float t0y = fmaf(q0.y, idy, -ody), t1y = fmaf(q1.x, idy, -ody);
-    float t0z = fmaf(q0.z, idz, -odz), t1z = fmaf(q1.y, idz, -odz);
-    const float ln = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), kTMin));
-    const float lf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best_t));
-    t0x = fmaf(q1.z, idx, -odx); t1x = fmaf(q2.y, idx, -odx);
-    t0y = fmaf(q1.w, idy, -ody); t1y = fmaf(q2.z, idy, -ody);
-    t0z = fmaf(q2.x, idz, -odz); t1z = fmaf(q2.w, idz, -odz);
-    const float rn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), kTMin));
-    const float rf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best_t));
+    float ln, lf, rn, rf;
+    node_slabs(q0, q1, q2, idx, idy, idz, odx, ody, odz, best_t, ln, lf, rn, rf);
     const bool hl = ln <= lf, hr = rn <= rf;
     const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
     if (hl && hr) {
@@ -646,16 +638,8 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
         if (STATS) ++n_nodes;
         const float4 q0 = ld4<SMEM>(tb.nodes, 4 * node), q1 = ld4<SMEM>(tb.nodes, 4 * node + 1), q2 = ld4<SMEM>(tb.nodes, 4 * node + 2),
                      q3 = ld4<SMEM>(tb.nodes, 4 * node + 3);
-        float t0x = fmaf(q0.x, idx, -odx), t1x = fmaf(q0.w, idx, -odx);
-        float t0y = fmaf(q0.y, idy, -ody), t1y = fmaf(q1.x, idy, -ody);
-        float t0z = fmaf(q0.z, idz, -odz), t1z = fmaf(q1.y, idz, -odz);
-        const float ln = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), kTMin));
-        const float lf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best_t));
-        t0x = fmaf(q1.z, idx, -odx); t1x = fmaf(q2.y, idx, -odx);
-        t0y = fmaf(q1.w, idy, -ody); t1y = fmaf(q2.z, idy, -ody);
-        t0z = fmaf(q2.x, idz, -odz); t1z = fmaf(q2.w, idz, -odz);
-        const float rn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), kTMin));
-        const float rf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best_t));
+        float ln, lf, rn, rf;
+        node_slabs(q0, q1, q2, idx, idy, idz, odx, ody, odz, best_t, ln, lf, rn, rf);
         const bool hl = ln <= lf, hr = rn <= rf;
         const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
         if (hl && hr) {
@@ -984,16 +968,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_render_wf(const __grid_constant_
         if (STATS) ++n_nodes;
         const float4 q0 = ld4<SMEM>(tb.nodes, 4 * node), q1 = ld4<SMEM>(tb.nodes, 4 * node + 1), q2 = ld4<SMEM>(tb.nodes, 4 * node + 2),
                      q3 = ld4<SMEM>(tb.nodes, 4 * node + 3);
-        float t0x = fmaf(q0.x, idx, -odx), t1x = fmaf(q0.w, idx, -odx);
-        float t0y = fmaf(q0.y, idy, -ody), t1y = fmaf(q1.x, idy, -ody);
-        float t0z = fmaf(q0.z, idz, -odz), t1z = fmaf(q1.y, idz, -odz);
-        const float ln = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), kTMin));
-        const float lf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best_t));
-        t0x = fmaf(q1.z, idx, -odx); t1x = fmaf(q2.y, idx, -odx);
-        t0y = fmaf(q1.w, idy, -ody); t1y = fmaf(q2.z, idy, -ody);
-        t0z = fmaf(q2.x, idz, -odz); t1z = fmaf(q2.w, idz, -odz);
-        const float rn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), kTMin));
-        const float rf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best_t));
+        float ln, lf, rn, rf;
+        node_slabs(q0, q1, q2, idx, idy, idz, odx, ody, odz, best_t, ln, lf, rn, rf);
         const bool hl = ln <= lf, hr = rn <= rf;
         const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
         if (hl && hr) {
