@@ -4,7 +4,7 @@ set -euo pipefail
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 OUT=../librtw_b200.so
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -ccbin /usr/bin/g++"
+FLAGS="${RTW_EXTRA:-} -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -ccbin /usr/bin/g++"
 newer=0
 for f in rtw_kernels.cu rtw_abi.cu rtw_multi.cu rtw_device.cuh rtw_internal.h rtw_bvh.h ../../include/rtw_b200.h build.sh; do
   if [ ! -e "$OUT" ] || [ "$f" -nt "$OUT" ]; then newer=1; fi
