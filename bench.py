@@ -202,6 +202,8 @@ def main() -> int:
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (a reduced-size run is NOT the headline)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "spheres", "bvh"])
     ap.add_argument("--rays-per-lane", type=int, default=0)
+    ap.add_argument("--split", default="spp", choices=["spp", "rows"], help="multi-GPU work split: samples + one reduce (default), or interleaved row tiles + one gather (SURVEY 8(e) alternative)")
+    ap.add_argument("--tile-rows", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--traffic-bytes", type=float, default=None, help="override: dram bytes per launch of the render kernel from an ncu --set full capture")
@@ -234,10 +236,15 @@ def main() -> int:
     kernel = {"auto": rtw.KERNEL_AUTO, "spheres": rtw.KERNEL_SPHERES_SMEM, "bvh": rtw.KERNEL_BVH}[args.kernel]
     scene = build_scene(rtw, args.workload, wl)
     scene_has_triangles = bool((scene.prims["kind"] == rtw.RTW_TRIANGLE).any())
-    s_begin, s_end = rtw.sample_shard(spp, rank, world)
+    rows = args.split == "rows" and world > 1
+    s_begin, s_end = (0, spp) if rows else rtw.sample_shard(spp, rank, world)
+    row_tiles = (args.tile_rows, world, rank) if rows else None
     ds = rtw.DeviceScene(scene, local_rank)
     npix = width * height
-    accum = torch.zeros((height, width, 4), dtype=torch.int64, device=dev)
+    # row split: this rank's packed tiles; rank 0 also holds the assembled image
+    local_rows = rtw.row_tile_local_rows(height, args.tile_rows, world) if rows else height
+    accum = torch.zeros((local_rows, width, 4), dtype=torch.int64, device=dev)
+    accum_full = torch.zeros((height, width, 4), dtype=torch.int64, device=dev) if rows and rank == 0 else None
     out_f32 = torch.zeros((height, width, 4), dtype=torch.float32, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream()
@@ -245,11 +252,21 @@ def main() -> int:
     def step(collect_stats=False):
         accum.zero_()
         st = ds.render_into(accum, width, height, s_end - s_begin, depth, sample_begin=s_begin, stream_ptr=stream.cuda_stream, seed=0,
-                            kernel=kernel, rays_per_lane=args.rays_per_lane, want_stats=collect_stats)
-        rtw.reduce_accum(accum, dst=0)
-        if rank == 0:
-            ds.accum_to_float(accum, out_f32, npix, stream_ptr=stream.cuda_stream)
+                            kernel=kernel, rays_per_lane=args.rays_per_lane, want_stats=collect_stats, row_tiles=row_tiles)
+        combine()
         return st
+
+    def combine():
+        """The one collective of the step, then the float accumulation buffer on rank 0."""
+        if rows:
+            g = rtw.gather_row_tiles(accum, dst=0)
+            if rank == 0:
+                ds.untile(g, accum_full, width, height, args.tile_rows, world, stream_ptr=stream.cuda_stream)
+                ds.accum_to_float(accum_full, out_f32, npix, stream_ptr=stream.cuda_stream)
+        else:
+            rtw.reduce_accum(accum, dst=0)
+            if rank == 0:
+                ds.accum_to_float(accum, out_f32, npix, stream_ptr=stream.cuda_stream)
 
     def barrier():
         if world > 1:
@@ -274,11 +291,9 @@ def main() -> int:
         a.record(stream)
         accum.zero_()
         ds.render_into(accum, width, height, s_end - s_begin, depth, sample_begin=s_begin, stream_ptr=stream.cuda_stream, seed=0, kernel=kernel,
-                       rays_per_lane=args.rays_per_lane)
+                       rays_per_lane=args.rays_per_lane, row_tiles=row_tiles)
         k.record(stream)   # end of the render kernel (for the roofline)
-        rtw.reduce_accum(accum, dst=0)
-        if rank == 0:
-            ds.accum_to_float(accum, out_f32, npix, stream_ptr=stream.cuda_stream)
+        combine()
         b.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -317,10 +332,9 @@ def main() -> int:
                 ds2 = rtw.DeviceScene(scene, local_rank)  # host arrays -> HBM
                 accum.zero_()
                 ds2.render_into(accum, width, height, s_end - s_begin, depth, sample_begin=s_begin, stream_ptr=stream.cuda_stream, seed=0,
-                                kernel=kernel, rays_per_lane=args.rays_per_lane)
-                rtw.reduce_accum(accum, dst=0)
+                                kernel=kernel, rays_per_lane=args.rays_per_lane, row_tiles=row_tiles)
+                combine()
                 if rank == 0:
-                    ds2.accum_to_float(accum, out_f32, npix, stream_ptr=stream.cuda_stream)
                     pinned.copy_(out_f32, non_blocking=False)
                 torch.cuda.synchronize()
                 ds2.close()
@@ -383,7 +397,7 @@ def main() -> int:
         cs = min(8, s_end - s_begin)
         accum.zero_()
         sst = ds.render_into(accum, width, height, cs, depth, sample_begin=s_begin, stream_ptr=stream.cuda_stream, seed=0, kernel=kernel,
-                             rays_per_lane=args.rays_per_lane, want_stats=True, stats=True)
+                             rays_per_lane=args.rays_per_lane, want_stats=True, stats=True, row_tiles=row_tiles)
         nodes_pr, tests_pr, tris_pr = sst["node_visits"] / sst["rays"], sst["sphere_tests"] / sst["rays"], sst["tri_tests"] / sst["rays"]
         flop = rays_gpu * (nodes_pr * 24.0 + tests_pr * test_flop + tris_pr * 36.0 + n_big * FLOP_STATIC_TEST + FLOP_SHADE) + (rays_gpu - paths_gpu) * FLOP_HIT
         ach = flop / (kernel_ms * 1e-3) / 1e12
@@ -424,7 +438,8 @@ def main() -> int:
         "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "width": width, "height": height, "spp": spp, "max_child_rays": depth, "primitives": int(len(scene.prims)),
-                   "parallelism": f"spp-shard x{world}, one int64 NCCL reduce", "kernel": "spheres_smem (K1)" if kernel_used == rtw.KERNEL_SPHERES_SMEM else "bvh (K2)",
+                   "parallelism": (f"row tiles of {args.tile_rows} rows interleaved over {world} GPUs, one int64 NCCL gather" if rows
+                                   else f"spp-shard x{world}, one int64 NCCL reduce"), "kernel": "spheres_smem (K1)" if kernel_used == rtw.KERNEL_SPHERES_SMEM else "bvh (K2)",
                    "l2": "256 MB buffer written between timed iterations (scene tables live in shared memory; accumulation buffer 66 MB)"},
         "mrays_per_s": rays_total / (ms_per_step * 1e-3) / 1e6, "rays_per_path": rays_total / paths_total,
         "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks, "roofline": roofline, "roofline_sphere_sweep": roofline_sweep,

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RTW_ABI_VERSION 1
+#define RTW_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define RTW_API __attribute__((visibility("default")))
@@ -37,7 +37,7 @@ extern "C" {
 enum rtw_prim_kind { RTW_SPHERE = 0, RTW_MOVING_SPHERE = 1, RTW_TRIANGLE = 2 };
 enum rtw_mat_kind { RTW_LAMBERTIAN = 0, RTW_METAL = 1, RTW_DIELECTRIC = 2 };
 enum rtw_kernel { RTW_KERNEL_AUTO = 0, RTW_KERNEL_SPHERES_SMEM = 1, RTW_KERNEL_BVH = 2 };
-enum rtw_flags { RTW_FLAG_STATS = 1 };
+enum rtw_flags { RTW_FLAG_STATS = 1, RTW_FLAG_SPLIT_ROWS = 2 };
 
 /* One primitive, in scene insertion order (index in the array == primitive id used for parity).
  * Mirrors the constructor arguments of Sphere / MovingSphere / Triangle (oo-primitives.h:28,49,76). */
@@ -82,7 +82,10 @@ typedef struct rtw_render_cfg {
   int32_t device;                 /* CUDA device ordinal */
   int32_t flags;                  /* rtw_flags */
   int32_t rays_per_lane;          /* 0 = default; sphere kernel variant (1, 2 or 4 paths in flight per lane) */
-  int32_t reserved;
+  /* Row-tile split (the alternative to the sample split): the image is cut into tiles of row_tile_rows rows and
+   * this call renders tiles row_tile_index, row_tile_index + row_tile_count, ... at the full sample range.  The accumulation
+   * buffer then holds only those tiles, packed: rtw_row_tile_local_rows() rows of `width` pixels.  row_tile_count <= 1: whole image. */
+  int32_t row_tile_rows, row_tile_count, row_tile_index;
 } rtw_render_cfg;
 
 typedef struct rtw_stats {
@@ -123,10 +126,19 @@ RTW_API int rtw_render_device(const rtw_scene* scene, const rtw_render_cfg* cfg,
 RTW_API int rtw_accum_to_float(const int64_t* accum_fx, float* accum_rgba, int64_t npixels, int32_t device,
                        void* cuda_stream);
 
+/* Rows of the packed accumulation buffer of ONE participant of a row-tile split (the same for every participant, so that
+ * the buffers can be gathered with equal counts): ceil(ceil(height / tile_rows) / count) * tile_rows. */
+RTW_API int32_t rtw_row_tile_local_rows(int32_t height, int32_t tile_rows, int32_t count);
+/* gathered: `count` packed buffers back to back ([count][local_rows][width][4] int64, device) -> accum_fx ([height][width][4]). */
+RTW_API int rtw_untile_accum(const int64_t* gathered, int64_t* accum_fx, int32_t width, int32_t height, int32_t tile_rows,
+                     int32_t count, int32_t device, void* cuda_stream);
+
 /* Single-process multi-GPU render: samples split evenly over devices 0..ngpus-1 (requires ngpus | spp), one
  * ncclReduce(sum) of the accumulation buffers onto device 0 over NVLink, then one download. */
 RTW_API int rtw_render_multi_gpu(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, int32_t ngpus, float* accum_rgba,
                          rtw_stats* stats);
+/* The same with cfg->flags & RTW_FLAG_SPLIT_ROWS: every GPU renders ALL samples of its interleaved row tiles (cfg->row_tile_rows
+ * rows each, default 8) and the packed buffers are gathered on device 0 (ncclSend/ncclRecv), no summation. */
 
 /* write_color (render.cpp:11-20) on the device: rgb8 = int(256 * clamp(sqrt(sum / spp), 0, 0.999)).
  * accum_rgba and rgb8 are HOST buffers (npixels*4 floats in, npixels*3 bytes out). */

@@ -29,6 +29,7 @@ RTW_SPHERE, RTW_MOVING_SPHERE, RTW_TRIANGLE = 0, 1, 2
 RTW_LAMBERTIAN, RTW_METAL, RTW_DIELECTRIC = 0, 1, 2
 KERNEL_AUTO, KERNEL_SPHERES_SMEM, KERNEL_BVH = 0, 1, 2
 FLAG_STATS = 1
+FLAG_SPLIT_ROWS = 2
 
 
 class RtwError(RuntimeError):
@@ -62,7 +63,8 @@ class SceneDesc(C.Structure):
 class RenderCfg(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("sample_begin", C.c_int32), ("sample_end", C.c_int32),
                 ("max_child_rays", C.c_int32), ("kernel", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32),
-                ("flags", C.c_int32), ("rays_per_lane", C.c_int32), ("reserved", C.c_int32)]
+                ("flags", C.c_int32), ("rays_per_lane", C.c_int32), ("row_tile_rows", C.c_int32), ("row_tile_count", C.c_int32),
+                ("row_tile_index", C.c_int32)]
 
 
 class FlattenReport(C.Structure):
@@ -102,6 +104,8 @@ ABI = {
     "rtw_release_cached_buffers": (None, []),
     "rtw_render_device": (C.c_int, [_VP, C.POINTER(RenderCfg), _VP, _VP, C.POINTER(Stats)]),
     "rtw_accum_to_float": (C.c_int, [_VP, _VP, C.c_int64, C.c_int32, _VP]),
+    "rtw_row_tile_local_rows": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
+    "rtw_untile_accum": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _VP]),
     "rtw_render_multi_gpu": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(RenderCfg), C.c_int32, _VP, C.POINTER(Stats)]),
     "rtw_finalize_rgb8": (C.c_int, [_VP, C.c_int64, C.c_int32, C.c_int32, _VP]),
     "rtw_primary_hits": (C.c_int, [C.POINTER(SceneDesc), C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32,
@@ -277,12 +281,15 @@ def image_height(width: int, aspect: float) -> int:
 # Rendering through the C ABI
 # ----------------------------------------------------------------------------------------------------------
 def make_cfg(width, height, spp, max_child_rays=20, sample_begin=0, kernel=KERNEL_AUTO, seed=0, device=0, stats=False,
-             rays_per_lane=0) -> RenderCfg:
+             rays_per_lane=0, row_tiles=None, flags=0) -> RenderCfg:
+    """row_tiles = (rows per tile, number of participants, index of this participant) selects the row-tile split."""
     c = RenderCfg()
     c.width, c.height = width, height
     c.sample_begin, c.sample_end = sample_begin, sample_begin + spp
     c.max_child_rays, c.kernel, c.seed, c.device = max_child_rays, kernel, seed, device
-    c.flags = FLAG_STATS if stats else 0
+    c.flags = (FLAG_STATS if stats else 0) | flags
+    if row_tiles is not None:
+        c.row_tile_rows, c.row_tile_count, c.row_tile_index = row_tiles
     c.rays_per_lane = rays_per_lane
     return c
 
@@ -392,6 +399,11 @@ class DeviceScene:
         _check(lib().rtw_accum_to_float(_VP(accum_fx.data_ptr()), _VP(out_f32.data_ptr()), npixels, self.device,
                                         _VP(stream_ptr)), "rtw_accum_to_float")
 
+    def untile(self, gathered, accum_fx, width, height, tile_rows, count, stream_ptr=0):
+        """[count][local_rows][width][4] int64 gathered buffers -> [height][width][4] (device tensors)."""
+        _check(lib().rtw_untile_accum(_VP(gathered.data_ptr()), _VP(accum_fx.data_ptr()), width, height, tile_rows, count, self.device,
+                                      _VP(stream_ptr)), "rtw_untile_accum")
+
     def close(self):
         if self._h:
             lib().rtw_scene_free(self._h)
@@ -435,6 +447,37 @@ def sample_shard(spp: int, rank: int, world: int) -> tuple[int, int]:
         raise ValueError(f"samples_per_pixel={spp} does not split evenly over {world} GPUs")
     per = spp // world
     return rank * per, (rank + 1) * per
+
+
+def row_tile_local_rows(height: int, tile_rows: int, count: int) -> int:
+    """Rows of one participant's packed buffer in a row-tile split (same formula as rtw_row_tile_local_rows)."""
+    if height < 1 or tile_rows < 1 or count < 1:
+        raise ValueError("bad row-tile split")
+    tiles = -(-height // tile_rows)
+    return -(-tiles // count) * tile_rows
+
+
+def untile_rows(gathered, height: int, tile_rows: int, count: int):
+    """Host/torch restatement of rtw_untile_accum for tensors on any device: gathered [count, local_rows, W, C] ->
+    [height, W, C].  Tile t of the image belongs to participant t % count and is its (t // count)-th tile."""
+    local_rows = gathered.shape[1]
+    tiles_local = local_rows // tile_rows
+    g = gathered.reshape(count, tiles_local, tile_rows, *gathered.shape[2:])
+    full = g.transpose(0, 1).reshape(tiles_local * count * tile_rows, *gathered.shape[2:])
+    return full[:height]
+
+
+def gather_row_tiles(accum_local, dst: int = 0):
+    """The collective of the row-tile alternative: the packed per-rank buffers are gathered on `dst`, no summation.
+    Returns the [world, local_rows, W, 4] tensor on dst (None elsewhere); world 1 is a view of the input."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return accum_local.unsqueeze(0)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    out = torch.empty((world, *accum_local.shape), dtype=accum_local.dtype, device=accum_local.device) if rank == dst else None
+    dist.gather(accum_local, list(out.unbind(0)) if rank == dst else None, dst=dst)
+    return out
 
 
 def reduce_accum(accum_fx, dst: int = 0):

@@ -352,6 +352,14 @@ int fill_params(const rtw_scene* sc, const rtw_render_cfg* cfg, int mode, unsign
   p->counters = sc->counters;
   p->width = static_cast<uint32_t>(cfg->width); p->height = static_cast<uint32_t>(cfg->height);
   p->npix = p->width * p->height;
+  p->tile_rows = 1; p->tile_count = 1; p->tile_index = 0;
+  if (cfg->row_tile_count > 1) {
+    if (cfg->row_tile_rows < 1 || cfg->row_tile_index < 0 || cfg->row_tile_index >= cfg->row_tile_count)
+      return fail("render: row-tile split needs row_tile_rows >= 1 and 0 <= row_tile_index < row_tile_count");
+    p->tile_rows = static_cast<uint32_t>(cfg->row_tile_rows); p->tile_count = static_cast<uint32_t>(cfg->row_tile_count);
+    p->tile_index = static_cast<uint32_t>(cfg->row_tile_index);
+    p->npix = p->width * static_cast<uint32_t>(rtw_row_tile_local_rows(cfg->height, cfg->row_tile_rows, cfg->row_tile_count));
+  }
   p->s_begin = static_cast<uint32_t>(cfg->sample_begin); p->s_end = static_cast<uint32_t>(cfg->sample_end);
   const uint32_t S = p->s_end - p->s_begin;
   const unsigned long long n_groups = (p->npix + rtw::kGroupPixels - 1) / rtw::kGroupPixels;
@@ -483,6 +491,23 @@ int rtw_render_device(const rtw_scene* scene, const rtw_render_cfg* cfg, int64_t
   return 0;
 }
 
+int32_t rtw_row_tile_local_rows(int32_t height, int32_t tile_rows, int32_t count) {
+  if (height < 1 || tile_rows < 1 || count < 1) return 0;
+  const int32_t tiles = (height + tile_rows - 1) / tile_rows;
+  return (tiles + count - 1) / count * tile_rows;
+}
+
+int rtw_untile_accum(const int64_t* gathered, int64_t* accum_fx, int32_t width, int32_t height, int32_t tile_rows, int32_t count,
+                     int32_t device, void* cuda_stream) {
+  if (!gathered || !accum_fx || width < 1 || height < 1 || tile_rows < 1 || count < 1) return fail("rtw_untile_accum: invalid argument");
+  RTW_CUDA(cudaSetDevice(device));
+  cudaError_t e = rtw::launch_untile(reinterpret_cast<const long long*>(gathered), reinterpret_cast<long long*>(accum_fx), static_cast<uint32_t>(width),
+                                     static_cast<uint32_t>(height), static_cast<uint32_t>(tile_rows), static_cast<uint32_t>(count),
+                                     static_cast<uint32_t>(rtw_row_tile_local_rows(height, tile_rows, count)), static_cast<cudaStream_t>(cuda_stream));
+  if (e != cudaSuccess) return fail_cuda("launch k_untile", e);
+  return 0;
+}
+
 int rtw_accum_to_float(const int64_t* accum_fx, float* accum_rgba, int64_t npixels, int32_t device, void* cuda_stream) {
   if (!accum_fx || !accum_rgba || npixels <= 0) return fail("rtw_accum_to_float: invalid argument");
   RTW_CUDA(cudaSetDevice(device));
@@ -518,6 +543,7 @@ void rtw_release_cached_buffers(void) {
 int rtw_render(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, float* accum_rgba, rtw_stats* stats) {
   if (!desc || !cfg || !accum_rgba) return fail("rtw_render: null argument");
   if (cfg->width < 2 || cfg->height < 2) return fail("render: width and height must be >= 2 (pixel mapping divides by W-1, H-1)");
+  if (cfg->row_tile_count > 1) return fail("rtw_render: the row-tile split goes through rtw_render_device or rtw_render_multi_gpu");
   const double t_start = now_ms();
   std::lock_guard<std::mutex> lock(g_cache_mutex);  // also serialises host-buffer renders per process (not re-entrant per device)
   if (cfg->device < 0 || cfg->device >= 64) return fail("rtw_render: device ordinal out of range");

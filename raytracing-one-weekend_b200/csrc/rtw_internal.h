@@ -33,6 +33,9 @@ struct RenderParams {
   uint64_t seed;
   uint32_t n_leaf_refs;
   SmemLayout so;
+  // row-tile split: this launch renders tiles tile_index, tile_index + tile_count, ... of tile_rows rows; npix counts the pixels of
+  // the packed local buffer (accum); Philox and the camera are keyed on the GLOBAL pixel.  tile_count <= 1: whole image.
+  uint32_t tile_rows, tile_count, tile_index;
 };
 
 struct PrimaryParams {
@@ -49,6 +52,8 @@ cudaError_t launch_render(const RenderParams& p, int mode, int rays_per_lane, bo
 cudaError_t launch_primary_f32(const PrimaryParams& p, int mode, cudaStream_t stream);
 cudaError_t launch_primary_f64(const rtw_primitive* prims, int nprims, const rtw_camera& cam, uint32_t width, uint32_t height, double time,
                                int32_t* prim_id, double* t, double* normal, uint8_t* front, cudaStream_t stream);
+cudaError_t launch_untile(const long long* gathered, long long* full, uint32_t width, uint32_t height, uint32_t tile_rows, uint32_t count,
+                          uint32_t local_rows, cudaStream_t stream);
 cudaError_t launch_accum_to_float(const long long* fx, float* out, long long npix, cudaStream_t stream);
 cudaError_t launch_finalize_rgb8(const float* acc, uint8_t* rgb, long long npix, int spp, cudaStream_t stream);
 cudaError_t launch_debug_scatter(long long n, const int* kind, const float* fuzz, const float* ior, const float* dir_in, const float* normal,

@@ -292,6 +292,26 @@ __device__ __forceinline__ void trace_bvh(const DevScene& sc, F3 o, F3 d, float 
 // ---------------------------------------------------------------------------------------------------------
 // The render kernel
 // ---------------------------------------------------------------------------------------------------------
+// Row-tile split: pixel lp of the packed local buffer -> global image row i, column j and global pixel index (false: outside the image)
+__device__ __forceinline__ bool local_to_global(const RenderParams& p, uint32_t lp, uint32_t& gp, uint32_t& i, uint32_t& j) {
+  if (lp >= p.npix) return false;
+  i = lp / p.width; j = lp - i * p.width;
+  if (p.tile_count > 1u) {
+    const uint32_t t = i / p.tile_rows, w = i - t * p.tile_rows;
+    i = (t * p.tile_count + p.tile_index) * p.tile_rows + w;
+    if (i >= p.height) return false;
+  }
+  gp = i * p.width + j;
+  return true;
+}
+// ... and back: where global pixel gp lives in the packed local accumulation buffer
+__device__ __forceinline__ uint32_t accum_index(const RenderParams& p, uint32_t gp) {
+  if (p.tile_count <= 1u) return gp;
+  const uint32_t i = gp / p.width, j = gp - i * p.width;
+  const uint32_t t = i / p.tile_rows, w = i - t * p.tile_rows;
+  return ((t / p.tile_count) * p.tile_rows + w) * p.width + j;
+}
+
 __device__ __forceinline__ void accum_add(unsigned long long* accum, uint32_t pix, float r, float g, float b) {
   // NaN / negative / absurd contributions are dropped (the reference would print garbage for them)
   const float lim = 1.0e9f;
@@ -356,12 +376,12 @@ __global__ void __launch_bounds__(kRenderThreads, (R >= 4 ? 2 : (R == 2 ? 3 : 4)
         const uint32_t rank = __popc(need & lt);
         if (!alive[r] && rank < avail) {
           const uint32_t within = pool_next + rank;
-          const uint32_t px = grp * kGroupPixels + (within & (kGroupPixels - 1u));
+          const uint32_t lp = grp * kGroupPixels + (within & (kGroupPixels - 1u));
           const uint32_t sm = s0 + within / kGroupPixels;
-          if (px < p.npix) {
+          uint32_t px, i, j;
+          if (local_to_global(p, lp, px, i, j)) {
             // primary ray: render.cpp:158-160 with the pixel mapping of SURVEY Q12
             const uint4 x0 = philox4x32_10(make_uint4(px, sm, 0u, 0u), key);
-            const uint32_t i = px / p.width, j = px - i * p.width;
             const float u = (static_cast<float>(j) + u01(x0.x)) * p.inv_wm1;
             const float v = (static_cast<float>(p.height - 1u - i) + u01(x0.y)) * p.inv_hm1;
             const float2 dk = sample_disk(u01(x0.z), u01(x0.w));
@@ -403,7 +423,7 @@ __global__ void __launch_bounds__(kRenderThreads, (R >= 4 ? 2 : (R == 2 ? 3 : 4)
       const F3 o = mk<float>(ray.ox[r], ray.oy[r], ray.oz[r]), d = mk<float>(ray.dx[r], ray.dy[r], ray.dz[r]);
       if (best_i[r] == kMiss) {
         const F3 c = sky_color(d);
-        accum_add(p.accum, pix[r], tr[r] * c.x, tg[r] * c.y, tb[r] * c.z);
+        accum_add(p.accum, accum_index(p, pix[r]), tr[r] * c.x, tg[r] * c.y, tb[r] * c.z);
         alive[r] = false;
       } else if (depth[r] >= p.max_depth) {
         alive[r] = false;  // hit at depth 0 of the recursion: black
@@ -426,7 +446,7 @@ __global__ void __launch_bounds__(kRenderThreads, (R >= 4 ? 2 : (R == 2 ? 3 : 4)
       }
       if (!alive[r]) {
         ++n_paths;
-        atomicAdd(p.accum + 4ull * pix[r] + 3, 1ull);
+        atomicAdd(p.accum + 4ull * accum_index(p, pix[r]) + 3, 1ull);
       }
     }
   }
@@ -559,7 +579,7 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
         bool ended = false;
         if (best_i == kMiss) {
           const F3 c = sky_color(d);
-          accum_add(p.accum, pix, tr * c.x, tg * c.y, tbl * c.z);
+          accum_add(p.accum, accum_index(p, pix), tr * c.x, tg * c.y, tbl * c.z);
           ended = true;
         } else if (depth >= p.max_depth) {
           ended = true;
@@ -582,7 +602,7 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
         }
         if (ended) {
           ++n_paths;
-          atomicAdd(p.accum + 4ull * pix + 3, 1ull);
+          atomicAdd(p.accum + 4ull * accum_index(p, pix) + 3, 1ull);
           state = DEAD;
         }
       }
@@ -607,11 +627,11 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
         const uint32_t rank = __popc(need & lt);
         if (state == DEAD && rank < avail) {
           const uint32_t within = pool_next + rank;
-          const uint32_t px = grp * kGroupPixels + (within & (kGroupPixels - 1u));
+          const uint32_t lp = grp * kGroupPixels + (within & (kGroupPixels - 1u));
           const uint32_t sm = s0 + within / kGroupPixels;
-          if (px < p.npix) {
+          uint32_t px, i, j;
+          if (local_to_global(p, lp, px, i, j)) {
             const uint4 x0 = philox4x32_10(make_uint4(px, sm, 0u, 0u), key);
-            const uint32_t i = px / p.width, j = px - i * p.width;
             const float u = (static_cast<float>(j) + u01(x0.x)) * p.inv_wm1;
             const float v = (static_cast<float>(p.height - 1u - i) + u01(x0.y)) * p.inv_hm1;
             const float2 dk = sample_disk(u01(x0.z), u01(x0.w));
@@ -896,14 +916,14 @@ __global__ void __launch_bounds__(NW * 32, 1) k_render_wf(const __grid_constant_
         const float4 c = recT[r2];
         const int code = __float_as_int(c.w);
         if (code != kFresh) {
-          const uint32_t px = recI[r2].x;
+          const uint32_t ax = accum_index(p, recI[r2].x);
           if (code == kMiss) {
             const float4 b = recD[r2];
             const F3 s = sky_color(mk<float>(b.x, b.y, b.z));
-            accum_add(p.accum, px, c.x * s.x, c.y * s.y, c.z * s.z);
+            accum_add(p.accum, ax, c.x * s.x, c.y * s.y, c.z * s.z);
           }
           ++n_paths;
-          atomicAdd(p.accum + 4ull * px + 3, 1ull);
+          atomicAdd(p.accum + 4ull * ax + 3, 1ull);
         }
       }
       bool got = false, retry = false;
@@ -927,11 +947,11 @@ __global__ void __launch_bounds__(NW * 32, 1) k_render_wf(const __grid_constant_
         const uint32_t rank = __popc(need & lt);
         if (act && !got && rank < avail) {
           const uint32_t within = pool_next + rank;
-          const uint32_t px = grp * kGroupPixels + (within & (kGroupPixels - 1u));
+          const uint32_t lp = grp * kGroupPixels + (within & (kGroupPixels - 1u));
           const uint32_t sm = s0 + within / kGroupPixels;
-          if (px < p.npix) {
+          uint32_t px, i, j;
+          if (local_to_global(p, lp, px, i, j)) {
             const uint4 x0 = philox4x32_10(make_uint4(px, sm, 0u, 0u), key);
-            const uint32_t i = px / p.width, j = px - i * p.width;
             const float u = (static_cast<float>(j) + u01(x0.x)) * p.inv_wm1;
             const float v = (static_cast<float>(p.height - 1u - i) + u01(x0.y)) * p.inv_hm1;
             const float2 dk = sample_disk(u01(x0.z), u01(x0.w));
@@ -1134,6 +1154,16 @@ __global__ void __launch_bounds__(256) k_primary_f64(const rtw_primitive* __rest
 // ---------------------------------------------------------------------------------------------------------
 // Finalize (render.cpp:11-20, 176-186)
 // ---------------------------------------------------------------------------------------------------------
+// Row-tile split, after the gather: [count][local_rows][width] packed pixels -> [height][width]
+__global__ void k_untile(const longlong4* __restrict__ gathered, longlong4* __restrict__ full, uint32_t width, uint32_t height, uint32_t tile_rows,
+                         uint32_t count, uint32_t local_rows) {
+  const uint32_t gp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gp >= width * height) return;
+  const uint32_t i = gp / width, j = gp - i * width;
+  const uint32_t t = i / tile_rows, w = i - t * tile_rows;
+  const uint32_t owner = t % count, lrow = (t / count) * tile_rows + w;
+  full[gp] = gathered[(static_cast<size_t>(owner) * local_rows + lrow) * width + j];
+}
 __global__ void k_accum_to_float(const long long* __restrict__ fx, float4* __restrict__ out, long long npix) {
   const long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (k >= npix) return;
@@ -1314,6 +1344,13 @@ cudaError_t launch_primary_f64(const rtw_primitive* prims, int nprims, const rtw
   return cudaGetLastError();
 }
 
+cudaError_t launch_untile(const long long* gathered, long long* full, uint32_t width, uint32_t height, uint32_t tile_rows, uint32_t count,
+                          uint32_t local_rows, cudaStream_t stream) {
+  const uint32_t npix = width * height;
+  k_untile<<<(npix + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const longlong4*>(gathered), reinterpret_cast<longlong4*>(full), width, height,
+                                                   tile_rows, count, local_rows);
+  return cudaGetLastError();
+}
 cudaError_t launch_accum_to_float(const long long* fx, float* out, long long npix, cudaStream_t stream) {
   k_accum_to_float<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, stream>>>(fx, reinterpret_cast<float4*>(out), npix);
   return cudaGetLastError();

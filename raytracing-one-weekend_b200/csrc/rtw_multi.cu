@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cstdio>
 
 #include <cstring>
@@ -29,6 +30,8 @@ struct NcclApi {
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   int (*Reduce)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   std::string error;
   bool load() {
@@ -44,6 +47,8 @@ struct NcclApi {
     RTW_SYM(GroupStart, "ncclGroupStart");
     RTW_SYM(GroupEnd, "ncclGroupEnd");
     RTW_SYM(Reduce, "ncclReduce");
+    RTW_SYM(Send, "ncclSend");
+    RTW_SYM(Recv, "ncclRecv");
     RTW_SYM(GetErrorString, "ncclGetErrorString");
 #undef RTW_SYM
     return true;
@@ -64,11 +69,16 @@ extern "C" int rtw_render_multi_gpu(const rtw_scene_desc* desc, const rtw_render
   if (rtw_device_count(&ndev) != 0) return 2;
   if (ngpus > ndev) return rtw_set_error_("rtw_render_multi_gpu: more GPUs requested than present");
   const int S = cfg->sample_end - cfg->sample_begin;
-  if (S <= 0 || S % ngpus != 0) return rtw_set_error_("rtw_render_multi_gpu: samples must split evenly over the GPUs (reference analogue: render.cpp:174)");
+  const bool rows = (cfg->flags & RTW_FLAG_SPLIT_ROWS) != 0;
+  const int tile_rows = cfg->row_tile_rows > 0 ? cfg->row_tile_rows : 8;
+  if (S <= 0 || (!rows && S % ngpus != 0)) return rtw_set_error_("rtw_render_multi_gpu: samples must split evenly over the GPUs (reference analogue: render.cpp:174)");
   if (cfg->width < 2 || cfg->height < 2) return rtw_set_error_("render: width and height must be >= 2");
   if (!g_nccl.load()) return rtw_set_error_(g_nccl.error.c_str());
 
   const size_t npix = static_cast<size_t>(cfg->width) * static_cast<size_t>(cfg->height);
+  // row-tile split: every GPU fills a packed buffer of local_rows rows; device 0 additionally holds the gathered buffers
+  const size_t local_pix = rows ? static_cast<size_t>(rtw_row_tile_local_rows(cfg->height, tile_rows, ngpus)) * static_cast<size_t>(cfg->width) : npix;
+  long long* gathered = nullptr;
   std::vector<rtw_scene*> scenes(ngpus, nullptr);
   std::vector<long long*> fx(ngpus, nullptr);
   std::vector<cudaStream_t> streams(ngpus, nullptr);
@@ -104,12 +114,16 @@ extern "C" int rtw_render_multi_gpu(const rtw_scene_desc* desc, const rtw_render
     th.emplace_back([&, g]() {
       rtw_render_cfg c = *cfg;
       c.device = g;
-      c.sample_begin = cfg->sample_begin + g * (S / ngpus);
-      c.sample_end = c.sample_begin + S / ngpus;
+      if (rows) {
+        c.row_tile_rows = tile_rows; c.row_tile_count = ngpus; c.row_tile_index = g;
+      } else {
+        c.sample_begin = cfg->sample_begin + g * (S / ngpus);
+        c.sample_end = c.sample_begin + S / ngpus;
+      }
       rcs[g] = rtw_scene_upload(desc, g, &scenes[g]);
       if (rcs[g]) { errs[g] = rtw_last_error(); return; }
-      if (cudaStreamCreate(&streams[g]) != cudaSuccess || cudaMalloc(reinterpret_cast<void**>(&fx[g]), npix * 4 * sizeof(long long)) != cudaSuccess ||
-          cudaMemsetAsync(fx[g], 0, npix * 4 * sizeof(long long), streams[g]) != cudaSuccess) {
+      if (cudaStreamCreate(&streams[g]) != cudaSuccess || cudaMalloc(reinterpret_cast<void**>(&fx[g]), std::max(npix, local_pix) * 4 * sizeof(long long)) != cudaSuccess ||
+          cudaMemsetAsync(fx[g], 0, local_pix * 4 * sizeof(long long), streams[g]) != cudaSuccess) {
         rcs[g] = 2; errs[g] = "device allocation failed"; return;
       }
       rcs[g] = rtw_render_device(scenes[g], &c, reinterpret_cast<int64_t*>(fx[g]), streams[g], &sts[g]);
@@ -120,15 +134,35 @@ extern "C" int rtw_render_multi_gpu(const rtw_scene_desc* desc, const rtw_render
   for (int g = 0; g < ngpus; ++g)
     if (rcs[g]) { cleanup(); return rtw_set_error_(("GPU " + std::to_string(g) + ": " + errs[g]).c_str()); }
 
-  // the one collective of the path: sum of the accumulation buffers onto device 0 (in place on the root)
-  g_nccl.GroupStart();
-  for (int g = 0; g < ngpus; ++g) {
-    cudaSetDevice(g);
-    nrc = g_nccl.Reduce(fx[g], fx[g], npix * 4, kNcclInt64, kNcclSum, 0, comms[g], streams[g]);
-    if (nrc != 0) break;
+  if (!rows) {
+    // the one collective of the path: sum of the accumulation buffers onto device 0 (in place on the root)
+    g_nccl.GroupStart();
+    for (int g = 0; g < ngpus; ++g) {
+      cudaSetDevice(g);
+      nrc = g_nccl.Reduce(fx[g], fx[g], npix * 4, kNcclInt64, kNcclSum, 0, comms[g], streams[g]);
+      if (nrc != 0) break;
+    }
+    const int nrc2 = g_nccl.GroupEnd();
+    if (nrc != 0 || nrc2 != 0) { cleanup(); return rtw_set_error_((std::string("ncclReduce: ") + g_nccl.GetErrorString(nrc ? nrc : nrc2)).c_str()); }
+  } else {
+    // row-tile alternative: gather the packed buffers on device 0 (send/recv pairs in one group), then put the tiles in place
+    cudaSetDevice(0);
+    if (cudaMalloc(reinterpret_cast<void**>(&gathered), static_cast<size_t>(ngpus) * local_pix * 4 * sizeof(long long)) != cudaSuccess) {
+      cleanup(); return rtw_set_error_("cudaMalloc (gather buffer) failed");
+    }
+    g_nccl.GroupStart();
+    for (int g = 0; g < ngpus && nrc == 0; ++g) {
+      cudaSetDevice(g);
+      nrc = g_nccl.Send(fx[g], local_pix * 4, kNcclInt64, 0, comms[g], streams[g]);
+      if (nrc == 0) { cudaSetDevice(0); nrc = g_nccl.Recv(gathered + static_cast<size_t>(g) * local_pix * 4, local_pix * 4, kNcclInt64, g, comms[0], streams[0]); }
+    }
+    const int nrc2 = g_nccl.GroupEnd();
+    if (nrc != 0 || nrc2 != 0) { cudaSetDevice(0); cudaFree(gathered); cleanup(); return rtw_set_error_((std::string("ncclSend/Recv: ") + g_nccl.GetErrorString(nrc ? nrc : nrc2)).c_str()); }
+    cudaSetDevice(0);
+    if (rtw_untile_accum(reinterpret_cast<const int64_t*>(gathered), reinterpret_cast<int64_t*>(fx[0]), cfg->width, cfg->height, tile_rows, ngpus, 0, streams[0]) != 0) {
+      cudaFree(gathered); cleanup(); return 2;
+    }
   }
-  const int nrc2 = g_nccl.GroupEnd();
-  if (nrc != 0 || nrc2 != 0) { cleanup(); return rtw_set_error_((std::string("ncclReduce: ") + g_nccl.GetErrorString(nrc ? nrc : nrc2)).c_str()); }
   for (int g = 0; g < ngpus; ++g) { cudaSetDevice(g); cudaStreamSynchronize(streams[g]); }
 
   cudaSetDevice(0);
@@ -139,6 +173,7 @@ extern "C" int rtw_render_multi_gpu(const rtw_scene_desc* desc, const rtw_render
   if (!rc && cudaMemcpyAsync(accum_rgba, out, npix * 4 * sizeof(float), cudaMemcpyDeviceToHost, streams[0]) != cudaSuccess) rc = rtw_set_error_("D2H failed");
   if (!rc && cudaStreamSynchronize(streams[0]) != cudaSuccess) rc = rtw_set_error_("stream sync failed");
   if (out) cudaFree(out);
+  if (gathered) cudaFree(gathered);
   if (stats && !rc) {
     std::memset(stats, 0, sizeof *stats);
     for (int g = 0; g < ngpus; ++g) {
@@ -148,7 +183,7 @@ extern "C" int rtw_render_multi_gpu(const rtw_scene_desc* desc, const rtw_render
       if (sts[g].kernel_ms > stats->kernel_ms) stats->kernel_ms = sts[g].kernel_ms;  // max over GPUs
     }
     stats->kernel_used = sts[0].kernel_used;
-    stats->launches = ngpus + 1;
+    stats->launches = ngpus + 1 + (rows ? 1 : 0);
   }
   cleanup();
   return rc;

@@ -1,7 +1,8 @@
 // main.cpp -- command line of the B200 renderer.  Same options as the reference executable (main.cpp:147-159):
 //   -t,--threads  -w,--image-width  -s,--samples-per-pixel  -c,--max-child-rays  -a,--aspect-ratio  -n,--balls_sqrt
 //   -m,--moving-spheres  -q,--quick  --dry-run  -l,--load
-// plus device options: --gpus N, --seed S, --kernel auto|spheres|bvh, --stats, --scene cover|model|mesh-on-ground,
+// plus device options: --gpus N, --split spp|rows, --tile-rows R, --seed S, --kernel auto|spheres|bvh, --stats,
+// --scene cover|model|mesh-on-ground,
 // and a mesh utility: --make-mesh OUT.obj --rounds K (high-poly stand-in generated from the -l model).
 #include <cstdlib>
 #include <cstring>
@@ -72,6 +73,12 @@ int main(int argc, char* argv[]) {
   number({"--device"}, dev.device);
   flag({"--stats"}, dev.stats);
   number({"--rounds"}, rounds);
+  number({"--tile-rows"}, dev.tile_rows);
+  table["--split"] = {true, [&dev](const std::string& v) {
+    if (v == "spp") dev.split_rows = false;
+    else if (v == "rows") dev.split_rows = true;
+    else throw std::invalid_argument("--split must be spp or rows");
+  }};
   table["--static-spheres"] = {false, [&cfg](const std::string&) { cfg.moving_spheres = false; }};
   table["--scene"] = {true, [&scene_name](const std::string& v) { scene_name = v; }};
   table["--make-mesh"] = {true, [&make_mesh](const std::string& v) { make_mesh = v; }};

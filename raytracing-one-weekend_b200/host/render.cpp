@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <iostream>
 #include <stdexcept>
+#include <string>
 #include <unordered_map>
 
 namespace rtweekend::detail {
@@ -21,6 +22,8 @@ DeviceOptions& device_options() {
     if (const char* e = std::getenv("RTW_KERNEL")) o.kernel = std::atoi(e);
     if (const char* e = std::getenv("RTW_DEVICE")) o.device = std::atoi(e);
     if (const char* e = std::getenv("RTW_STATS")) o.stats = std::atoi(e) != 0;
+    if (const char* e = std::getenv("RTW_SPLIT")) o.split_rows = std::string(e) == "rows";
+    if (const char* e = std::getenv("RTW_TILE_ROWS")) o.tile_rows = std::max(1, std::atoi(e));
     return o;
   }();
   return opts;
@@ -80,7 +83,8 @@ Accum render_accum(const Scene& world, const Config& cfg) {
   rc.kernel = opt.kernel;
   rc.seed = opt.seed;
   rc.device = opt.device;
-  rc.flags = opt.stats ? RTW_FLAG_STATS : 0;
+  rc.flags = (opt.stats ? RTW_FLAG_STATS : 0) | (opt.split_rows && opt.ngpus > 1 ? RTW_FLAG_SPLIT_ROWS : 0);
+  rc.row_tile_rows = opt.tile_rows;
   img.rgba.assign(static_cast<std::size_t>(img.width) * static_cast<std::size_t>(img.height) * 4, 0.0f);
   const int status = opt.ngpus > 1 ? rtw_render_multi_gpu(&flat.desc, &rc, opt.ngpus, img.rgba.data(), &img.stats)
                                    : rtw_render(&flat.desc, &rc, img.rgba.data(), &img.stats);

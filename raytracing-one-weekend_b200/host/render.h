@@ -32,6 +32,8 @@ struct DeviceOptions {
   int kernel = RTW_KERNEL_AUTO;
   int device = 0;           // first device (single-GPU renders)
   bool stats = false;       // count rays / tests (slower)
+  bool split_rows = false;  // multi-GPU: interleaved row tiles + one gather instead of the sample split + one reduce
+  int tile_rows = 8;        // rows per tile of the row split
 };
 DeviceOptions& device_options();  // process-wide knobs, also settable through RTW_GPUS / RTW_SEED / RTW_KERNEL
 

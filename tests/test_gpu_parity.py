@@ -407,6 +407,38 @@ def test_multi_gpu_in_process(gpu):
     one, _ = gpu.render(scene, 200, 133, 32, 20, seed=8)
     two, st = gpu.render_multi_gpu(scene, 200, 133, 32, 2, 20, seed=8)
     assert np.array_equal(one, two) and st["paths"] == 200 * 133 * 32
+    rows, st = gpu.render_multi_gpu(scene, 200, 133, 32, 2, 20, seed=8, flags=gpu.FLAG_SPLIT_ROWS, row_tiles=(8, 0, 0))
+    assert np.array_equal(one, rows) and st["paths"] == 200 * 133 * 32
+
+
+@pytest.mark.parametrize("kernel_name", ["spheres", "bvh"])
+@pytest.mark.parametrize("tile_rows,count", [(8, 2), (5, 3), (16, 8), (1, 4)])
+def test_row_tile_split_is_bit_identical(gpu, kernel_name, tile_rows, count):
+    """SURVEY 8(e) alternative: each participant renders ALL samples of its interleaved row tiles into a packed buffer; the
+    gathered buffers, put back in place, are the unsplit image bit for bit (Philox is keyed on the global pixel).  133 rows
+    are no multiple of any tile size here, so the last tiles are ragged or missing."""
+    import torch
+    scene = gpu.cover_scene()
+    W, H, S = 200, 133, 8
+    k = {"spheres": gpu.KERNEL_SPHERES_SMEM, "bvh": gpu.KERNEL_BVH}[kernel_name]
+    ds = gpu.DeviceScene(scene, 0)
+    stream = torch.cuda.current_stream().cuda_stream
+    full = torch.zeros((H, W, 4), dtype=torch.int64, device="cuda:0")
+    ds.render_into(full, W, H, S, 20, stream_ptr=stream, seed=5, kernel=k)
+    lr = gpu.row_tile_local_rows(H, tile_rows, count)
+    assert lr == gpu.lib().rtw_row_tile_local_rows(H, tile_rows, count)
+    gathered = torch.zeros((count, lr, W, 4), dtype=torch.int64, device="cuda:0")
+    paths = 0
+    for g in range(count):
+        st = ds.render_into(gathered[g], W, H, S, 20, stream_ptr=stream, seed=5, kernel=k, row_tiles=(tile_rows, count, g), want_stats=True)
+        paths += st["paths"]
+    back = torch.zeros_like(full)
+    ds.untile(gathered, back, W, H, tile_rows, count, stream_ptr=stream)
+    torch.cuda.synchronize()
+    assert paths == W * H * S
+    assert torch.equal(back, full)
+    assert torch.equal(gpu.untile_rows(gathered, H, tile_rows, count), full)   # the torch restatement used on CPU agrees
+    ds.close()
 
 
 def test_high_poly_stand_in_mesh(gpu, port, oracle_mod, tmp_path):

@@ -55,3 +55,44 @@ def test_spp_shards_reduce_to_the_unsharded_image(rtw, port, tmp_path):
     import torch
     x = torch.ones(4, dtype=torch.int64)
     assert rtw.reduce_accum(x) is x
+
+
+def _rows_worker(rank, world, port_no, full_path, out_path, tile_rows):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    import torch
+    import torch.distributed as dist
+    rtw = importlib.import_module("raytracing-one-weekend_b200")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.from_numpy(np.load(full_path))
+    h = full.shape[0]
+    lr = rtw.row_tile_local_rows(h, tile_rows, world)
+    local = torch.zeros((lr, *full.shape[1:]), dtype=full.dtype)
+    # what the kernel does for this rank: global row r lives in tile r // tile_rows; tiles rank, rank + world, ... are ours
+    for r in range(h):
+        t, w = divmod(r, tile_rows)
+        if t % world == rank:
+            local[(t // world) * tile_rows + w] = full[r]
+    g = rtw.gather_row_tiles(local, dst=0)
+    if rank == 0:
+        np.save(out_path, rtw.untile_rows(g, h, tile_rows, world).numpy())
+    else:
+        assert g is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("tile_rows", [1, 5, 8])
+def test_row_tiles_gather_to_the_unsplit_image(rtw, tmp_path, tile_rows):
+    """The row-tile alternative of SURVEY 8(e) on CPU (gloo, world 2): packed per-rank buffers, one gather, tiles put back."""
+    import torch.multiprocessing as mp
+    rng = np.random.default_rng(tile_rows)
+    full = rng.integers(0, 1 << 40, size=(H + 1, W, 4), dtype=np.int64)   # 33 rows: ragged against every tile size
+    fp, out = str(tmp_path / "full.npy"), str(tmp_path / "rows.npy")
+    np.save(fp, full)
+    mp.spawn(_rows_worker, args=(2, _free_port(), fp, out, tile_rows), nprocs=2, join=True)
+    assert np.array_equal(np.load(out), full)
+    assert rtw.row_tile_local_rows(33, tile_rows, 2) == rtw.lib().rtw_row_tile_local_rows(33, tile_rows, 2)
+    import torch
+    x = torch.arange(24, dtype=torch.int64).reshape(6, 2, 2)
+    assert torch.equal(rtw.untile_rows(rtw.gather_row_tiles(x), 6, 2, 1), x)   # world 1: identity
