@@ -37,6 +37,7 @@ Handle* guarded(F&& f) {
 RTWH_API const char* rtwh_last_error() { return g_err.c_str(); }
 RTWH_API void rtwh_seed(unsigned seed) { rt::seed_host_rng(seed); }
 RTWH_API double rtwh_random_double() { return rt::random_double(); }
+RTWH_API void rtwh_set_obj_all_shapes(int on) { rt::device_options().obj_all_shapes = on != 0; }
 
 RTWH_API void* rtwh_scene_cover(int nsqrt, double aspect, int moving) {
   rt::Config cfg{};

@@ -2,7 +2,7 @@
 //   -t,--threads  -w,--image-width  -s,--samples-per-pixel  -c,--max-child-rays  -a,--aspect-ratio  -n,--balls_sqrt
 //   -m,--moving-spheres  -q,--quick  --dry-run  -l,--load
 // plus device options: --gpus N, --split spp|rows, --tile-rows R, --seed S, --kernel auto|spheres|bvh, --stats,
-// --scene cover|model|mesh-on-ground,
+// --format p3|p6, --checkpoint FILE [--checkpoint-every N] (progressive / resumable), --scene cover|model|mesh-on-ground,
 // and a mesh utility: --make-mesh OUT.obj --rounds K (high-poly stand-in generated from the -l model).
 #include <cstdlib>
 #include <cstring>
@@ -72,8 +72,16 @@ int main(int argc, char* argv[]) {
   number({"--seed"}, dev.seed);
   number({"--device"}, dev.device);
   flag({"--stats"}, dev.stats);
+  flag({"--all-shapes"}, dev.obj_all_shapes);
   number({"--rounds"}, rounds);
   number({"--tile-rows"}, dev.tile_rows);
+  number({"--checkpoint-every"}, dev.checkpoint_every);
+  table["--checkpoint"] = {true, [&dev](const std::string& v) { dev.checkpoint = v; }};
+  table["--format"] = {true, [&dev](const std::string& v) {
+    if (v == "p3") dev.binary_ppm = false;
+    else if (v == "p6") dev.binary_ppm = true;
+    else throw std::invalid_argument("--format must be p3 or p6");
+  }};
   table["--split"] = {true, [&dev](const std::string& v) {
     if (v == "spp") dev.split_rows = false;
     else if (v == "rows") dev.split_rows = true;

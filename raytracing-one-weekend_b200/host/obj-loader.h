@@ -15,7 +15,8 @@ struct ObjMesh {
   std::vector<point> vertices;
   std::vector<std::array<int, 3>> faces;  // zero-based vertex indices, first shape only
 };
-ObjMesh load_obj(const std::string& path);  // throws std::runtime_error("Can't load because ...")
+// all_shapes = false: the reference's behaviour (faces of shapes[0] only, main.cpp:117); true: every `f` of the file
+ObjMesh load_obj(const std::string& path, bool all_shapes = false);  // throws std::runtime_error("Can't load because ...")
 void save_obj(const std::string& path, const ObjMesh& mesh);
 // deterministic high-poly stand-in for the missing dragon.obj: `rounds` 1->4 midpoint subdivisions with a
 // fixed-seed radial displacement

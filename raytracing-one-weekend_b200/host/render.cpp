@@ -6,6 +6,9 @@
 #include "render.h"
 
 #include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
 #include <cstdlib>
 #include <iostream>
 #include <stdexcept>
@@ -113,13 +116,96 @@ void write_ppm(std::ostream& out, const Accum& img) {
   out.write(text.data(), static_cast<std::streamsize>(text.size()));
 }
 
+void write_ppm_binary(std::ostream& out, const Accum& img, int device) {
+  const std::size_t npix = static_cast<std::size_t>(img.width) * static_cast<std::size_t>(img.height);
+  std::vector<std::uint8_t> rgb(npix * 3);
+  if (rtw_finalize_rgb8(img.rgba.data(), static_cast<int64_t>(npix), img.spp, device, rgb.data()) != 0)
+    throw std::runtime_error(std::string("rtw_b200: ") + rtw_last_error());
+  out << "P6\n" << img.width << ' ' << img.height << "\n255\n";
+  out.write(reinterpret_cast<const char*>(rgb.data()), static_cast<std::streamsize>(rgb.size()));
+}
+
+namespace {
+// checkpoint file: header (magic, width, height, spp target, cursor, max_child_rays, seed) + width*height*4 floats (sums + sample counts)
+struct CheckpointHeader {
+  char magic[8];
+  std::int32_t width, height, spp, cursor, max_child_rays, reserved;
+  std::uint64_t seed;
+};
+constexpr char kCheckpointMagic[8] = {'R', 'T', 'W', 'C', 'K', 'P', 'T', '1'};
+
+bool read_checkpoint(const std::string& path, CheckpointHeader& h, std::vector<float>& rgba) {
+  std::ifstream in(path, std::ios::binary);
+  if (!in) return false;
+  in.read(reinterpret_cast<char*>(&h), sizeof h);
+  if (!in || std::memcmp(h.magic, kCheckpointMagic, 8) != 0 || h.width < 2 || h.height < 2) throw std::runtime_error("checkpoint " + path + ": not a checkpoint file");
+  rgba.resize(static_cast<std::size_t>(h.width) * static_cast<std::size_t>(h.height) * 4);
+  in.read(reinterpret_cast<char*>(rgba.data()), static_cast<std::streamsize>(rgba.size() * sizeof(float)));
+  if (!in) throw std::runtime_error("checkpoint " + path + ": truncated");
+  return true;
+}
+void write_checkpoint(const std::string& path, const CheckpointHeader& h, const std::vector<float>& rgba) {
+  const std::string tmp = path + ".tmp";
+  {
+    std::ofstream out(tmp, std::ios::binary | std::ios::trunc);
+    out.write(reinterpret_cast<const char*>(&h), sizeof h);
+    out.write(reinterpret_cast<const char*>(rgba.data()), static_cast<std::streamsize>(rgba.size() * sizeof(float)));
+    if (!out) throw std::runtime_error("checkpoint " + tmp + ": write failed");
+  }
+  if (std::rename(tmp.c_str(), path.c_str()) != 0) throw std::runtime_error("checkpoint " + path + ": rename failed");
+}
+}  // namespace
+
+Accum render_progressive(const Scene& world, const Config& cfg, const std::string& path, int every) {
+  const DeviceOptions& opt = device_options();
+  Accum img;
+  img.width = cfg.image_width;
+  img.height = image_height(cfg);
+  img.spp = effective_spp(cfg);
+  if (img.spp <= 0) throw std::invalid_argument("samples_per_pixel / nthreads * nthreads is 0: nothing to render");
+  if (img.width < 2 || img.height < 2) throw std::invalid_argument("image must be at least 2x2");
+  CheckpointHeader h{};
+  std::memcpy(h.magic, kCheckpointMagic, 8);
+  h.width = img.width; h.height = img.height; h.spp = img.spp; h.cursor = 0; h.max_child_rays = cfg.max_child_rays; h.seed = opt.seed;
+  CheckpointHeader old{};
+  if (read_checkpoint(path, old, img.rgba)) {
+    if (old.width != h.width || old.height != h.height || old.max_child_rays != h.max_child_rays || old.seed != h.seed)
+      throw std::invalid_argument("checkpoint " + path + " belongs to a different render (size, depth or seed differ)");
+    h.cursor = std::min(old.cursor, img.spp);
+    std::cerr << "resuming at sample " << h.cursor << " of " << img.spp << "\n";
+  } else {
+    img.rgba.assign(static_cast<std::size_t>(img.width) * static_cast<std::size_t>(img.height) * 4, 0.0f);
+  }
+  const Scene::Flat flat = world.flatten();
+  std::vector<float> slice(img.rgba.size());
+  const int step = every > 0 ? every : img.spp;
+  while (h.cursor < img.spp) {
+    rtw_render_cfg rc{};
+    rc.width = img.width; rc.height = img.height;
+    rc.sample_begin = h.cursor; rc.sample_end = std::min(img.spp, h.cursor + step);
+    rc.max_child_rays = cfg.max_child_rays; rc.kernel = opt.kernel; rc.seed = opt.seed; rc.device = opt.device;
+    rtw_stats st{};
+    if (rtw_render(&flat.desc, &rc, slice.data(), &st) != 0) throw std::runtime_error(std::string("rtw_b200: ") + rtw_last_error());
+    // every slice is an exact 2^-32 fixed-point sum converted to float; slices add in double so that the running total does not
+    // depend on where the render was interrupted beyond one float rounding per slice
+    for (std::size_t k = 0; k < img.rgba.size(); ++k) img.rgba[k] = static_cast<float>(static_cast<double>(img.rgba[k]) + static_cast<double>(slice[k]));
+    img.stats.paths += st.paths; img.stats.rays += st.rays; img.stats.kernel_ms += st.kernel_ms;
+    h.cursor = rc.sample_end;
+    write_checkpoint(path, h, img.rgba);
+    std::cerr << "\rsamples " << h.cursor << "/" << img.spp << std::flush;
+  }
+  std::cerr << "\n";
+  return img;
+}
+
 void render(const Scene& world, const Config& cfg) {
   namespace khr = std::chrono;
   const DeviceOptions& opt = device_options();
   std::cerr << "Started rendering on " << opt.ngpus << " GPU(s)\n";
   const auto start = khr::steady_clock::now();
-  const Accum img = render_accum(world, cfg);
-  write_ppm(std::cout, img);
+  const Accum img = opt.checkpoint.empty() ? render_accum(world, cfg) : render_progressive(world, cfg, opt.checkpoint, opt.checkpoint_every);
+  if (opt.binary_ppm) write_ppm_binary(std::cout, img, opt.device);
+  else write_ppm(std::cout, img);
   std::cout.flush();
   const auto took = khr::duration_cast<khr::milliseconds>(khr::steady_clock::now() - start);
   const double paths = static_cast<double>(img.stats.paths), rays = static_cast<double>(img.stats.rays);

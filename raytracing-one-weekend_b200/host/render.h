@@ -34,6 +34,10 @@ struct DeviceOptions {
   bool stats = false;       // count rays / tests (slower)
   bool split_rows = false;  // multi-GPU: interleaved row tiles + one gather instead of the sample split + one reduce
   int tile_rows = 8;        // rows per tile of the row split
+  bool obj_all_shapes = false;  // -l: take the faces of every shape of the OBJ file, not only shapes[0] as the reference does
+  bool binary_ppm = false;  // P6 (binary) instead of the reference's P3 text; quantised on the device (rtw_finalize_rgb8)
+  std::string checkpoint;   // progressive rendering: file holding the accumulation buffer + sample cursor (see render_progressive)
+  int checkpoint_every = 0; // samples per slice between checkpoint writes (0: one slice)
 };
 DeviceOptions& device_options();  // process-wide knobs, also settable through RTW_GPUS / RTW_SEED / RTW_KERNEL
 
@@ -70,6 +74,11 @@ int image_height(const Config& cfg);      // int(width / aspect), render.cpp:137
 int effective_spp(const Config& cfg);     // spp / nthreads * nthreads, render.cpp:174,185
 Accum render_accum(const Scene& world, const Config& cfg);
 void write_ppm(std::ostream& out, const Accum& img);  // render.cpp:11-20,182-186
+void write_ppm_binary(std::ostream& out, const Accum& img, int device = 0);  // same pixels as P6, write_color evaluated on the device
+// Progressive / resumable accumulation: renders the samples [cursor, spp) in slices of `every`, adding into the
+// buffer stored in `path` (created when absent) and rewriting it after every slice.  Samples are keyed by their global index, so
+// a render resumed from its checkpoint produces the same bytes as the uninterrupted progressive render with the same slice size.
+Accum render_progressive(const Scene& world, const Config& cfg, const std::string& path, int every);
 void render(const Scene& world, const Config& cfg);   // P3 text on stdout, progress on stderr
 
 std::ostream& operator<<(std::ostream& o, const Config& c);
@@ -84,4 +93,6 @@ using detail::render;
 using detail::render_accum;
 using detail::Scene;
 using detail::write_ppm;
+using detail::write_ppm_binary;
+using detail::render_progressive;
 }  // namespace rtweekend

@@ -62,7 +62,7 @@ Scene foo(const Config& cfg) {
   Scene world{Camera{point(1, 0, -1), point(0, 0, 0), vec3(0, 1, 0), 35.0, cfg.aspect_ratio, 0.01, std::nullopt, 0, 1}};
   const Material& grey = world.boutique().add<Lambertian>(color{0.5, 0.5, 0.5});
   if (!cfg.model) throw std::runtime_error("foo(): Config::model is not set");
-  const detail::ObjMesh mesh = detail::load_obj(*cfg.model);
+  const detail::ObjMesh mesh = detail::load_obj(*cfg.model, device_options().obj_all_shapes);
   for (const auto& f : mesh.faces)
     world.primitives().add<Triangle>(mesh.vertices[static_cast<std::size_t>(f[0])], mesh.vertices[static_cast<std::size_t>(f[1])],
                                      mesh.vertices[static_cast<std::size_t>(f[2])], grey);
@@ -73,7 +73,7 @@ Scene foo(const Config& cfg) {
 // Mesh standing on the r=1000 ground sphere of the cover scene, seen from a three-quarter view.
 Scene mesh_on_ground(const Config& cfg) {
   if (!cfg.model) throw std::runtime_error("mesh_on_ground(): Config::model is not set");
-  const detail::ObjMesh mesh = detail::load_obj(*cfg.model);
+  const detail::ObjMesh mesh = detail::load_obj(*cfg.model, device_options().obj_all_shapes);
   double ymin = 1e300, ymax = -1e300;
   for (const auto& v : mesh.vertices) { ymin = std::min(ymin, v.y); ymax = std::max(ymax, v.y); }
   const double lift = -ymin;

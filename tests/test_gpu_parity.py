@@ -400,6 +400,34 @@ def test_host_executable_end_to_end(gpu, golden):
     assert psnr8(gpu.read_ppm(r.stdout), d["rgb"]) > 22.0  # two independent 16-20 spp renders
 
 
+def test_host_executable_binary_output_and_resume(gpu, tmp_path):
+    """--format p6 carries the same pixels as the P3 text (write_color evaluated on the device), and a render
+    resumed from its checkpoint equals the uninterrupted progressive render with the same slice size."""
+    exe = str(gpu.EXE_PATH)
+    base = [exe, "-w", "96", "-t", "1", "--seed", "3"]
+    p3 = subprocess.run(base + ["-s", "8"], capture_output=True, timeout=300)
+    p6 = subprocess.run(base + ["-s", "8", "--format", "p6"], capture_output=True, timeout=300)
+    assert p3.returncode == 0 and p6.returncode == 0, p6.stderr
+    head = b"P6\n96 64\n255\n"
+    assert p6.stdout.startswith(head) and len(p6.stdout) == len(head) + 96 * 64 * 3
+    img6 = np.frombuffer(p6.stdout[len(head):], np.uint8).reshape(64, 96, 3)
+    assert np.array_equal(img6, gpu.read_ppm(p3.stdout.decode()))
+    whole, part = str(tmp_path / "whole.ckpt"), str(tmp_path / "part.ckpt")
+    a = subprocess.run(base + ["-s", "8", "--checkpoint", whole, "--checkpoint-every", "4"], capture_output=True, timeout=300)
+    b1 = subprocess.run(base + ["-s", "4", "--checkpoint", part, "--checkpoint-every", "4"], capture_output=True, timeout=300)
+    b2 = subprocess.run(base + ["-s", "8", "--checkpoint", part, "--checkpoint-every", "4"], capture_output=True, timeout=300)
+    assert a.returncode == 0 and b1.returncode == 0 and b2.returncode == 0, b2.stderr
+    assert b"resuming at sample 4 of 8" in b2.stderr
+    assert a.stdout == b2.stdout and a.stdout != b1.stdout
+    assert open(whole, "rb").read() == open(part, "rb").read()
+    # the slices sum to the one-shot render up to one float rounding per slice: the 8-bit images differ in at most a few pixels
+    d = np.abs(gpu.read_ppm(a.stdout.decode()).astype(int) - gpu.read_ppm(p3.stdout.decode()).astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3
+    # a checkpoint of another render is refused
+    bad = subprocess.run([exe, "-w", "100", "-t", "1", "-s", "8", "--checkpoint", part], capture_output=True, timeout=300)
+    assert bad.returncode != 0
+
+
 def test_multi_gpu_in_process(gpu):
     if gpu.device_count() < 2:
         pytest.skip("needs 2 GPUs")

@@ -110,6 +110,13 @@ def test_obj_loader(rtw, port, tmp_path):
     assert np.array_equal(q.prims["a"][2], [0.5, 0.5, 1.0]) and np.array_equal(q.prims["b"][2], [0, 0, 0])
     with pytest.raises(rtw.RtwError, match="Can't load because"):
         rtw.obj_scene(str(tmp_path / "missing.obj"))
+    # --all-shapes: every shape of the file, not only shapes[0]
+    rtw.host().rtwh_set_obj_all_shapes(1)
+    try:
+        q4 = rtw.obj_scene(str(obj))
+    finally:
+        rtw.host().rtwh_set_obj_all_shapes(0)
+    assert len(q4.prims) == 4 and np.array_equal(q4.prims["c"][3], [1, 1, 0])
 
 
 def test_high_poly_stand_in_generator(rtw, tmp_path):
