@@ -172,6 +172,23 @@ __device__ __forceinline__ void camera_ray(const Cam& cam, T s, T t, T diskx, T 
 // ---------------------------------------------------------------------------------------------------------
 // Intersection
 // ---------------------------------------------------------------------------------------------------------
+// One 64-byte BVH node.  From global memory: two 256-bit loads (LDG.E.256, sm_100) instead of four 128-bit ones -- the traversal of
+// a big mesh is bound by L1 wavefronts (one per distinct line per load instruction), and every lane reads a different node.
+__device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
+  asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+      : "l"(p));
+}
+template <bool SMEM>
+__device__ __forceinline__ void load_node(const float4* nodes, int node, float4& q0, float4& q1, float4& q2, float4& q3) {
+  if (SMEM) {
+    q0 = nodes[4 * node]; q1 = nodes[4 * node + 1]; q2 = nodes[4 * node + 2]; q3 = nodes[4 * node + 3];
+  } else {
+    ldg256(nodes + 4 * node, q0, q1);
+    ldg256(nodes + 4 * node + 2, q2, q3);
+  }
+}
+
 // Slab test of both children of a BVH node (Aabb::hit, common-model.h:71-84) against [kTMin, tmax].  With the box stored as
 // centre c and half-extent e >= 0 the entry/exit parameters along one axis are (c -+ e) * (1/d) - o/d = tc -+ e * |1/d|:
 // three FFMA per axis on the FMA pipe and no per-axis min/max on the ALU pipe, which is the busiest pipe of the traversal

@@ -267,8 +267,8 @@ __device__ __forceinline__ void trace_bvh(const DevScene& sc, F3 o, F3 d, float 
       continue;
     }
     if (STATS) ++n_nodes;
-    const float4 q0 = __ldg(&sc.nodes[4 * node]), q1 = __ldg(&sc.nodes[4 * node + 1]), q2 = __ldg(&sc.nodes[4 * node + 2]),
-                 q3 = __ldg(&sc.nodes[4 * node + 3]);
+    float4 q0, q1, q2, q3;
+    load_node<false>(sc.nodes, node, q0, q1, q2, q3);
     // slab test of both children against [tmin, best_t]
     float ln, lf, rn, rf;
     node_slabs(q0, q1, q2, idx, idy, idz, odx, ody, odz, best_t, ln, lf, rn, rf);
@@ -656,8 +656,8 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
     for (int step = 0; step < STEPS; ++step) {
       if (state == TRAV && node >= 0) {
         if (STATS) ++n_nodes;
-        const float4 q0 = ld4<SMEM>(tb.nodes, 4 * node), q1 = ld4<SMEM>(tb.nodes, 4 * node + 1), q2 = ld4<SMEM>(tb.nodes, 4 * node + 2),
-                     q3 = ld4<SMEM>(tb.nodes, 4 * node + 3);
+        float4 q0, q1, q2, q3;
+        load_node<SMEM>(tb.nodes, node, q0, q1, q2, q3);
         float ln, lf, rn, rf;
         node_slabs(q0, q1, q2, idx, idy, idz, odx, ody, odz, best_t, ln, lf, rn, rf);
         const bool hl = ln <= lf, hr = rn <= rf;
@@ -986,8 +986,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_render_wf(const __grid_constant_
     for (int step = 0; step < STEPS; ++step) {
       if (state == TRAV && node >= 0) {
         if (STATS) ++n_nodes;
-        const float4 q0 = ld4<SMEM>(tb.nodes, 4 * node), q1 = ld4<SMEM>(tb.nodes, 4 * node + 1), q2 = ld4<SMEM>(tb.nodes, 4 * node + 2),
-                     q3 = ld4<SMEM>(tb.nodes, 4 * node + 3);
+        float4 q0, q1, q2, q3;
+        load_node<SMEM>(tb.nodes, node, q0, q1, q2, q3);
         float ln, lf, rn, rf;
         node_slabs(q0, q1, q2, idx, idy, idz, odx, ody, odz, best_t, ln, lf, rn, rf);
         const bool hl = ln <= lf, hr = rn <= rf;
