@@ -200,7 +200,7 @@ def main() -> int:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cover_1080p_1024spp_depth50", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (a reduced-size run is NOT the headline)")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "spheres", "bvh"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "spheres", "bvh", "bvh-perlane"])
     ap.add_argument("--rays-per-lane", type=int, default=0)
     ap.add_argument("--split", default="spp", choices=["spp", "rows"], help="multi-GPU work split: samples + one reduce (default), or interleaved row tiles + one gather (SURVEY 8(e) alternative)")
     ap.add_argument("--tile-rows", type=int, default=8)
@@ -233,7 +233,7 @@ def main() -> int:
     if args.spp:
         spp = args.spp
     height = rtw.image_height(width, aspect)
-    kernel = {"auto": rtw.KERNEL_AUTO, "spheres": rtw.KERNEL_SPHERES_SMEM, "bvh": rtw.KERNEL_BVH}[args.kernel]
+    kernel = {"auto": rtw.KERNEL_AUTO, "spheres": rtw.KERNEL_SPHERES_SMEM, "bvh": rtw.KERNEL_BVH, "bvh-perlane": rtw.KERNEL_BVH_PERLANE}[args.kernel]
     scene = build_scene(rtw, args.workload, wl)
     scene_has_triangles = bool((scene.prims["kind"] == rtw.RTW_TRIANGLE).any())
     rows = args.split == "rows" and world > 1
@@ -279,6 +279,10 @@ def main() -> int:
     st = step(collect_stats=True)
     rays_local = st["rays"]
     kernel_used = st["kernel_used"]
+    wavefront = st.get("bvh_variant") == rtw.BVH_WAVEFRONT
+    kernel_label = ("k_render_sweep<2> (K1 shared-memory sphere sweep)" if kernel_used == rtw.KERNEL_SPHERES_SMEM else
+                    "k_render_wf (K2w: BVH traversal, wavefront per warp, tables + path records in shared memory)" if wavefront else
+                    "k_render_bvh (K2: BVH traversal, per-lane resumable state machine" + (", tables in shared memory)" if not scene_has_triangles and len(scene.prims) < 600 else ", tables in L1/L2)"))
     barrier()
 
     sampler = ClockSampler(local_rank)
@@ -401,7 +405,7 @@ def main() -> int:
         nodes_pr, tests_pr, tris_pr = sst["node_visits"] / sst["rays"], sst["sphere_tests"] / sst["rays"], sst["tri_tests"] / sst["rays"]
         flop = rays_gpu * (nodes_pr * 24.0 + tests_pr * test_flop + tris_pr * 36.0 + n_big * FLOP_STATIC_TEST + FLOP_SHADE) + (rays_gpu - paths_gpu) * FLOP_HIT
         ach = flop / (kernel_ms * 1e-3) / 1e12
-        roofline = {"bound": "fp32_fma", "kernel": "k_render_bvh (K2 resumable BVH traversal, tables in shared memory)", "achieved": ach,
+        roofline = {"bound": "fp32_fma", "kernel": kernel_label, "achieved": ach,
                     "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops, "traffic": traffic("bvh"), "peak_source": peak_note,
                     "algorithmic_flop_per_launch": flop, "kernel_ms": kernel_ms,
                     "per_ray": {"node_visits": nodes_pr, "sphere_tests": tests_pr, "triangle_tests": tris_pr},
@@ -439,7 +443,7 @@ def main() -> int:
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "width": width, "height": height, "spp": spp, "max_child_rays": depth, "primitives": int(len(scene.prims)),
                    "parallelism": (f"row tiles of {args.tile_rows} rows interleaved over {world} GPUs, one int64 NCCL gather" if rows
-                                   else f"spp-shard x{world}, one int64 NCCL reduce"), "kernel": "spheres_smem (K1)" if kernel_used == rtw.KERNEL_SPHERES_SMEM else "bvh (K2)",
+                                   else f"spp-shard x{world}, one int64 NCCL reduce"), "kernel": "spheres_smem (K1)" if kernel_used == rtw.KERNEL_SPHERES_SMEM else ("bvh wavefront (K2w)" if wavefront else "bvh per-lane (K2)"),
                    "l2": "256 MB buffer written between timed iterations (scene tables live in shared memory; accumulation buffer 66 MB)"},
         "mrays_per_s": rays_total / (ms_per_step * 1e-3) / 1e6, "rays_per_path": rays_total / paths_total,
         "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks, "roofline": roofline, "roofline_sphere_sweep": roofline_sweep,

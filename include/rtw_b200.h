@@ -36,7 +36,11 @@ extern "C" {
 
 enum rtw_prim_kind { RTW_SPHERE = 0, RTW_MOVING_SPHERE = 1, RTW_TRIANGLE = 2 };
 enum rtw_mat_kind { RTW_LAMBERTIAN = 0, RTW_METAL = 1, RTW_DIELECTRIC = 2 };
-enum rtw_kernel { RTW_KERNEL_AUTO = 0, RTW_KERNEL_SPHERES_SMEM = 1, RTW_KERNEL_BVH = 2 };
+/* AUTO: sphere sweep for tiny sphere scenes, else BVH.  BVH picks between its two kernels: the wavefront-per-warp kernel when the
+ * scene tables and the per-warp path records fit in shared memory (sphere scenes up to ~900 spheres), else the per-lane state
+ * machine (meshes, large scenes).  BVH_PERLANE forces the latter (A/B measurements). */
+enum rtw_kernel { RTW_KERNEL_AUTO = 0, RTW_KERNEL_SPHERES_SMEM = 1, RTW_KERNEL_BVH = 2, RTW_KERNEL_BVH_PERLANE = 3 };
+enum rtw_bvh_variant { RTW_BVH_NONE = 0, RTW_BVH_PERLANE = 1, RTW_BVH_WAVEFRONT = 2 };
 enum rtw_flags { RTW_FLAG_STATS = 1, RTW_FLAG_SPLIT_ROWS = 2 };
 
 /* One primitive, in scene insertion order (index in the array == primitive id used for parity).
@@ -94,8 +98,10 @@ typedef struct rtw_stats {
   uint64_t tri_tests, node_visits;            /* RTW_FLAG_STATS only */
   double kernel_ms;                           /* CUDA-event time of the render kernel(s) */
   double h2d_ms, d2h_ms, total_ms;            /* host-buffer entry points */
-  int32_t kernel_used;                        /* rtw_kernel actually launched */
+  int32_t kernel_used;                        /* rtw_kernel actually launched (SPHERES_SMEM or BVH) */
   int32_t launches;                           /* kernels of this library launched by the call */
+  int32_t bvh_variant;                        /* rtw_bvh_variant when kernel_used == RTW_KERNEL_BVH */
+  int32_t reserved;
 } rtw_stats;
 
 typedef struct rtw_scene rtw_scene; /* device-resident flattened scene (SoA tables, BVH, materials, camera) */

@@ -27,7 +27,8 @@ HEADER_PATH = REPO_ROOT / "include" / "rtw_b200.h"
 
 RTW_SPHERE, RTW_MOVING_SPHERE, RTW_TRIANGLE = 0, 1, 2
 RTW_LAMBERTIAN, RTW_METAL, RTW_DIELECTRIC = 0, 1, 2
-KERNEL_AUTO, KERNEL_SPHERES_SMEM, KERNEL_BVH = 0, 1, 2
+KERNEL_AUTO, KERNEL_SPHERES_SMEM, KERNEL_BVH, KERNEL_BVH_PERLANE = 0, 1, 2, 3
+BVH_NONE, BVH_PERLANE, BVH_WAVEFRONT = 0, 1, 2
 FLAG_STATS = 1
 FLAG_SPLIT_ROWS = 2
 
@@ -80,7 +81,7 @@ class Stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("sphere_tests", C.c_uint64),
                 ("sphere_candidates", C.c_uint64), ("tri_tests", C.c_uint64), ("node_visits", C.c_uint64),
                 ("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
-                ("kernel_used", C.c_int32), ("launches", C.c_int32)]
+                ("kernel_used", C.c_int32), ("launches", C.c_int32), ("bvh_variant", C.c_int32), ("reserved", C.c_int32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

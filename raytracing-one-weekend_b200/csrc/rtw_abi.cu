@@ -332,7 +332,7 @@ int choose_mode(const rtw_scene* sc, int requested, int* mode) {
   if (requested == RTW_KERNEL_SPHERES_SMEM) {
     if (!smem_ok) return fail("RTW_KERNEL_SPHERES_SMEM needs a sphere-only scene whose tables fit in shared memory");
     *mode = 0;
-  } else if (requested == RTW_KERNEL_BVH) {
+  } else if (requested == RTW_KERNEL_BVH || requested == RTW_KERNEL_BVH_PERLANE) {
     *mode = 1;
   } else if (requested == RTW_KERNEL_AUTO) {
     *mode = (smem_ok && nspheres <= kSweepAutoMax) ? 0 : 1;
@@ -472,7 +472,8 @@ int rtw_render_device(const rtw_scene* scene, const rtw_render_cfg* cfg, int64_t
     RTW_CUDA(cudaEventCreate(&e1));
     RTW_CUDA(cudaEventRecord(e0, stream));
   }
-  cudaError_t le = rtw::launch_render(p, mode, rpl, want_stats, scene->sm_count, stream);
+  int variant = RTW_BVH_NONE;
+  cudaError_t le = rtw::launch_render(p, mode, rpl, cfg->kernel == RTW_KERNEL_BVH_PERLANE, want_stats, scene->sm_count, stream, &variant);
   if (le != cudaSuccess) return fail_cuda("launch k_render", le);
   if (stats) {
     RTW_CUDA(cudaEventRecord(e1, stream));
@@ -486,6 +487,7 @@ int rtw_render_device(const rtw_scene* scene, const rtw_render_cfg* cfg, int64_t
     read_counters(h, stats);
     stats->kernel_ms = ms;
     stats->kernel_used = mode == 0 ? RTW_KERNEL_SPHERES_SMEM : RTW_KERNEL_BVH;
+    stats->bvh_variant = variant;
     stats->launches = 1;
   }
   return 0;

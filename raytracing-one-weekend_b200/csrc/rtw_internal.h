@@ -48,7 +48,9 @@ struct PrimaryParams {
   uint8_t* front;
 };
 
-cudaError_t launch_render(const RenderParams& p, int mode, int rays_per_lane, bool stats, int sm_count, cudaStream_t stream);
+// mode 0: sphere sweep (rays_per_lane 1/2/4); mode 1: BVH (force_perlane: never the wavefront kernel).  *variant <- rtw_bvh_variant launched.
+cudaError_t launch_render(const RenderParams& p, int mode, int rays_per_lane, bool force_perlane, bool stats, int sm_count, cudaStream_t stream,
+                          int* variant);
 cudaError_t launch_primary_f32(const PrimaryParams& p, int mode, cudaStream_t stream);
 cudaError_t launch_primary_f64(const rtw_primitive* prims, int nprims, const rtw_camera& cam, uint32_t width, uint32_t height, double time,
                                int32_t* prim_id, double* t, double* normal, uint8_t* front, cudaStream_t stream);

@@ -1298,8 +1298,10 @@ static SmemLayout smem_layout(const RenderParams& p) {
   return so;
 }
 
-cudaError_t launch_render(const RenderParams& p_in, int mode, int rays_per_lane, bool stats, int sm_count, cudaStream_t stream) {
+cudaError_t launch_render(const RenderParams& p_in, int mode, int rays_per_lane, bool force_perlane, bool stats, int sm_count, cudaStream_t stream,
+                          int* variant) {
   RenderParams p = p_in;
+  if (variant) *variant = RTW_BVH_NONE;
   p.so = smem_layout(p);
   const size_t smem = mode == 0 ? 16 + static_cast<size_t>(p.sc.n_static + p.sc.n_moving + 1) * 32 : 0;
   if (mode == 0) {
@@ -1314,9 +1316,12 @@ cudaError_t launch_render(const RenderParams& p_in, int mode, int rays_per_lane,
   // 96 records per warp, 16 traversal steps between exchanges, shading batches of 32 (tuning record in DESIGN.md)
   constexpr int kWfWarps = 28, kWfRecords = 96;
   const size_t wf_smem = p.so.records + static_cast<size_t>(kWfWarps) * wf_warp_bytes(kWfRecords);
-  if (bsm && p.sc.leaf_direct && wf_smem <= 227u * 1024u && rays_per_lane != 100)
+  if (bsm && p.sc.leaf_direct && wf_smem <= 227u * 1024u && !force_perlane) {
+    if (variant) *variant = RTW_BVH_WAVEFRONT;
     return stats ? launch_wf_t<true, true, kWfWarps, kWfRecords, 16, 32>(p, sm_count, wf_smem, stream)
                  : launch_wf_t<true, false, kWfWarps, kWfRecords, 16, 32>(p, sm_count, wf_smem, stream);
+  }
+  if (variant) *variant = RTW_BVH_PERLANE;
 #define RTW_BVH(ST, SV, MB)                                                                                         \
   return bsm ? (stats ? launch_bvh_t<true, true, ST, SV, MB>(p, sm_count, bsm, stream) : launch_bvh_t<true, false, ST, SV, MB>(p, sm_count, bsm, stream)) \
              : (stats ? launch_bvh_t<false, true, ST, SV, MB>(p, sm_count, 0, stream) : launch_bvh_t<false, false, ST, SV, MB>(p, sm_count, 0, stream))

@@ -183,6 +183,7 @@ extern "C" int rtw_render_multi_gpu(const rtw_scene_desc* desc, const rtw_render
       if (sts[g].kernel_ms > stats->kernel_ms) stats->kernel_ms = sts[g].kernel_ms;  // max over GPUs
     }
     stats->kernel_used = sts[0].kernel_used;
+    stats->bvh_variant = sts[0].bvh_variant;
     stats->launches = ngpus + 1 + (rows ? 1 : 0);
   }
   cleanup();

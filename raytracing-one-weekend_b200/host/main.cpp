@@ -94,7 +94,8 @@ int main(int argc, char* argv[]) {
     if (v == "auto") dev.kernel = RTW_KERNEL_AUTO;
     else if (v == "spheres") dev.kernel = RTW_KERNEL_SPHERES_SMEM;
     else if (v == "bvh") dev.kernel = RTW_KERNEL_BVH;
-    else throw std::invalid_argument("--kernel must be auto, spheres or bvh");
+    else if (v == "bvh-perlane") dev.kernel = RTW_KERNEL_BVH_PERLANE;
+    else throw std::invalid_argument("--kernel must be auto, spheres, bvh or bvh-perlane");
   }};
 
   try {

@@ -10,7 +10,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 rtw = importlib.import_module("raytracing-one-weekend_b200")
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--kernel", default="auto", choices=["auto", "spheres", "bvh"])
+ap.add_argument("--kernel", default="auto", choices=["auto", "spheres", "bvh", "bvh-perlane"])
 ap.add_argument("--rays-per-lane", type=int, default=0, help="sphere sweep only: 1, 2 or 4 paths per lane")
 ap.add_argument("--spp", type=int, default=16)
 ap.add_argument("--width", type=int, default=1920)
@@ -26,7 +26,7 @@ elif a.scene == "suzanne":
 else:
     scene = rtw.mesh_on_ground_scene(a.scene, aspect)
 H = rtw.image_height(a.width, aspect)
-k = {"auto": rtw.KERNEL_AUTO, "spheres": rtw.KERNEL_SPHERES_SMEM, "bvh": rtw.KERNEL_BVH}[a.kernel]
+k = {"auto": rtw.KERNEL_AUTO, "spheres": rtw.KERNEL_SPHERES_SMEM, "bvh": rtw.KERNEL_BVH, "bvh-perlane": rtw.KERNEL_BVH_PERLANE}[a.kernel]
 for i in range(2):
     acc, st = rtw.render(scene, a.width, H, a.spp, a.depth, kernel=k, rays_per_lane=a.rays_per_lane, stats=a.stats)
 p, r = st["paths"], st["rays"]

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""Kernel-variant sweep on one GPU: each variant id (passed through rtw_render_cfg.rays_per_lane) renders the same frame; prints
-throughput and the difference of its accumulation buffer from the default kernel's.
-    python scripts/variant_sweep.py --variants 0,200,201 [--scene cover|suzanne|PATH.obj] [--spp 64]"""
+"""Kernel-variant sweep on one GPU: every variant renders the same frame; prints throughput and the difference of its accumulation
+buffer from the first variant's.  Variant ids: 0 = BVH (library's choice), 100 = BVH per-lane kernel forced, 1 = sphere sweep;
+any other id is passed through rtw_render_cfg.rays_per_lane to whatever experimental instantiations the library was built with.
+    python scripts/variant_sweep.py --variants 0,100 [--scene cover|suzanne|standin|PATH.obj] [--spp 64]"""
 import argparse
 import importlib
 import sys
@@ -39,7 +40,8 @@ for v in [int(x) for x in a.variants.split(",")]:
     best = None
     try:
         for i in range(a.reps):
-            acc, st = rtw.render(scene, a.width, H, a.spp, a.depth, kernel=rtw.KERNEL_BVH, rays_per_lane=v)
+            kw = {100: dict(kernel=rtw.KERNEL_BVH_PERLANE), 1: dict(kernel=rtw.KERNEL_SPHERES_SMEM)}.get(v, dict(kernel=rtw.KERNEL_BVH, rays_per_lane=v))
+            acc, st = rtw.render(scene, a.width, H, a.spp, a.depth, **kw)
             best = st["kernel_ms"] if best is None else min(best, st["kernel_ms"])
     except Exception as e:  # noqa: BLE001
         print(f"variant {v}: FAILED {e}")

@@ -209,13 +209,15 @@ def test_samplers_have_the_reference_distribution(gpu, port):
 # ------------------------------------------------------------------------------------------------------------------
 # K1 / K2: the render loop on the oracle's random stream
 # ------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("kernel_name,rpl", [("spheres", 4), ("spheres", 2), ("spheres", 1), ("bvh", 0)])
+@pytest.mark.parametrize("kernel_name,rpl", [("spheres", 4), ("spheres", 2), ("spheres", 1), ("bvh", 0), ("bvh-perlane", 0)])
 def test_render_same_stream_cover(gpu, port, kernel_name, rpl):
-    kernel = gpu.KERNEL_SPHERES_SMEM if kernel_name == "spheres" else gpu.KERNEL_BVH
+    kernel = {"spheres": gpu.KERNEL_SPHERES_SMEM, "bvh": gpu.KERNEL_BVH, "bvh-perlane": gpu.KERNEL_BVH_PERLANE}[kernel_name]
     scene, osc = gpu.cover_scene(), port.scene_cover()
     acc, st = same_stream_check(gpu, port, scene, osc, 200, 133, 20, 20, seed=0, kernel=kernel, rays_per_lane=rpl)
     assert abs(st["rays"] / st["paths"] - 2.30) < 0.02  # SURVEY: 2.30 rays per path at depth 20
-    assert st["kernel_used"] == kernel
+    assert st["kernel_used"] == (gpu.KERNEL_SPHERES_SMEM if kernel_name == "spheres" else gpu.KERNEL_BVH)
+    # the cover scene's tables leave room for the path records: BVH means the wavefront-per-warp kernel unless the per-lane one is forced
+    assert st["bvh_variant"] == {"spheres": gpu.BVH_NONE, "bvh": gpu.BVH_WAVEFRONT, "bvh-perlane": gpu.BVH_PERLANE}[kernel_name]
 
 
 @pytest.mark.parametrize("depth", [0, 1, 2, 50])
@@ -439,7 +441,7 @@ def test_multi_gpu_in_process(gpu):
     assert np.array_equal(one, rows) and st["paths"] == 200 * 133 * 32
 
 
-@pytest.mark.parametrize("kernel_name", ["spheres", "bvh"])
+@pytest.mark.parametrize("kernel_name", ["spheres", "bvh", "bvh-perlane"])
 @pytest.mark.parametrize("tile_rows,count", [(8, 2), (5, 3), (16, 8), (1, 4)])
 def test_row_tile_split_is_bit_identical(gpu, kernel_name, tile_rows, count):
     """SURVEY 8(e) alternative: each participant renders ALL samples of its interleaved row tiles into a packed buffer; the
@@ -448,7 +450,7 @@ def test_row_tile_split_is_bit_identical(gpu, kernel_name, tile_rows, count):
     import torch
     scene = gpu.cover_scene()
     W, H, S = 200, 133, 8
-    k = {"spheres": gpu.KERNEL_SPHERES_SMEM, "bvh": gpu.KERNEL_BVH}[kernel_name]
+    k = {"spheres": gpu.KERNEL_SPHERES_SMEM, "bvh": gpu.KERNEL_BVH, "bvh-perlane": gpu.KERNEL_BVH_PERLANE}[kernel_name]
     ds = gpu.DeviceScene(scene, 0)
     stream = torch.cuda.current_stream().cuda_stream
     full = torch.zeros((H, W, 4), dtype=torch.int64, device="cuda:0")
