@@ -54,10 +54,18 @@ def build_scene(rtw, name, wl):
             if rtw.host().rtwh_make_mesh(str(SUZANNE).encode(), path.encode(), a, 20221018, 0.08, C.byref(n)) != 0:
                 raise RuntimeError(rtw.host().rtwh_last_error().decode())
     return rtw.mesh_on_ground_scene(path, aspect)
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the `ncu --set full` captures summarised
-# under profiles/ (r01_prof_k2_final.txt, r01_prof_k1_final.txt, r01_prof_k2_dragon.txt).  The traffic is the accumulation
-# buffer (66 MB at 1080p) being read after the memset and partly written back, plus the scene once: it does not scale with spp.
-NCU_TRAFFIC_BYTES = {("cover", "bvh"): 66.46e6 + 17.97e6, ("cover", "sweep"): 66.45e6 + 19.11e6, ("dragon", "bvh"): 284.46e6 + 71.33e6}
+# Per-launch figures of the dominant kernel taken from the `ncu --set full` captures summarised under profiles/ (one launch each):
+#   traffic = dram__bytes_read.sum + dram__bytes_write.sum.  It is the accumulation buffer (66 MB at 1080p) being read after the memset
+#             and partly written back, plus the scene once: it does not scale with spp.
+#   tinst_per_ray = smsp__inst_executed.sum x smsp__thread_inst_executed_per_inst_executed.ratio / rays of that launch: the thread
+#             instructions one ray costs, the numerator of the instruction-issue roofline below.
+NCU = {
+    ("cover", "wf"): {"traffic": 66.87e6 + 16.75e6, "tinst_per_ray": 1412.0, "lanes_per_inst": 23.89, "issue_active_pct": 79.3, "file": "profiles/r01_prof_k2w.txt"},
+    ("cover", "perlane"): {"traffic": 66.46e6 + 15.43e6, "tinst_per_ray": 1374.0, "lanes_per_inst": 18.89, "issue_active_pct": 82.7, "file": "profiles/r01_prof_k2_perlane.txt"},
+    ("cover", "sweep"): {"traffic": 66.47e6 + 17.30e6, "tinst_per_ray": 7476.0, "lanes_per_inst": 29.71, "issue_active_pct": 79.1, "file": "profiles/r01_prof_k1.txt"},
+    ("dragon", "perlane"): {"traffic": 286.01e6 + 69.93e6, "tinst_per_ray": 1623.0, "lanes_per_inst": 12.62, "issue_active_pct": 61.4, "file": "profiles/r01_prof_k2_dragon.txt"},
+    ("suzanne", "perlane"): {"traffic": 66.51e6 + 18.81e6, "tinst_per_ray": 1124.0, "lanes_per_inst": 15.74, "issue_active_pct": 80.5, "file": "profiles/r01_prof_k2_suzanne.txt"},
+}
 # canonical FP32 flop costs of SURVEY.md 8(d) (FMA = 2)
 FLOP_STATIC_TEST, FLOP_MOVING_TEST, FLOP_HIT, FLOP_SHADE = 17.0, 23.0, 40.0, 80.0
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
@@ -378,11 +386,29 @@ def main() -> int:
     paths_gpu = paths_total / world
     peak_tflops, _ = rtw.fp32_peak(local_rank, 1.0)
     peak_note = "FFMA micro-benchmark (rtw_fp32_peak) measured in this run; MEASURED_PEAKS.json carries no FP32 figure; nominal %.1f" % NOMINAL_FP32_TFLOPS
+    fam = "cover" if args.workload.startswith("cover") else ("dragon" if args.workload.startswith("dragon") else "suzanne")
+
+    def ncu(kernel_key):
+        return NCU.get((fam, kernel_key), {})
+
     def traffic(kernel_key):
         if args.traffic_bytes is not None:
             return args.traffic_bytes
-        fam = "cover" if args.workload.startswith("cover_1080p") else ("dragon" if args.workload.startswith("dragon") else None)
-        return NCU_TRAFFIC_BYTES.get((fam, kernel_key))
+        return ncu(kernel_key).get("traffic") if args.workload.startswith(("cover_1080p", "dragon", "suzanne")) else None
+
+    def issue_roofline(kernel_key, rays, ms):
+        """Instruction-issue roofline: thread instructions per second against SMs x 4 schedulers x 32 lanes x SM clock."""
+        n = ncu(kernel_key)
+        if not n:
+            return None
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        peak = sm_count * 4 * 32 * mhz * 1e6 / 1e12
+        ach = n["tinst_per_ray"] * rays / (ms * 1e-3) / 1e12
+        return {"bound": "instruction_issue", "achieved": ach, "peak": peak, "unit": "T thread-instructions/s", "frac": ach / peak,
+                "thread_instructions_per_ray": n["tinst_per_ray"], "lanes_per_instruction": n["lanes_per_inst"],
+                "issue_active_pct": n["issue_active_pct"], "source": n["file"] + " (ncu, one launch)",
+                "peak_source": f"{sm_count} SMs x 4 schedulers x 32 lanes x {mhz:.0f} MHz (SM clock sampled during the timed region)"}
 
     moving_frac = n_moving / max(n_moving + n_static, 1)
     test_flop = FLOP_MOVING_TEST * moving_frac + FLOP_STATIC_TEST * (1 - moving_frac)
@@ -406,13 +432,13 @@ def main() -> int:
         flop = rays_gpu * (nodes_pr * 24.0 + tests_pr * test_flop + tris_pr * 36.0 + n_big * FLOP_STATIC_TEST + FLOP_SHADE) + (rays_gpu - paths_gpu) * FLOP_HIT
         ach = flop / (kernel_ms * 1e-3) / 1e12
         roofline = {"bound": "fp32_fma", "kernel": kernel_label, "achieved": ach,
-                    "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops, "traffic": traffic("bvh"), "peak_source": peak_note,
+                    "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops, "traffic": traffic("wf" if wavefront else "perlane"), "peak_source": peak_note,
                     "algorithmic_flop_per_launch": flop, "kernel_ms": kernel_ms,
                     "per_ray": {"node_visits": nodes_pr, "sphere_tests": tests_pr, "triangle_tests": tris_pr},
                     "flop_model": "rays x (nodes x 2 boxes x 12 + sphere tests x 17|23 + triangle tests x 36 + big spheres x 17 + 80) + hits x 40 (SURVEY 8(d))",
                     "note": "culling removes ~97% of the sweep's flops, so the flop fraction is low by construction; what limits this kernel is "
-                            "instruction issue under divergence (profiles/r01_prof_k2_final.txt: 81% issue-active, 18.7 of 32 lanes per "
-                            "instruction = 47% of the thread-instruction peak; HBM 0.3% of peak)"}
+                            "instruction issue under divergence: see roofline_issue (thread instructions per second against the issue peak)"}
+    roofline_issue = issue_roofline("sweep" if kernel_used == rtw.KERNEL_SPHERES_SMEM else ("wf" if wavefront else "perlane"), rays_gpu, kernel_ms)
     # the SURVEY's FP32-roofline target is defined on the brute-force sweep: measure that kernel too (reduced spp, same scene)
     roofline_sweep = None
     if world == 1 and kernel_used != rtw.KERNEL_SPHERES_SMEM and not scene_has_triangles:
@@ -446,7 +472,7 @@ def main() -> int:
                                    else f"spp-shard x{world}, one int64 NCCL reduce"), "kernel": "spheres_smem (K1)" if kernel_used == rtw.KERNEL_SPHERES_SMEM else ("bvh wavefront (K2w)" if wavefront else "bvh per-lane (K2)"),
                    "l2": "256 MB buffer written between timed iterations (scene tables live in shared memory; accumulation buffer 66 MB)"},
         "mrays_per_s": rays_total / (ms_per_step * 1e-3) / 1e6, "rays_per_path": rays_total / paths_total,
-        "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks, "roofline": roofline, "roofline_sphere_sweep": roofline_sweep,
+        "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks, "roofline": roofline, "roofline_issue": roofline_issue, "roofline_sphere_sweep": roofline_sweep,
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))
