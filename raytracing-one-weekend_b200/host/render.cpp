@@ -203,14 +203,21 @@ void render(const Scene& world, const Config& cfg) {
   const DeviceOptions& opt = device_options();
   std::cerr << "Started rendering on " << opt.ngpus << " GPU(s)\n";
   const auto start = khr::steady_clock::now();
+  const auto ms_since = [](khr::steady_clock::time_point t0) { return khr::duration<double, std::milli>(khr::steady_clock::now() - t0).count(); };
   const Accum img = opt.checkpoint.empty() ? render_accum(world, cfg) : render_progressive(world, cfg, opt.checkpoint, opt.checkpoint_every);
+  const double render_ms = ms_since(start);
+  const auto t_out = khr::steady_clock::now();
   if (opt.binary_ppm) write_ppm_binary(std::cout, img, opt.device);
   else write_ppm(std::cout, img);
   std::cout.flush();
+  const double out_ms = ms_since(t_out);
   const auto took = khr::duration_cast<khr::milliseconds>(khr::steady_clock::now() - start);
   const double paths = static_cast<double>(img.stats.paths), rays = static_cast<double>(img.stats.rays);
   std::cerr << "kernel " << img.stats.kernel_ms << " ms: " << paths / (img.stats.kernel_ms * 1e3) << " Mpaths/s, "
             << rays / (img.stats.kernel_ms * 1e3) << " Mrays/s (" << rays / std::max(paths, 1.0) << " rays/path)\n";
+  // where the wall time went: the first CUDA call of a process creates the context (seconds on a cold box)
+  std::cerr << "host: render call " << render_ms << " ms (flatten + upload " << img.stats.h2d_ms << ", download " << img.stats.d2h_ms
+            << "), image output " << out_ms << " ms\n";
   std::cerr << "\nDone in " << took.count() << "ms\n";
 }
 
