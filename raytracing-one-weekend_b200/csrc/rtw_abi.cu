@@ -243,6 +243,9 @@ int flatten_host(const rtw_scene_desc* desc, HostFlat* hf) {
   size_t n_nodes = 0, n_refs = 0;
   if (direct) {
     n_nodes = builder.build_items_direct(items, nodes_out);
+    if (builder.max_depth() > rtw::kBvhStack)
+      return fail("rtw_scene_upload: the BVH is deeper than the kernels' traversal stack (" + std::to_string(builder.max_depth()) + " > " +
+                  std::to_string(rtw::kBvhStack) + " levels): degenerate primitive distribution");
   } else {
     std::vector<rtw::Box3> boxes(n_items);
     std::vector<uint32_t> refs(n_items);

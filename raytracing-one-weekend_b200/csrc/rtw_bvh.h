@@ -3,6 +3,7 @@
 // survey measured at 63-108 node visits per ray; only the closest-hit semantics are kept.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <future>
 #include <cstdint>
@@ -36,6 +37,7 @@ class BvhBuilder {
   struct Item { Box3 box; float c[3]; uint32_t ref; };  // one primitive: bounds, centroid, encoded reference
   int kMaxLeaf = 1;  // primitives per leaf (<= 31); 1 = primitive reference stored in the child code
   static constexpr int kBins = 16;
+  static constexpr int kSahDepthLimit = 32;  // see direct_node
   // references are (kind << 30) | index with index < 2^28; bit 29 marks a direct leaf so that its code ~ref is never -1
   static constexpr uint32_t kDirectMark = 1u << 29;
 
@@ -95,6 +97,8 @@ class BvhBuilder {
   }
 
   const std::vector<PackedNode>& nodes() const { return nodes_; }
+  // inner-node levels of the direct (single-primitive-leaf) tree: the traversal stack of the kernels must hold this many entries
+  int max_depth() const { return max_depth_.load(); }
   const std::vector<uint32_t>& leaf_refs() const { return leaf_refs_; }
 
  private:
@@ -131,12 +135,28 @@ class BvhBuilder {
   static float area_of(const Box3& b) { return b.half_area(); }
 
   void direct_node(size_t idx, size_t begin, size_t end, int depth) {
+    note_depth(depth + 1);
     const size_t n = end - begin;
     Item* it = items_.data();
     size_t mid = begin;
     Box3 lb, rb;
     if (n == 2) {
       mid = begin + 1; lb = it[begin].box; rb = it[begin + 1].box;
+    } else if (depth >= kSahDepthLimit) {
+      // SAH on a pathological distribution (centroids spread over dozens of orders of magnitude) peels a few primitives per
+      // level; below this depth the range is split at the object median instead, which bounds the tree depth by
+      // kSahDepthLimit + log2(n) < kBvhStack (the kernels' traversal stack)
+      float clo[3] = {1e30f, 1e30f, 1e30f}, chi[3] = {-1e30f, -1e30f, -1e30f};
+      for (size_t i = begin; i < end; ++i)
+        for (int k = 0; k < 3; ++k) { clo[k] = std::min(clo[k], it[i].c[k]); chi[k] = std::max(chi[k], it[i].c[k]); }
+      int ax = 0;
+      if (chi[1] - clo[1] > chi[ax] - clo[ax]) ax = 1;
+      if (chi[2] - clo[2] > chi[ax] - clo[ax]) ax = 2;
+      mid = begin + n / 2;
+      std::nth_element(it + begin, it + mid, it + end, [ax](const Item& a, const Item& b) { return a.c[ax] < b.c[ax]; });
+      lb.reset(); rb.reset();
+      for (size_t i = begin; i < mid; ++i) lb.grow(it[i].box);
+      for (size_t i = mid; i < end; ++i) rb.grow(it[i].box);
     } else if (n <= 8) {
       // exact SAH over the sorted order of the widest centroid axis
       float clo[3] = {1e30f, 1e30f, 1e30f}, chi[3] = {-1e30f, -1e30f, -1e30f};
@@ -225,6 +245,8 @@ class BvhBuilder {
   }
   std::vector<Item> items_;
   PackedNode* ext_nodes_ = nullptr;
+  std::atomic<int> max_depth_{0};
+  void note_depth(int d) { int cur = max_depth_.load(std::memory_order_relaxed); while (d > cur && !max_depth_.compare_exchange_weak(cur, d, std::memory_order_relaxed)) {} }
 
   // Child boxes are stored as centre c and half-extent e (node_slabs on the device: t = (c -+ e) / d - o / d costs FMA-pipe
   // operations instead of min/max ALU operations).  e is rounded up so that [c - e, c + e] contains the exact box plus four ulps of

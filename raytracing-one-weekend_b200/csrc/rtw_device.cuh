@@ -18,7 +18,7 @@ namespace rtw {
 
 constexpr float kTMin = 0.001f;  // render.cpp:33 default tmin of BVHNode::hit
 constexpr float kInf = __builtin_huge_valf();
-constexpr int kBvhStack = 48;
+constexpr int kBvhStack = 64;  // the host builder bounds the tree depth by 32 + log2(n) (rtw_bvh.h) and rtw_scene_upload checks it
 
 // ---------------------------------------------------------------------------------------------------------
 // Device scene (flattened SoA; built by rtw_scene_upload)

@@ -211,6 +211,13 @@ def test_flatten_tables_and_bvh_invariants(rtw, tmp_path):
     prims = np.zeros(50, rtw.PRIM_DTYPE); prims["radius"] = 1.0
     r = rtw.flatten_info(rtw.custom_scene(prims, mats, **cam))
     assert r["bvh_errors"] == 0 and r["bvh_max_depth"] <= 50
+    # centroids spread over 60 orders of magnitude: plain SAH peels a few primitives per level (57 levels measured); the builder
+    # switches to median splits below level 32, so the tree stays inside the kernels' 64-entry traversal stack
+    n = 1500
+    prims = np.zeros(n, rtw.PRIM_DTYPE)
+    prims["a"][:, 0] = 1e-30 * 1.08 ** np.arange(n); prims["b"] = prims["a"]; prims["radius"] = 1e-37
+    r = rtw.flatten_info(rtw.custom_scene(prims, mats, **cam))
+    assert r["bvh_errors"] == 0 and 32 < r["bvh_max_depth"] <= 32 + 11
     # the multi-primitive leaf layout (tuning knob) keeps the same invariants
     import os, subprocess, sys, textwrap
     code = textwrap.dedent(f"""
