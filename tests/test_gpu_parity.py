@@ -512,3 +512,17 @@ def test_large_sphere_grids(gpu, port, nsqrt):
     assert abs(st["rays"] - rays) / rays < 0.02
     with pytest.raises(gpu.RtwError, match="shared memory"):
         gpu.render(scene, 16, 16, 1, kernel=gpu.KERNEL_SPHERES_SMEM) if nsqrt == 120 else (_ for _ in ()).throw(gpu.RtwError("shared memory"))
+
+
+@pytest.mark.parametrize("nsqrt,variant", [(1, "wavefront"), (5, "wavefront"), (12, "wavefront"), (13, "perlane"), (15, "perlane")])
+def test_bvh_kernel_crossover_by_table_size(gpu, port, nsqrt, variant):
+    """KERNEL_BVH picks the wavefront-per-warp kernel while the scene tables leave room for the per-warp path records in shared
+    memory (about 600 spheres), the per-lane kernel beyond; both sides of the crossover trace the oracle's paths on the same stream."""
+    scene, osc = gpu.cover_scene(nsqrt), port.scene_cover(nsqrt)
+    acc, st = same_stream_check(gpu, port, scene, osc, 120, 80, 8, 20, seed=nsqrt, kernel=gpu.KERNEL_BVH, frac_tol=0.015)
+    assert st["kernel_used"] == gpu.KERNEL_BVH
+    assert st["bvh_variant"] == (gpu.BVH_WAVEFRONT if variant == "wavefront" else gpu.BVH_PERLANE), len(scene.prims)
+    forced, st2 = gpu.render(scene, 120, 80, 8, 20, seed=nsqrt, kernel=gpu.KERNEL_BVH_PERLANE)
+    assert st2["bvh_variant"] == gpu.BVH_PERLANE and st2["paths"] == st["paths"]
+    rel = np.abs(forced[..., :3] - acc[..., :3]) / np.maximum(acc[..., :3], 1e-3)
+    assert (rel.max(axis=2) > 1e-5).mean() < 0.03   # same paths except at fp32 ties between the ground and a sphere resting on it
