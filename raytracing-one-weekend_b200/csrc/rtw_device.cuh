@@ -257,6 +257,21 @@ __device__ __forceinline__ T triangle_hit(V3<T> o, V3<T> d, V3<T> a, V3<T> e1, V
   return T(-1);
 }
 
+// The same test for the fp32 tracers, without the division on the reject path: with det > 0 the reference's conditions
+// u >= 0, v >= 0, u + v <= 1, tmin <= t <= tmax on u = un/det, v = vn/det, t = tn/det are the same conditions on the numerators
+// scaled by det; only an accepted hit (one in three or four tests on the meshes) pays for t = tn / det.  The leaf test runs at
+// ~6 of 32 lanes (profiles/r01_prof_k2_suzanne_hotlines.txt), so every instruction removed from it counts five-fold.
+__device__ __forceinline__ float triangle_hit_fast(F3 o, F3 d, F3 a, F3 e1, F3 e2, F3 n, float tmin, float tmax) {
+  const float det = -dot(d, n);
+  const F3 ao = o - a;
+  const F3 dao = cross(ao, d);
+  const float un = dot(e2, dao);
+  const float vn = -dot(e1, dao);
+  const float tn = dot(ao, n);
+  if (det >= 1e-6f && un >= 0.0f && vn >= 0.0f && (un + vn) <= det && tn >= tmin * det && tn <= tmax * det) return tn / det;
+  return -1.0f;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Materials (common-model.cpp:13-62).  Returns false when the path is absorbed.
 // ---------------------------------------------------------------------------------------------------------

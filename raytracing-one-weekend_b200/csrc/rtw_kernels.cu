@@ -247,7 +247,7 @@ __device__ __forceinline__ void trace_bvh(const DevScene& sc, F3 o, F3 d, float 
       if (ref >> 30) {
         if (STATS) ++n_tri;
         const float4 q0 = __ldg(&sc.tri[3 * i]), q1 = __ldg(&sc.tri[3 * i + 1]), q2 = __ldg(&sc.tri[3 * i + 2]);
-        const float t = triangle_hit<float>(o, d, mk<float>(q0.x, q0.y, q0.z), mk<float>(q1.x, q1.y, q1.z), mk<float>(q2.x, q2.y, q2.z),
+        const float t = triangle_hit_fast(o, d, mk<float>(q0.x, q0.y, q0.z), mk<float>(q1.x, q1.y, q1.z), mk<float>(q2.x, q2.y, q2.z),
                                             mk<float>(q0.w, q1.w, q2.w), kTMin, best_t);
         if (t >= 0.0f) { best_t = t; best_i = kHitTri | i; }
       } else {
@@ -685,7 +685,7 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
           if (ref >> 30) {
             if (STATS) ++n_tri;
             const float4 q0 = ld4<SMEM>(tb.tri, 3 * i), q1 = ld4<SMEM>(tb.tri, 3 * i + 1), q2 = ld4<SMEM>(tb.tri, 3 * i + 2);
-            const float t = triangle_hit<float>(o, d, mk<float>(q0.x, q0.y, q0.z), mk<float>(q1.x, q1.y, q1.z), mk<float>(q2.x, q2.y, q2.z),
+            const float t = triangle_hit_fast(o, d, mk<float>(q0.x, q0.y, q0.z), mk<float>(q1.x, q1.y, q1.z), mk<float>(q2.x, q2.y, q2.z),
                                                 mk<float>(q0.w, q1.w, q2.w), kTMin, best_t);
             if (t >= 0.0f) { best_t = t; best_i = kHitTri | i; }
           } else {
@@ -1013,7 +1013,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_render_wf(const __grid_constant_
           if (ref >> 30) {
             if (STATS) ++n_tri;
             const float4 q0 = ld4<SMEM>(tb.tri, 3 * i), q1 = ld4<SMEM>(tb.tri, 3 * i + 1), q2 = ld4<SMEM>(tb.tri, 3 * i + 2);
-            const float t = triangle_hit<float>(o, d, mk<float>(q0.x, q0.y, q0.z), mk<float>(q1.x, q1.y, q1.z), mk<float>(q2.x, q2.y, q2.z),
+            const float t = triangle_hit_fast(o, d, mk<float>(q0.x, q0.y, q0.z), mk<float>(q1.x, q1.y, q1.z), mk<float>(q2.x, q2.y, q2.z),
                                                 mk<float>(q0.w, q1.w, q2.w), kTMin, best_t);
             if (t >= 0.0f) { best_t = t; best_i = kHitTri | i; }
           } else {
