@@ -526,3 +526,7 @@ def test_bvh_kernel_crossover_by_table_size(gpu, port, nsqrt, variant):
     assert st2["bvh_variant"] == gpu.BVH_PERLANE and st2["paths"] == st["paths"]
     rel = np.abs(forced[..., :3] - acc[..., :3]) / np.maximum(acc[..., :3], 1e-3)
     assert (rel.max(axis=2) > 1e-5).mean() < 0.03   # same paths except at fp32 ties between the ground and a sphere resting on it
+    # fewer paths than one warp's record pool, fewer units than warps: the kernels must still count every path exactly once
+    for (w, h, spp) in ((2, 2, 1), (3, 2, 5), (130, 2, 1), (129, 3, 33)):
+        tiny, st3 = gpu.render(scene, w, h, spp, 3, seed=1, kernel=gpu.KERNEL_BVH)
+        assert st3["paths"] == w * h * spp and np.all(tiny[..., 3] == spp), (w, h, spp)
