@@ -461,6 +461,9 @@ def main() -> int:
     if world == 1 and not args.no_cpu_baseline and not scene_has_triangles:
         threads = min(os.cpu_count() or 1, 64)
         cpu_baseline = cpu_reference_run(max(width // 2, 200), aspect, 1, depth, threads)
+        if threads > 4:  # also at the reference's default -t 4 (all threads share one unsynchronised mt19937)
+            t4 = cpu_reference_run(max(width // 4, 200), aspect, 1, depth, 4)
+            cpu_baseline["reference_default_threads"] = {"value": t4["value"], "unit": "Mpaths/s", "cores": 4, "sample": t4["sample"]}
     elif world == 1 and not args.no_cpu_baseline:
         cpu_baseline = cpu_reference_mesh(scene, aspect, depth)
 
