@@ -38,6 +38,7 @@ class BvhBuilder {
   int kMaxLeaf = 1;  // primitives per leaf (<= 31); 1 = primitive reference stored in the child code
   static constexpr int kBins = 16;
   static constexpr int kSahDepthLimit = 32;  // see direct_node
+  static constexpr size_t kTaskRange = 16384; // subtrees over more primitives than this are built by their own task
   // references are (kind << 30) | index with index < 2^28; bit 29 marks a direct leaf so that its code ~ref is never -1
   static constexpr uint32_t kDirectMark = 1u << 29;
 
@@ -237,7 +238,7 @@ class BvhBuilder {
     // big subtrees go to other threads (disjoint item and node ranges)
     std::future<void> task;
     if (nl > 1) {
-      if (n > 65536 && depth < 8) task = std::async(std::launch::async, [=] { direct_node(left_idx, begin, mid, depth + 1); });
+      if (n > kTaskRange && depth < 12) task = std::async(std::launch::async, [=] { direct_node(left_idx, begin, mid, depth + 1); });
       else direct_node(left_idx, begin, mid, depth + 1);
     }
     if (end - mid > 1) direct_node(right_idx, mid, end, depth + 1);
