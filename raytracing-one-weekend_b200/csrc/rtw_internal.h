@@ -36,6 +36,7 @@ struct RenderParams {
   // row-tile split: this launch renders tiles tile_index, tile_index + tile_count, ... of tile_rows rows; npix counts the pixels of
   // the packed local buffer (accum); Philox and the camera are keyed on the GLOBAL pixel.  tile_count <= 1: whole image.
   uint32_t tile_rows, tile_count, tile_index;
+  uint32_t leaf_min;   // per-lane BVH kernel: lanes that must stand on a leaf before leaves are tested (set by launch_render)
 };
 
 struct PrimaryParams {

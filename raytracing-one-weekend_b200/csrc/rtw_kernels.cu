@@ -650,8 +650,10 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
       }
     }
 
-    // ---- traversal phase: STEPS steps; in each, lanes on an inner node visit it, then lanes on a leaf test its primitive(s)
-    // at once.  (Holding leaves back until 4..16 lanes stand on one was measured twice and lost 3-8 %: DESIGN.md.)
+    // ---- traversal phase: STEPS steps; in each, lanes on an inner node visit it, then lanes on a leaf test its primitive(s):
+    // at once in sphere scenes (holding sphere leaves back until 4..16 lanes stand on one lost 3-8 % on the cover scene), once
+    // p.leaf_min lanes stand on one in scenes with triangles (measured on the 991k-triangle mesh, Mpaths/s: 1/2/3/4/5/6/8/12 lanes =
+    // 3034/3094/3176/3211/3205/3163/3017/2573; suzanne 7290 -> 7345).
 #pragma unroll 1
     for (int step = 0; step < STEPS; ++step) {
       if (state == TRAV && node >= 0) {
@@ -676,7 +678,12 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
           node = kMiss; state = DONE;
         }
       }
-      if (state == TRAV && node < 0) {
+      bool do_leaf = true;
+      if (p.leaf_min > 1u) {  // hold leaves back until enough lanes stand on one, or no lane has an inner node left to visit
+        const uint32_t lm = __ballot_sync(0xffffffffu, state == TRAV && node < 0), im = __ballot_sync(0xffffffffu, state == TRAV && node >= 0);
+        do_leaf = static_cast<uint32_t>(__popc(lm)) >= p.leaf_min || im == 0u;
+      }
+      if (do_leaf && state == TRAV && node < 0) {
         const uint32_t v = static_cast<uint32_t>(~node);
         const uint32_t first = v >> 5, cnt = sc.leaf_direct ? 1u : (v & 31u);
         for (uint32_t k = 0; k < cnt; ++k) {
@@ -1302,6 +1309,9 @@ cudaError_t launch_render(const RenderParams& p_in, int mode, int rays_per_lane,
                           int* variant) {
   RenderParams p = p_in;
   if (variant) *variant = RTW_BVH_NONE;
+  // triangle leaves (a ~50-instruction test run by ~6 of 32 lanes when tested at once) are held back until 4 lanes stand on one;
+  // sphere leaves are tested at once (holding them back lost 3-8 % on the cover scene)
+  p.leaf_min = p.sc.n_tri > 0 ? 4u : 1u;
   p.so = smem_layout(p);
   const size_t smem = mode == 0 ? 16 + static_cast<size_t>(p.sc.n_static + p.sc.n_moving + 1) * 32 : 0;
   if (mode == 0) {
