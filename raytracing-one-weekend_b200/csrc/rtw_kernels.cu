@@ -1320,7 +1320,6 @@ cudaError_t launch_render(const RenderParams& p_in, int mode, int rays_per_lane,
     if (rays_per_lane == 4) return stats ? launch_sweep_t<4, true>(p, sm_count, smem, stream, nullptr) : launch_sweep_t<4, false>(p, sm_count, smem, stream, nullptr);
     return stats ? launch_sweep_t<2, true>(p, sm_count, smem, stream, nullptr) : launch_sweep_t<2, false>(p, sm_count, smem, stream, nullptr);
   }
-  // BVH kernel: 8 traversal steps between service checks, service once 24 lanes need it, 4 CTAs/SM (tuning record in DESIGN.md)
   const size_t bsm = bvh_smem_bytes(p);
   // sphere scenes whose tables leave room for the per-warp path records: wavefront-per-warp kernel, 28 warps per SM (72 registers),
   // 96 records per warp, 16 traversal steps between exchanges, shading batches of 32 (tuning record in DESIGN.md)
@@ -1332,11 +1331,11 @@ cudaError_t launch_render(const RenderParams& p_in, int mode, int rays_per_lane,
                  : launch_wf_t<true, false, kWfWarps, kWfRecords, 16, 32>(p, sm_count, wf_smem, stream);
   }
   if (variant) *variant = RTW_BVH_PERLANE;
-#define RTW_BVH(ST, SV, MB)                                                                                         \
-  return bsm ? (stats ? launch_bvh_t<true, true, ST, SV, MB>(p, sm_count, bsm, stream) : launch_bvh_t<true, false, ST, SV, MB>(p, sm_count, bsm, stream)) \
-             : (stats ? launch_bvh_t<false, true, ST, SV, MB>(p, sm_count, 0, stream) : launch_bvh_t<false, false, ST, SV, MB>(p, sm_count, 0, stream))
-  RTW_BVH(8, 24, 4);
-#undef RTW_BVH
+  // <steps per traversal phase, lanes that must need service before the service phase runs, CTAs per SM>: tables in shared memory
+  // (sphere scenes) 8 / 24; tables in L1/L2 (meshes) 4 / 20, measured on suzanne and the 991k-triangle mesh against (8,24):
+  // +2.8 % / +3.5 % (the whole (steps, threshold) landscape is within +-4 %: DESIGN.md)
+  if (bsm) return stats ? launch_bvh_t<true, true, 8, 24, 4>(p, sm_count, bsm, stream) : launch_bvh_t<true, false, 8, 24, 4>(p, sm_count, bsm, stream);
+  return stats ? launch_bvh_t<false, true, 4, 20, 4>(p, sm_count, 0, stream) : launch_bvh_t<false, false, 4, 20, 4>(p, sm_count, 0, stream);
 }
 
 cudaError_t launch_primary_f32(const PrimaryParams& p, int mode, cudaStream_t stream) {
