@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
         }
       }
       bool do_leaf = true;
-      if (p.leaf_min > 1u) {  // hold leaves back until enough lanes stand on one, or no lane has an inner node left to visit
+      if (!SMEM && p.leaf_min > 1u) {  // (tables in L1/L2 only) hold leaves back until enough lanes stand on one, or no lane has an inner node left to visit
         const uint32_t lm = __ballot_sync(0xffffffffu, state == TRAV && node < 0), im = __ballot_sync(0xffffffffu, state == TRAV && node >= 0);
         do_leaf = static_cast<uint32_t>(__popc(lm)) >= p.leaf_min || im == 0u;
       }
