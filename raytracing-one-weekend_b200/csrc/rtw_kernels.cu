@@ -1,16 +1,19 @@
 // rtw_kernels.cu -- sm_100a kernels of the B200 path tracer and their launchers.
 //
-//   Both render kernels are the per-pixel / per-sample loop of render.cpp:150-167 with ray_color (render.cpp:112-129) turned
+//   The three render kernels are the per-pixel / per-sample loop of render.cpp:150-167 with ray_color (render.cpp:112-129) turned
 //   into an iterative bounce loop.  Persistent warps pull units of (128 pixels x SU samples) from a global atomic counter; a
 //   finished path is replaced at once from the warp's pool (ballot + popc ranking).
-//   k_render_bvh (K2)   the default: SAH BVH (64-byte two-child nodes, single-primitive leaves), resumable per-lane
-//                       traversal, tables staged in shared memory with TMA bulk copies when they fit.
+//   k_render_wf (K2w)   sphere scenes whose tables leave room in shared memory: SAH BVH (64-byte two-child nodes, single-primitive
+//                       leaves), tables staged with TMA bulk copies, the warp's paths kept as records in shared memory, shading in
+//                       batches of 32 records of one kind ("wavefront per warp").
+//   k_render_bvh (K2)   meshes and big sphere scenes: the same tree walked by a resumable per-lane state machine, tables in
+//                       shared memory when they fit, else read through L1/L2 (nodes with two 256-bit loads).
 //   k_render_sweep<R> (K1)  small sphere scenes: the whole sphere table staged in shared memory (cp.async.bulk + mbarrier)
 //                       and swept brute force, R paths per lane: per (ray, sphere) 8 FMA for the line-distance reject test
 //                       (+3 for the centre lerp of moving spheres); survivors go through the exact reference-rule root selection.
 //   k_primary_f32       K3: deterministic primary hits through the SAME tracing routines (parity mode)
 //   k_primary_f64       K3 in double: reference formulas verbatim, brute force over the raw primitive list
-//   k_accum_to_float, k_finalize_rgb8   render.cpp:11-20,176-186 on the device
+//   k_accum_to_float, k_finalize_rgb8, k_untile   render.cpp:11-20,176-186 on the device; row-tile split reassembly
 //   k_debug_*, k_ffma_peak              unit hooks and the FP32 roofline denominator
 //
 // Radiance is accumulated as int64 fixed point (2^-32) with RED.ADD.64: integer sums are exact, so the image
