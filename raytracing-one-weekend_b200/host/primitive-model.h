@@ -1,8 +1,9 @@
 // primitive-model.h -- Sphere / MovingSphere / Triangle and their store.
 // One model instead of the reference's two interchangeable ones (oo-primitives.h, variant-primitives.h selected by
-// primitive-model.h:1-4): constructors and accessors match both (oo-primitives.h:28,49,76,37-43,60-67), the
-// store offers the same add<T>(args...) -> T&.  Primitives are plain records that know how to flatten themselves;
-// intersection and bounding boxes are computed on the device / in the BVH builder.
+// primitive-model.h:1-4): constructor signatures and accessor names match both (oo-primitives.h:28,49,76,37-43,60-67) and the
+// store offers the same add<T>(args...) -> T&.  A primitive here is nothing but its flat C-ABI record (rtw_primitive) plus the
+// material it points at: intersection and bounding boxes are computed on the device and in the BVH builder, so the host classes
+// only have to remember their constructor arguments in the form Scene::flatten() hands to rtw_render.
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -13,59 +14,54 @@ namespace rtweekend::detail {
 
 class Primitive {
  public:
-  explicit Primitive(const Material& m) : material_{&m} {}
   virtual ~Primitive() = default;
   [[nodiscard]] const Material& material() const { return *material_; }
-  // kind, geometry; the material index is filled in by Scene::flatten
-  [[nodiscard]] virtual rtw_primitive flat() const = 0;
+  // kind + geometry as the C ABI wants them; the material index is filled in by Scene::flatten
+  [[nodiscard]] const rtw_primitive& flat() const { return record_; }
+
+ protected:
+  Primitive(rtw_prim_kind kind, const Material& m) : material_{&m} { record_.kind = kind; }
+  static void store(double (&dst)[3], const point& p) { dst[0] = p.x; dst[1] = p.y; dst[2] = p.z; }
+  static point load(const double (&src)[3]) { return point{src[0], src[1], src[2]}; }
+  rtw_primitive record_{};
 
  private:
   const Material* material_;
 };
 
+// record_.a = record_.b = centre
 class Sphere final : public Primitive {
  public:
-  Sphere(point center, double radius, const Material& material) : Primitive{material}, center_{center}, radius_{radius} {}
-  [[nodiscard]] const point& center() const { return center_; }
-  [[nodiscard]] const double& radius() const { return radius_; }
-  [[nodiscard]] rtw_primitive flat() const override {
-    return {RTW_SPHERE, 0, {center_.x, center_.y, center_.z}, {center_.x, center_.y, center_.z}, {0, 0, 0}, radius_};
+  Sphere(point center, double radius, const Material& material) : Primitive{RTW_SPHERE, material} {
+    store(record_.a, center); store(record_.b, center); record_.radius = radius;
   }
-
- private:
-  point center_;
-  double radius_;
+  [[nodiscard]] point center() const { return load(record_.a); }
+  [[nodiscard]] double radius() const { return record_.radius; }
 };
 
+// record_.a = centre when the shutter opens (time 0), record_.b = centre when it closes (time 1), oo-primitives.h:51-52
 class MovingSphere final : public Primitive {
  public:
-  MovingSphere(point c0, point c1, double radius, const Material& material)
-      : Primitive{material}, center0_{c0}, center1_{c1}, radius_{radius} {}
-  [[nodiscard]] const point& center() const { return center0_; }
-  // shutter runs over [0,1] (oo-primitives.h:51-52)
-  [[nodiscard]] point center(time_t time) const { return center0_ + time * (center1_ - center0_); }
-  [[nodiscard]] const double& radius() const { return radius_; }
-  [[nodiscard]] rtw_primitive flat() const override {
-    return {RTW_MOVING_SPHERE, 0, {center0_.x, center0_.y, center0_.z}, {center1_.x, center1_.y, center1_.z}, {0, 0, 0}, radius_};
+  MovingSphere(point c0, point c1, double radius, const Material& material) : Primitive{RTW_MOVING_SPHERE, material} {
+    store(record_.a, c0); store(record_.b, c1); record_.radius = radius;
   }
-
- private:
-  point center0_, center1_;
-  double radius_;
+  [[nodiscard]] point center() const { return load(record_.a); }
+  [[nodiscard]] point center(time_t time) const {
+    const point from = load(record_.a), to = load(record_.b);
+    return from + time * (to - from);
+  }
+  [[nodiscard]] double radius() const { return record_.radius; }
 };
 
+// record_.a/b/c = the three vertices in the order given (the winding decides the culled side)
 class Triangle final : public Primitive {
  public:
-  Triangle(point a, point b, point c, const Material& material) : Primitive{material}, a_{a}, b_{b}, c_{c} {}
-  [[nodiscard]] const point& a() const { return a_; }
-  [[nodiscard]] const point& b() const { return b_; }
-  [[nodiscard]] const point& c() const { return c_; }
-  [[nodiscard]] rtw_primitive flat() const override {
-    return {RTW_TRIANGLE, 0, {a_.x, a_.y, a_.z}, {b_.x, b_.y, b_.z}, {c_.x, c_.y, c_.z}, 0.0};
+  Triangle(point a, point b, point c, const Material& material) : Primitive{RTW_TRIANGLE, material} {
+    store(record_.a, a); store(record_.b, b); store(record_.c, c);
   }
-
- private:
-  point a_, b_, c_;
+  [[nodiscard]] point a() const { return load(record_.a); }
+  [[nodiscard]] point b() const { return load(record_.b); }
+  [[nodiscard]] point c() const { return load(record_.c); }
 };
 
 }  // namespace rtweekend::detail
