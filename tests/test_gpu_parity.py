@@ -344,6 +344,31 @@ def test_full_size_properties_1080p(gpu):
     assert np.array_equal(gpu.finalize_rgb8(acc, spp), gpu.quantize(acc, spp))  # write_color on the device, in double: exact
 
 
+def test_full_size_properties_4k(gpu):
+    """BASELINE config 5 geometry (3840x2160) at 2 spp: 16.6 M paths, every pixel exactly spp paths, the packed row-tile
+    renders of 8 participants reassemble to the same buffer bit for bit."""
+    import torch
+    aspect = 1.7777777777777777
+    scene = gpu.cover_scene(11, aspect)
+    W, H, spp = 3840, 2160, 2
+    assert gpu.image_height(W, aspect) == H
+    ds = gpu.DeviceScene(scene, 0)
+    stream = torch.cuda.current_stream().cuda_stream
+    full = torch.zeros((H, W, 4), dtype=torch.int64, device="cuda:0")
+    st = ds.render_into(full, W, H, spp, 50, stream_ptr=stream, seed=9, want_stats=True)
+    assert st["paths"] == W * H * spp and bool((full[..., 3] == spp).all())
+    assert 2.25 < st["rays"] / st["paths"] < 2.45
+    lr = gpu.row_tile_local_rows(H, 8, 8)
+    gathered = torch.zeros((8, lr, W, 4), dtype=torch.int64, device="cuda:0")
+    for g in range(8):
+        ds.render_into(gathered[g], W, H, spp, 50, stream_ptr=stream, seed=9, row_tiles=(8, 8, g))
+    back = torch.zeros_like(full)
+    ds.untile(gathered, back, W, H, 8, 8, stream_ptr=stream)
+    torch.cuda.synchronize()
+    assert torch.equal(back, full)
+    ds.close()
+
+
 def test_edge_cases(gpu, port, oracle_mod):
     cam = dict(lookfrom=(0, 0, 0), lookat=(0, 0, -1), vup=(0, 1, 0), vfov=60.0, aspect=1.0, aperture=0.0, focus_dist=1.0, t0=0.0, t1=0.0)
     mats = np.zeros(1, gpu.MAT_DTYPE); mats["albedo"] = 0.5
