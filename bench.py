@@ -475,7 +475,8 @@ def main() -> int:
                                    else f"spp-shard x{world}, one int64 NCCL reduce"), "kernel": "spheres_smem (K1)" if kernel_used == rtw.KERNEL_SPHERES_SMEM else ("bvh wavefront (K2w)" if wavefront else "bvh per-lane (K2)"),
                    "l2": "256 MB buffer written between timed iterations (scene tables live in shared memory; accumulation buffer 66 MB)"},
         "mrays_per_s": rays_total / (ms_per_step * 1e-3) / 1e6, "rays_per_path": rays_total / paths_total,
-        "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks, "roofline": roofline, "roofline_issue": roofline_issue, "roofline_sphere_sweep": roofline_sweep,
+        "e2e": e2e, "gpu_launches": args.steps * (world + 1 + (1 if rows else 0)),  # per step: one render kernel per GPU + k_accum_to_float (+ k_untile) on rank 0
+         "clocks": clocks, "roofline": roofline, "roofline_issue": roofline_issue, "roofline_sphere_sweep": roofline_sweep,
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))
