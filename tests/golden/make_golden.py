@@ -80,10 +80,16 @@ def main():
     print("primary hits done")
 
     # 3. converged linear-domain statistics (mean and per-sample variance per pixel and channel)
-    for name, kind, w, h, spp, depth, aspect in [("cover_converged_120x80", "cover", 120, 80, 1024, 20, 1.5),
-                                                  ("cover_static_converged_96x54", "cover_static", 96, 54, 512, 50, 1.7777777777777777),
-                                                  ("suzanne_converged_96x64", "suzanne", 96, 64, 512, 20, 1.5)]:
+    converged_sets = [("cover_converged_120x80", "cover", 120, 80, 1024, 20, 1.5),
+                      ("cover_static_converged_96x54", "cover_static", 96, 54, 512, 50, 1.7777777777777777),
+                      ("suzanne_converged_96x64", "suzanne", 96, 64, 512, 20, 1.5),
+                      # BASELINE config 2's scene, camera and depth (cover, 16:9, depth 50, motion blur) at a fifth of its resolution
+                      # and its full 1024 spp: the largest reference render that stays a small fixture (variance stored as float16)
+                      ("cover_converged_384x216_depth50", "cover", 384, 216, 1024, 50, 1.7777777777777777)]
+    for name, kind, w, h, spp, depth, aspect in converged_sets:
         mean, var, n = converged(kind, w, h, spp, depth, aspect)
+        if w * h > 20000:
+            var = var.astype(np.float16)
         np.savez_compressed(OUT / f"{name}.npz", mean=mean, var=var,
                             meta=json.dumps({**meta_common, "scene": kind, "width": w, "height": h, "spp": n, "max_child_rays": depth,
                                              "aspect": aspect, "how": "8 single-threaded runs of render.cpp:152-163 with seeds 1000+7919*i, summed"}))

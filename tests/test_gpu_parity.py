@@ -283,6 +283,15 @@ def test_converged_cover_vs_reference(gpu, golden, kernel_name):
     converged_check(gpu, golden, "cover_converged_120x80.npz", gpu.cover_scene(), kernel)
 
 
+@pytest.mark.parametrize("kernel_name", ["spheres", "bvh", "bvh-perlane"])
+def test_converged_cover_config2_geometry_vs_reference(gpu, golden, kernel_name):
+    """BASELINE config 2's scene, camera and depth (cover, 16:9, depth 50, motion blur) against the reference's own 1024-spp
+    render at 384x216: PSNR >= 40 dB on the 8-bit image, image mean within 3 sigma, every kernel."""
+    kernel = {"spheres": gpu.KERNEL_SPHERES_SMEM, "bvh": gpu.KERNEL_BVH, "bvh-perlane": gpu.KERNEL_BVH_PERLANE}[kernel_name]
+    p = converged_check(gpu, golden, "cover_converged_384x216_depth50.npz", gpu.cover_scene(11, 1.7777777777777777), kernel)
+    assert p >= 42.0   # 4096 against 1024 samples: the noise floor of the 1024-spp reference alone is ~46 dB (SURVEY section 6)
+
+
 def test_converged_static_cover_16x9_depth50_vs_reference(gpu, golden):
     converged_check(gpu, golden, "cover_static_converged_96x54.npz", gpu.cover_scene(11, 1.7777777777777777, False), gpu.KERNEL_AUTO)
 
