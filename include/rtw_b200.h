@@ -36,7 +36,8 @@ extern "C" {
 
 enum rtw_prim_kind { RTW_SPHERE = 0, RTW_MOVING_SPHERE = 1, RTW_TRIANGLE = 2 };
 enum rtw_mat_kind { RTW_LAMBERTIAN = 0, RTW_METAL = 1, RTW_DIELECTRIC = 2 };
-/* AUTO: sphere sweep for tiny sphere scenes, else BVH.  BVH picks between its two kernels: the wavefront-per-warp kernel when the
+/* AUTO = BVH (the faster choice at every scene size measured).  SPHERES_SMEM: the brute-force shared-memory sphere sweep, the kernel
+ * the FP32-FMA roofline is defined on (sphere-only scenes whose tables fit in shared memory).  BVH picks between its two kernels: the wavefront-per-warp kernel when the
  * scene tables and the per-warp path records fit in shared memory (sphere scenes up to ~900 spheres), else the per-lane state
  * machine (meshes, large scenes).  BVH_PERLANE forces the latter (A/B measurements). */
 enum rtw_kernel { RTW_KERNEL_AUTO = 0, RTW_KERNEL_SPHERES_SMEM = 1, RTW_KERNEL_BVH = 2, RTW_KERNEL_BVH_PERLANE = 3 };

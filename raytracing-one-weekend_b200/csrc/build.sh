@@ -16,5 +16,5 @@ $NVCC $FLAGS ${RTW_PTXAS_V:+-Xptxas -v} -c rtw_kernels.cu -o ../build/rtw_kernel
 $NVCC $FLAGS -c rtw_abi.cu -o ../build/rtw_abi.o & p2=$!
 $NVCC $FLAGS -c rtw_multi.cu -o ../build/rtw_multi.o & p3=$!
 wait $p1; wait $p2; wait $p3   # each wait returns that compiler's status; set -e stops on the first failure
-$NVCC -shared -o $OUT ../build/rtw_kernels.o ../build/rtw_abi.o ../build/rtw_multi.o -lcudart_static -ldl -lpthread -lrt
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT ../build/rtw_kernels.o ../build/rtw_abi.o ../build/rtw_multi.o -lcudart_static -ldl -lpthread -lrt
 echo "built $OUT"

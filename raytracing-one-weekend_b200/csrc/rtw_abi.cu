@@ -325,20 +325,20 @@ int flatten_and_upload(const rtw_scene_desc* desc, int device, rtw_scene* sc, De
   return 0;
 }
 
-// Which kernel a scene gets.  The shared-memory sphere sweep (K1) needs a sphere-only scene whose tables fit in shared
-// memory; it is the faster kernel only for small tables (its cost is linear in the sphere count, the BVH's is
-// logarithmic: measured crossover well below the cover scene's 484 spheres), so AUTO picks it up to kSweepAutoMax.
-constexpr size_t kSweepAutoMax = 64;
+// Which kernel a scene gets.  AUTO is always a BVH kernel: since the wavefront kernel (K2w) it is the faster one at every table
+// size (1080p, 64 spp, Mpaths/s, K1 vs K2w: 8 primitives 11 803 / 15 088, 20: 10 042 / 14 068, 40: 8 077 / 13 398, 66: 6 111 / 11 680,
+// 145: 3 870 / 9 504; scripts/kernel_crossover.py).  The shared-memory sphere sweep (K1) stays available on request
+// (RTW_KERNEL_SPHERES_SMEM) as the kernel the FP32-FMA roofline of SURVEY 8(d) is defined on; it needs a sphere-only scene
+// whose tables fit in shared memory.
 int choose_mode(const rtw_scene* sc, int requested, int* mode) {
   const bool smem_ok = !sc->has_triangles && sc->smem_bytes <= 100 * 1024;
-  const size_t nspheres = static_cast<size_t>(sc->dev.n_static + sc->dev.n_moving);
   if (requested == RTW_KERNEL_SPHERES_SMEM) {
     if (!smem_ok) return fail("RTW_KERNEL_SPHERES_SMEM needs a sphere-only scene whose tables fit in shared memory");
     *mode = 0;
   } else if (requested == RTW_KERNEL_BVH || requested == RTW_KERNEL_BVH_PERLANE) {
     *mode = 1;
   } else if (requested == RTW_KERNEL_AUTO) {
-    *mode = (smem_ok && nspheres <= kSweepAutoMax) ? 0 : 1;
+    *mode = 1;
   } else {
     return fail("unknown kernel selector");
   }
