@@ -1324,14 +1324,25 @@ cudaError_t launch_render(const RenderParams& p_in, int mode, int rays_per_lane,
     return stats ? launch_sweep_t<2, true>(p, sm_count, smem, stream, nullptr) : launch_sweep_t<2, false>(p, sm_count, smem, stream, nullptr);
   }
   const size_t bsm = bvh_smem_bytes(p);
-  // sphere scenes whose tables leave room for the per-warp path records: wavefront-per-warp kernel, 28 warps per SM (72 registers),
-  // 96 records per warp, 16 traversal steps between exchanges, shading batches of 32 (tuning record in DESIGN.md)
-  constexpr int kWfWarps = 28, kWfRecords = 96;
-  const size_t wf_smem = p.so.records + static_cast<size_t>(kWfWarps) * wf_warp_bytes(kWfRecords);
-  if (bsm && p.sc.leaf_direct && wf_smem <= 227u * 1024u && !force_perlane) {
-    if (variant) *variant = RTW_BVH_WAVEFRONT;
-    return stats ? launch_wf_t<true, true, kWfWarps, kWfRecords, 16, 32>(p, sm_count, wf_smem, stream)
-                 : launch_wf_t<true, false, kWfWarps, kWfRecords, 16, 32>(p, sm_count, wf_smem, stream);
+  // scenes whose tables leave room for the per-warp path records: wavefront-per-warp kernel, 28 warps per SM (72 registers),
+  // 96 records per warp, 16 traversal steps between exchanges, shading batches of 32 (tuning record in DESIGN.md).  Bigger sphere
+  // tables trade warps for table space: 24 warps up to ~87 KB of tables, 20 warps up to ~111 KB (cover scene with -n 13..17, 678 to
+  // 1159 spheres: +12..29 % over the per-lane kernel; 16 warps at 1296 spheres: -2 %, not instantiated).
+  constexpr int kWfRecords = 96;
+  constexpr size_t kSmemCap = 227u * 1024u;
+  const size_t wf_warp = wf_warp_bytes(kWfRecords);
+  if (p.sc.leaf_direct && !force_perlane) {
+#define RTW_WF_LAUNCH(NW)                                                                                             \
+  {                                                                                                                   \
+    if (variant) *variant = RTW_BVH_WAVEFRONT;                                                                        \
+    const size_t smem = p.so.records + static_cast<size_t>(NW) * wf_warp;                                             \
+    return stats ? launch_wf_t<true, true, NW, kWfRecords, 16, 32>(p, sm_count, smem, stream)                         \
+                 : launch_wf_t<true, false, NW, kWfRecords, 16, 32>(p, sm_count, smem, stream);                       \
+  }
+    if (p.so.records + 28 * wf_warp <= kSmemCap) RTW_WF_LAUNCH(28)
+    if (p.sc.n_tri == 0 && p.so.records + 24 * wf_warp <= kSmemCap) RTW_WF_LAUNCH(24)
+    if (p.sc.n_tri == 0 && p.so.records + 20 * wf_warp <= kSmemCap) RTW_WF_LAUNCH(20)
+#undef RTW_WF_LAUNCH
   }
   if (variant) *variant = RTW_BVH_PERLANE;
   // <steps per traversal phase, lanes that must need service before the service phase runs, CTAs per SM>: tables in shared memory

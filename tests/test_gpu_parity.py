@@ -548,10 +548,11 @@ def test_large_sphere_grids(gpu, port, nsqrt):
         gpu.render(scene, 16, 16, 1, kernel=gpu.KERNEL_SPHERES_SMEM) if nsqrt == 120 else (_ for _ in ()).throw(gpu.RtwError("shared memory"))
 
 
-@pytest.mark.parametrize("nsqrt,variant", [(1, "wavefront"), (5, "wavefront"), (12, "wavefront"), (13, "perlane"), (15, "perlane")])
+@pytest.mark.parametrize("nsqrt,variant", [(1, "wavefront"), (5, "wavefront"), (12, "wavefront"), (13, "wavefront"), (17, "wavefront"), (18, "perlane")])
 def test_bvh_kernel_crossover_by_table_size(gpu, port, nsqrt, variant):
     """KERNEL_BVH picks the wavefront-per-warp kernel while the scene tables leave room for the per-warp path records in shared
-    memory (about 600 spheres), the per-lane kernel beyond; both sides of the crossover trace the oracle's paths on the same stream."""
+    memory (28 warps per SM up to ~600 spheres, 24 up to ~900, 20 up to ~1150), the per-lane kernel beyond; every tier and both
+    sides of the crossover trace the oracle's paths on the same stream."""
     scene, osc = gpu.cover_scene(nsqrt), port.scene_cover(nsqrt)
     acc, st = same_stream_check(gpu, port, scene, osc, 120, 80, 8, 20, seed=nsqrt, kernel=gpu.KERNEL_BVH, frac_tol=0.015)
     assert st["kernel_used"] == gpu.KERNEL_BVH
