@@ -38,8 +38,8 @@ enum rtw_prim_kind { RTW_SPHERE = 0, RTW_MOVING_SPHERE = 1, RTW_TRIANGLE = 2 };
 enum rtw_mat_kind { RTW_LAMBERTIAN = 0, RTW_METAL = 1, RTW_DIELECTRIC = 2 };
 /* AUTO = BVH (the faster choice at every scene size measured).  SPHERES_SMEM: the brute-force shared-memory sphere sweep, the kernel
  * the FP32-FMA roofline is defined on (sphere-only scenes whose tables fit in shared memory).  BVH picks between its two kernels: the wavefront-per-warp kernel when the
- * scene tables and the per-warp path records fit in shared memory (sphere scenes up to ~900 spheres), else the per-lane state
- * machine (meshes, large scenes).  BVH_PERLANE forces the latter (A/B measurements). */
+ * scene tables and the per-warp path records fit in shared memory (up to ~1150 spheres) and for every larger sphere-only scene,
+ * the per-lane state machine for meshes.  BVH_PERLANE forces the latter (A/B measurements). */
 enum rtw_kernel { RTW_KERNEL_AUTO = 0, RTW_KERNEL_SPHERES_SMEM = 1, RTW_KERNEL_BVH = 2, RTW_KERNEL_BVH_PERLANE = 3 };
 enum rtw_bvh_variant { RTW_BVH_NONE = 0, RTW_BVH_PERLANE = 1, RTW_BVH_WAVEFRONT = 2 };
 enum rtw_flags { RTW_FLAG_STATS = 1, RTW_FLAG_SPLIT_ROWS = 2 };

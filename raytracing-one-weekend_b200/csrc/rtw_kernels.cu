@@ -749,8 +749,8 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
 constexpr int kFresh = -2;   // record holds no path yet
 constexpr int kEnded = -3;   // path ended without a sky term (depth cut / absorbed)
 
-template <bool SMEM, bool STATS, int NW, int P, int STEPS, int BATCH>
-__global__ void __launch_bounds__(NW * 32, 1) k_render_wf(const __grid_constant__ RenderParams p) {
+template <bool SMEM, bool STATS, int NW, int P, int STEPS, int BATCH, int MINB = 1>
+__global__ void __launch_bounds__(NW * 32, MINB) k_render_wf(const __grid_constant__ RenderParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const DevScene& sc = p.sc;
   BvhTables tb{sc.nodes, sc.leafRefs, sc.sphA, sc.sphB, sc.tri};
@@ -1273,9 +1273,9 @@ static cudaError_t launch_bvh_t(const RenderParams& p, int sm_count, size_t smem
   return cudaGetLastError();
 }
 
-template <bool SMEM, bool STATS, int NW, int P, int STEPS, int BATCH>
+template <bool SMEM, bool STATS, int NW, int P, int STEPS, int BATCH, int MINB = 1>
 static cudaError_t launch_wf_t(const RenderParams& p, int sm_count, size_t smem, cudaStream_t stream) {
-  auto kern = k_render_wf<SMEM, STATS, NW, P, STEPS, BATCH>;
+  auto kern = k_render_wf<SMEM, STATS, NW, P, STEPS, BATCH, MINB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
   int per_sm = 0;
@@ -1343,6 +1343,17 @@ cudaError_t launch_render(const RenderParams& p_in, int mode, int rays_per_lane,
     if (p.sc.n_tri == 0 && p.so.records + 24 * wf_warp <= kSmemCap) RTW_WF_LAUNCH(24)
     if (p.sc.n_tri == 0 && p.so.records + 20 * wf_warp <= kSmemCap) RTW_WF_LAUNCH(20)
 #undef RTW_WF_LAUNCH
+    // sphere scenes too big for shared memory: the same kernel with the tables read through L1/L2, three 256-thread CTAs per SM
+    // (80 registers).  -n 40 (6 402 spheres): 4 284 against 3 912 Mpaths/s for the per-lane kernel, -n 120 (57 603): 3 307 against 3 267.
+    // Not for meshes: on the 991k-triangle mesh it loses 10-15 %.
+    if (p.sc.n_tri == 0) {
+      if (variant) *variant = RTW_BVH_WAVEFRONT;
+      RenderParams q = p;
+      q.so.records = 16u;
+      const size_t smem = 16 + 8 * wf_warp;
+      return stats ? launch_wf_t<false, true, 8, kWfRecords, 16, 32, 3>(q, sm_count, smem, stream)
+                   : launch_wf_t<false, false, 8, kWfRecords, 16, 32, 3>(q, sm_count, smem, stream);
+    }
   }
   if (variant) *variant = RTW_BVH_PERLANE;
   // <steps per traversal phase, lanes that must need service before the service phase runs, CTAs per SM>: tables in shared memory

@@ -521,7 +521,7 @@ def test_high_poly_stand_in_mesh(gpu, port, oracle_mod, tmp_path):
     check_primary(gpu.primary_hits(scene, W, H, 0.0, 32), want, fp64=False, unit_normals=False, max_knife_edge=3)
     acc, st = gpu.render(scene, 64, 36, 4, 20, seed=6, stats=True)
     ref, _, rays = port.render_philox(osc, 64, 36, 0, 4, 20, seed=6, nthreads=8)
-    assert st["kernel_used"] == gpu.KERNEL_BVH and st["tri_tests"] > 0
+    assert st["kernel_used"] == gpu.KERNEL_BVH and st["bvh_variant"] == gpu.BVH_PERLANE and st["tri_tests"] > 0   # meshes: per-lane kernel
     got = acc[..., :3].astype(np.float64) / 4
     assert (np.abs(got - ref / 4).max(axis=2) > 1e-3).mean() < 0.03
     assert abs(st["rays"] - rays) / rays < 0.01
@@ -548,11 +548,12 @@ def test_large_sphere_grids(gpu, port, nsqrt):
         gpu.render(scene, 16, 16, 1, kernel=gpu.KERNEL_SPHERES_SMEM) if nsqrt == 120 else (_ for _ in ()).throw(gpu.RtwError("shared memory"))
 
 
-@pytest.mark.parametrize("nsqrt,variant", [(1, "wavefront"), (5, "wavefront"), (12, "wavefront"), (13, "wavefront"), (17, "wavefront"), (18, "perlane")])
+@pytest.mark.parametrize("nsqrt,variant", [(1, "wavefront"), (5, "wavefront"), (12, "wavefront"), (13, "wavefront"), (17, "wavefront"), (18, "wavefront")])
 def test_bvh_kernel_crossover_by_table_size(gpu, port, nsqrt, variant):
     """KERNEL_BVH picks the wavefront-per-warp kernel while the scene tables leave room for the per-warp path records in shared
-    memory (28 warps per SM up to ~600 spheres, 24 up to ~900, 20 up to ~1150), the per-lane kernel beyond; every tier and both
-    sides of the crossover trace the oracle's paths on the same stream."""
+    memory (28 warps per SM up to ~600 spheres, 24 up to ~900, 20 up to ~1150) and, for sphere-only scenes beyond that, the same
+    kernel with the tables read through L1/L2; every tier traces the oracle's paths on the same stream, and so does the per-lane
+    kernel when forced."""
     scene, osc = gpu.cover_scene(nsqrt), port.scene_cover(nsqrt)
     acc, st = same_stream_check(gpu, port, scene, osc, 120, 80, 8, 20, seed=nsqrt, kernel=gpu.KERNEL_BVH, frac_tol=0.015)
     assert st["kernel_used"] == gpu.KERNEL_BVH
