@@ -60,11 +60,11 @@ def build_scene(rtw, name, wl):
 #   tinst_per_ray = smsp__inst_executed.sum x smsp__thread_inst_executed_per_inst_executed.ratio / rays of that launch: the thread
 #             instructions one ray costs, the numerator of the instruction-issue roofline below.
 NCU = {
-    ("cover", "wf"): {"traffic": 66.86e6 + 15.94e6, "tinst_per_ray": 1412.0, "lanes_per_inst": 23.89, "issue_active_pct": 79.0, "file": "profiles/r01_prof_k2w.txt"},
-    ("cover", "perlane"): {"traffic": 66.47e6 + 16.61e6, "tinst_per_ray": 1452.0, "lanes_per_inst": 19.32, "issue_active_pct": 82.4, "file": "profiles/r01_prof_k2_perlane.txt"},
-    ("cover", "sweep"): {"traffic": 66.45e6 + 17.25e6, "tinst_per_ray": 7475.0, "lanes_per_inst": 29.72, "issue_active_pct": 79.2, "file": "profiles/r01_prof_k1.txt"},
-    ("dragon", "perlane"): {"traffic": 288.23e6 + 69.51e6, "tinst_per_ray": 1963.0, "lanes_per_inst": 16.20, "issue_active_pct": 61.3, "file": "profiles/r01_prof_k2_dragon.txt"},
-    ("suzanne", "perlane"): {"traffic": 66.52e6 + 17.08e6, "tinst_per_ray": 1256.0, "lanes_per_inst": 17.96, "issue_active_pct": 80.0, "file": "profiles/r01_prof_k2_suzanne.txt"},
+    ("cover", "wf"): {"traffic": 66.91e6 + 16.12e6, "tinst_per_ray": 1380.0, "lanes_per_inst": 23.92, "issue_active_pct": 79.0, "file": "profiles/r01_prof_k2w.txt"},
+    ("cover", "perlane"): {"traffic": 66.47e6 + 15.72e6, "tinst_per_ray": 1337.0, "lanes_per_inst": 18.81, "issue_active_pct": 82.4, "file": "profiles/r01_prof_k2_perlane.txt"},
+    ("cover", "sweep"): {"traffic": 66.45e6 + 17.22e6, "tinst_per_ray": 7476.0, "lanes_per_inst": 29.72, "issue_active_pct": 79.3, "file": "profiles/r01_prof_k1.txt"},
+    ("dragon", "perlane"): {"traffic": 287.96e6 + 72.64e6, "tinst_per_ray": 1960.0, "lanes_per_inst": 16.21, "issue_active_pct": 61.4, "file": "profiles/r01_prof_k2_dragon.txt"},
+    ("suzanne", "perlane"): {"traffic": 66.51e6 + 18.65e6, "tinst_per_ray": 1253.0, "lanes_per_inst": 17.98, "issue_active_pct": 80.0, "file": "profiles/r01_prof_k2_suzanne.txt"},
 }
 # canonical FP32 flop costs of SURVEY.md 8(d) (FMA = 2)
 FLOP_STATIC_TEST, FLOP_MOVING_TEST, FLOP_HIT, FLOP_SHADE = 17.0, 23.0, 40.0, 80.0
