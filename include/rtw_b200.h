@@ -175,6 +175,10 @@ typedef struct rtw_flatten_report {
   int32_t n_bvh_nodes, bvh_max_depth, leaf_direct, reserved;
   int64_t arena_bytes, bvh_errors; /* bvh_errors: primitives missing from / duplicated in the tree (must be 0) */
   double flatten_ms, bvh_build_ms;
+  /* the kernel RTW_KERNEL_BVH / AUTO would launch for this scene: rtw_bvh_variant, warps per CTA, whether the scene tables are
+   * staged in shared memory, and the dynamic shared memory of the launch */
+  int32_t bvh_variant, bvh_warps_per_cta, bvh_tables_in_smem, reserved2;
+  int64_t bvh_smem_bytes;
 } rtw_flatten_report;
 RTW_API int rtw_flatten_info(const rtw_scene_desc* desc, rtw_flatten_report* out);
 

@@ -71,7 +71,9 @@ class RenderCfg(C.Structure):
 class FlattenReport(C.Structure):
     _fields_ = [("n_static_spheres", C.c_int32), ("n_moving_spheres", C.c_int32), ("n_big_spheres", C.c_int32), ("n_triangles", C.c_int32),
                 ("n_bvh_nodes", C.c_int32), ("bvh_max_depth", C.c_int32), ("leaf_direct", C.c_int32), ("reserved", C.c_int32),
-                ("arena_bytes", C.c_int64), ("bvh_errors", C.c_int64), ("flatten_ms", C.c_double), ("bvh_build_ms", C.c_double)]
+                ("arena_bytes", C.c_int64), ("bvh_errors", C.c_int64), ("flatten_ms", C.c_double), ("bvh_build_ms", C.c_double),
+                ("bvh_variant", C.c_int32), ("bvh_warps_per_cta", C.c_int32), ("bvh_tables_in_smem", C.c_int32), ("reserved2", C.c_int32),
+                ("bvh_smem_bytes", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

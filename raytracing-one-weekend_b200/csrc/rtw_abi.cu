@@ -411,6 +411,13 @@ int rtw_flatten_info(const rtw_scene_desc* desc, rtw_flatten_report* out) {
   out->n_static_spheres = hf.n_static; out->n_moving_spheres = hf.n_moving; out->n_big_spheres = hf.n_big; out->n_triangles = hf.n_tri;
   out->n_bvh_nodes = hf.n_nodes; out->leaf_direct = hf.leaf_direct; out->arena_bytes = static_cast<int64_t>(hf.bytes);
   out->flatten_ms = now_ms() - t0; out->bvh_build_ms = hf.bvh_ms;
+  {
+    const size_t tables = 16 + static_cast<size_t>(hf.n_nodes) * 64 + ((hf.n_leaf_refs * 4 + 15) & ~size_t(15)) +
+                          static_cast<size_t>(hf.n_static + hf.n_moving) * 32 + static_cast<size_t>(hf.n_tri) * 48;
+    const rtw::BvhPlan plan = rtw::plan_bvh(tables, hf.n_tri, hf.leaf_direct != 0, false);
+    out->bvh_variant = plan.variant; out->bvh_warps_per_cta = plan.warps; out->bvh_tables_in_smem = plan.tables_in_smem ? 1 : 0;
+    out->reserved2 = 0; out->bvh_smem_bytes = static_cast<int64_t>(plan.smem_bytes);
+  }
   // structural self-check of the tree: every primitive referenced exactly once, child boxes inside the parent box
   const rtw::PackedNode* nodes = reinterpret_cast<const rtw::PackedNode*>(hf.host.get() + hf.o_nodes);
   const uint32_t* refs = reinterpret_cast<const uint32_t*>(hf.host.get() + hf.o_refs);

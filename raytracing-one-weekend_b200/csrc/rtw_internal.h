@@ -49,6 +49,38 @@ struct PrimaryParams {
   uint8_t* front;
 };
 
+// Which BVH kernel a scene gets (pure host logic, also reported by rtw_flatten_info so that it can be tested without a GPU).
+//   table_bytes: 16 + nodes + leaf refs + sphere tables + triangles, the shared-memory footprint of the staged tables.
+// Wavefront-per-warp kernel (K2w) while the tables leave room for the per-warp path records: 28 warps per SM (72 registers) up to
+// ~58 KB of tables, and for sphere-only scenes 24 warps up to ~87 KB and 20 warps up to ~111 KB (cover scene with -n 13..17, 678 to
+// 1159 spheres: +12..29 % over the per-lane kernel; 16 warps at 1296 spheres: -2 %, not instantiated).  Sphere-only scenes beyond
+// that: the same kernel with the tables read through L1/L2, three 256-thread CTAs per SM (-n 40, 6 402 spheres: 4 284 against 3 912
+// Mpaths/s; -n 120, 57 603 spheres: 3 307 against 3 267).  Meshes beyond the 28-warp tier, multi-primitive leaves, or on request:
+// the per-lane state machine (K2), its tables in shared memory up to 72 KB.
+constexpr int kWfRecords = 96;                      // path records per warp of K2w
+constexpr size_t kSmemCap = 227u * 1024u;           // dynamic shared memory one CTA may ask for on sm_100
+constexpr size_t kPerLaneSmemTables = 72u * 1024u;  // K2 stages its tables in shared memory up to this size (4 CTAs per SM for the cover scene)
+__host__ __device__ constexpr uint32_t wf_warp_bytes(int P) { return static_cast<uint32_t>((P * (48 + 8 + 4) + 3 * P + 15) & ~15); }
+struct BvhPlan {
+  int variant;          // rtw_bvh_variant
+  int warps;            // warps per CTA (K2w: one CTA per SM when the tables are in shared memory, three otherwise; K2: 8, four CTAs)
+  bool tables_in_smem;
+  size_t smem_bytes;    // dynamic shared memory of the launch
+};
+inline BvhPlan plan_bvh(size_t table_bytes, int n_tri, bool leaf_direct, bool force_perlane) {
+  const size_t wf_warp = wf_warp_bytes(kWfRecords);
+  if (leaf_direct && !force_perlane) {
+    if (table_bytes + 28 * wf_warp <= kSmemCap) return {RTW_BVH_WAVEFRONT, 28, true, table_bytes + 28 * wf_warp};
+    if (n_tri == 0) {
+      if (table_bytes + 24 * wf_warp <= kSmemCap) return {RTW_BVH_WAVEFRONT, 24, true, table_bytes + 24 * wf_warp};
+      if (table_bytes + 20 * wf_warp <= kSmemCap) return {RTW_BVH_WAVEFRONT, 20, true, table_bytes + 20 * wf_warp};
+      return {RTW_BVH_WAVEFRONT, 8, false, 16 + 8 * wf_warp};
+    }
+  }
+  if (table_bytes <= kPerLaneSmemTables) return {RTW_BVH_PERLANE, 8, true, table_bytes};
+  return {RTW_BVH_PERLANE, 8, false, 0};
+}
+
 // mode 0: sphere sweep (rays_per_lane 1/2/4); mode 1: BVH (force_perlane: never the wavefront kernel).  *variant <- rtw_bvh_variant launched.
 cudaError_t launch_render(const RenderParams& p, int mode, int rays_per_lane, bool force_perlane, bool stats, int sm_count, cudaStream_t stream,
                           int* variant);

@@ -486,8 +486,6 @@ __global__ void __launch_bounds__(kRenderThreads, (R >= 4 ? 2 : (R == 2 ? 3 : 4)
 //   this kernel at 15 of 32 active lanes per instruction.  With SMEM the nodes, leaf references, sphere tables and
 //   triangles are staged into shared memory with TMA bulk copies when they fit.
 // ---------------------------------------------------------------------------------------------------------
-__host__ __device__ constexpr uint32_t wf_warp_bytes(int P) { return static_cast<uint32_t>((P * (48 + 8 + 4) + 3 * P + 15) & ~15); }
-
 struct BvhTables {
   const float4* nodes;
   const uint32_t* leafRefs;
@@ -1289,14 +1287,6 @@ static cudaError_t launch_wf_t(const RenderParams& p, int sm_count, size_t smem,
   return cudaGetLastError();
 }
 
-// bytes of shared memory the BVH kernel needs to stage the whole scene (0 = does not fit, use global memory)
-size_t bvh_smem_bytes(const RenderParams& p) {
-  const size_t nspheres = static_cast<size_t>(p.sc.n_static + p.sc.n_moving);
-  const size_t bytes = 16 + static_cast<size_t>(p.sc.n_nodes) * 64 + ((static_cast<size_t>(p.n_leaf_refs) * 4 + 15) & ~size_t(15)) + nspheres * 32 +
-                       static_cast<size_t>(p.sc.n_tri) * 48;
-  return bytes <= 72 * 1024 ? bytes : 0;
-}
-
 // shared-memory layout of the staged BVH tables: [16 B mbarrier][nodes][leaf refs][sphA][sphB][triangles][per-warp records]
 static SmemLayout smem_layout(const RenderParams& p) {
   SmemLayout so{};
@@ -1323,43 +1313,29 @@ cudaError_t launch_render(const RenderParams& p_in, int mode, int rays_per_lane,
     if (rays_per_lane == 4) return stats ? launch_sweep_t<4, true>(p, sm_count, smem, stream, nullptr) : launch_sweep_t<4, false>(p, sm_count, smem, stream, nullptr);
     return stats ? launch_sweep_t<2, true>(p, sm_count, smem, stream, nullptr) : launch_sweep_t<2, false>(p, sm_count, smem, stream, nullptr);
   }
-  const size_t bsm = bvh_smem_bytes(p);
-  // scenes whose tables leave room for the per-warp path records: wavefront-per-warp kernel, 28 warps per SM (72 registers),
-  // 96 records per warp, 16 traversal steps between exchanges, shading batches of 32 (tuning record in DESIGN.md).  Bigger sphere
-  // tables trade warps for table space: 24 warps up to ~87 KB of tables, 20 warps up to ~111 KB (cover scene with -n 13..17, 678 to
-  // 1159 spheres: +12..29 % over the per-lane kernel; 16 warps at 1296 spheres: -2 %, not instantiated).
-  constexpr int kWfRecords = 96;
-  constexpr size_t kSmemCap = 227u * 1024u;
-  const size_t wf_warp = wf_warp_bytes(kWfRecords);
-  if (p.sc.leaf_direct && !force_perlane) {
-#define RTW_WF_LAUNCH(NW)                                                                                             \
-  {                                                                                                                   \
-    if (variant) *variant = RTW_BVH_WAVEFRONT;                                                                        \
-    const size_t smem = p.so.records + static_cast<size_t>(NW) * wf_warp;                                             \
-    return stats ? launch_wf_t<true, true, NW, kWfRecords, 16, 32>(p, sm_count, smem, stream)                         \
-                 : launch_wf_t<true, false, NW, kWfRecords, 16, 32>(p, sm_count, smem, stream);                       \
-  }
-    if (p.so.records + 28 * wf_warp <= kSmemCap) RTW_WF_LAUNCH(28)
-    if (p.sc.n_tri == 0 && p.so.records + 24 * wf_warp <= kSmemCap) RTW_WF_LAUNCH(24)
-    if (p.sc.n_tri == 0 && p.so.records + 20 * wf_warp <= kSmemCap) RTW_WF_LAUNCH(20)
-#undef RTW_WF_LAUNCH
-    // sphere scenes too big for shared memory: the same kernel with the tables read through L1/L2, three 256-thread CTAs per SM
-    // (80 registers).  -n 40 (6 402 spheres): 4 284 against 3 912 Mpaths/s for the per-lane kernel, -n 120 (57 603): 3 307 against 3 267.
-    // Not for meshes: on the 991k-triangle mesh it loses 10-15 %.
-    if (p.sc.n_tri == 0) {
-      if (variant) *variant = RTW_BVH_WAVEFRONT;
-      RenderParams q = p;
-      q.so.records = 16u;
-      const size_t smem = 16 + 8 * wf_warp;
-      return stats ? launch_wf_t<false, true, 8, kWfRecords, 16, 32, 3>(q, sm_count, smem, stream)
-                   : launch_wf_t<false, false, 8, kWfRecords, 16, 32, 3>(q, sm_count, smem, stream);
+  const BvhPlan plan = plan_bvh(p.so.records, p.sc.n_tri, p.sc.leaf_direct != 0, force_perlane);   // rtw_internal.h: who gets which kernel
+  if (variant) *variant = plan.variant;
+  if (plan.variant == RTW_BVH_WAVEFRONT) {
+    // 96 records per warp, 16 traversal steps between exchanges, shading batches of 32 (tuning record in DESIGN.md)
+#define RTW_WF_LAUNCH(SM, NW, MINB)                                                                                          \
+  return stats ? launch_wf_t<SM, true, NW, kWfRecords, 16, 32, MINB>(p, sm_count, plan.smem_bytes, stream)                   \
+               : launch_wf_t<SM, false, NW, kWfRecords, 16, 32, MINB>(p, sm_count, plan.smem_bytes, stream)
+    if (!plan.tables_in_smem) {
+      p.so.records = 16u;   // no staged tables in front of the records
+      RTW_WF_LAUNCH(false, 8, 3);
     }
+    switch (plan.warps) {
+      case 28: RTW_WF_LAUNCH(true, 28, 1);
+      case 24: RTW_WF_LAUNCH(true, 24, 1);
+      default: RTW_WF_LAUNCH(true, 20, 1);
+    }
+#undef RTW_WF_LAUNCH
   }
-  if (variant) *variant = RTW_BVH_PERLANE;
   // <steps per traversal phase, lanes that must need service before the service phase runs, CTAs per SM>: tables in shared memory
   // (sphere scenes) 8 / 24; tables in L1/L2 (meshes) 4 / 20, measured on suzanne and the 991k-triangle mesh against (8,24):
   // +2.8 % / +3.5 % (the whole (steps, threshold) landscape is within +-4 %: DESIGN.md)
-  if (bsm) return stats ? launch_bvh_t<true, true, 8, 24, 4>(p, sm_count, bsm, stream) : launch_bvh_t<true, false, 8, 24, 4>(p, sm_count, bsm, stream);
+  if (plan.tables_in_smem)
+    return stats ? launch_bvh_t<true, true, 8, 24, 4>(p, sm_count, plan.smem_bytes, stream) : launch_bvh_t<true, false, 8, 24, 4>(p, sm_count, plan.smem_bytes, stream);
   return stats ? launch_bvh_t<false, true, 4, 20, 4>(p, sm_count, 0, stream) : launch_bvh_t<false, false, 4, 20, 4>(p, sm_count, 0, stream);
 }
 

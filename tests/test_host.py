@@ -184,6 +184,29 @@ def test_sample_shard(rtw):
         rtw.sample_shard(20, 0, 8)
 
 
+def test_bvh_kernel_plan(rtw):
+    """Which BVH kernel a scene gets is host logic (plan_bvh, csrc/rtw_internal.h), reported by rtw_flatten_info: the wavefront
+    kernel with 28 / 24 / 20 warps per SM while tables + path records fit in the 227 KB of shared memory, the same kernel with the
+    tables in L1/L2 for bigger sphere scenes, the per-lane kernel for meshes."""
+    def plan(scene):
+        r = rtw.flatten_info(scene)
+        return r["bvh_variant"], r["bvh_warps_per_cta"], r["bvh_tables_in_smem"], r["bvh_smem_bytes"]
+    for nsqrt, warps in ((1, 28), (11, 28), (12, 28), (13, 24), (15, 24), (16, 20), (17, 20)):
+        v, w, in_smem, smem = plan(rtw.cover_scene(nsqrt))
+        assert (v, w, in_smem) == (rtw.BVH_WAVEFRONT, warps, 1), nsqrt
+        assert smem <= 227 * 1024 and smem + 4 * 6048 > 227 * 1024 or warps == 28   # the largest tier that fits
+    assert plan(rtw.cover_scene(11))[3] == 215760   # cover scene: 46 416 bytes of tables + 28 x 6 048 bytes of records
+    assert plan(rtw.cover_scene(18))[:3] == (rtw.BVH_WAVEFRONT, 8, 0)
+    assert plan(rtw.cover_scene(40))[:3] == (rtw.BVH_WAVEFRONT, 8, 0)
+    assert plan(rtw.mesh_on_ground_scene(SUZANNE))[:3] == (rtw.BVH_PERLANE, 8, 0)   # 968 triangles: 108 KB of tables, beyond K2's 72 KB
+    cam = dict(lookfrom=(0, 0, 0), lookat=(0, 0, -1), vup=(0, 1, 0), vfov=60.0, aspect=1.0, aperture=0.0, focus_dist=1.0)
+    prims = np.zeros(200, rtw.PRIM_DTYPE)
+    prims["kind"] = rtw.RTW_TRIANGLE
+    rng = np.random.default_rng(0)
+    prims["a"] = rng.uniform(-1, 1, (200, 3)); prims["b"] = prims["a"] + 0.1; prims["c"] = prims["a"] + [0.1, 0, 0.05]
+    assert plan(rtw.custom_scene(prims, np.zeros(1, rtw.MAT_DTYPE), **cam))[:3] == (rtw.BVH_WAVEFRONT, 28, 1)   # small meshes fit the first tier
+
+
 def test_flatten_tables_and_bvh_invariants(rtw, tmp_path):
     """north_star item 1 on the CPU: the primitive list flattened into sphere / big-sphere / triangle tables and a BVH in
     which every primitive appears exactly once (rtw_flatten_info runs the host half of rtw_scene_upload, no GPU)."""
