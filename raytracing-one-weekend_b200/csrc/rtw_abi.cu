@@ -365,7 +365,9 @@ int fill_params(const rtw_scene* sc, const rtw_render_cfg* cfg, int mode, unsign
   }
   p->s_begin = static_cast<uint32_t>(cfg->sample_begin); p->s_end = static_cast<uint32_t>(cfg->sample_end);
   const uint32_t S = p->s_end - p->s_begin;
-  const unsigned long long n_groups = (p->npix + rtw::kGroupPixels - 1) / rtw::kGroupPixels;
+  // work groups: 16 x 8 pixel tiles of the (local) image
+  p->tiles_x = (p->width + 15u) / 16u;
+  const unsigned long long n_groups = static_cast<unsigned long long>(p->tiles_x) * ((p->npix / p->width + 7u) / 8u);
   // enough units to keep every resident warp busy and the tail short: aim for >= 16 units per warp
   const unsigned long long warps = static_cast<unsigned long long>(sc->sm_count) * 4ull * (rtw::kRenderThreads / 32);
   unsigned long long su = (static_cast<unsigned long long>(S) * n_groups) / (16ull * warps);

@@ -9,7 +9,7 @@
 namespace rtw {
 
 constexpr int kRenderThreads = 256;
-constexpr uint32_t kGroupPixels = 128;  // pixels per work unit (consecutive in row-major order)
+constexpr uint32_t kGroupPixels = 128;  // pixels per work unit: a 16 x 8 tile of the image
 constexpr double kBigRadius = 100.0;    // |r| >= this: sphere leaves the fp32 tables and is tested in fp64
 
 enum : int { kCtrWork = 0, kCtrRays = 1, kCtrPaths = 2, kCtrSphereTests = 3, kCtrCandidates = 4, kCtrNodes = 5, kCtrTriTests = 6, kCtrCount = 8 };
@@ -24,6 +24,7 @@ struct RenderParams {
   unsigned long long* accum;     // [npix][4] int64 fixed point (2^-32) + finished-path count
   unsigned long long* counters;  // kCtr*
   uint32_t width, height, npix;
+  uint32_t tiles_x;              // 16-pixel tile columns: ceil(width / 16)
   uint32_t s_begin, s_end;       // global sample range of this launch
   uint32_t su;                   // samples per unit
   uint32_t n_chunks;             // ceil((s_end - s_begin) / su)

@@ -1,7 +1,7 @@
 // rtw_kernels.cu -- sm_100a kernels of the B200 path tracer and their launchers.
 //
 //   The three render kernels are the per-pixel / per-sample loop of render.cpp:150-167 with ray_color (render.cpp:112-129) turned
-//   into an iterative bounce loop.  Persistent warps pull units of (128 pixels x SU samples) from a global atomic counter; a
+//   into an iterative bounce loop.  Persistent warps pull units of (16 x 8 pixel tile x SU samples) from a global atomic counter; a
 //   finished path is replaced at once from the warp's pool (ballot + popc ranking).
 //   k_render_wf (K2w)   sphere scenes whose tables leave room in shared memory: SAH BVH (64-byte two-child nodes, single-primitive
 //                       leaves), tables staged with TMA bulk copies, the warp's paths kept as records in shared memory, shading in
@@ -297,11 +297,16 @@ __device__ __forceinline__ void trace_bvh(const DevScene& sc, F3 o, F3 d, float 
 // ---------------------------------------------------------------------------------------------------------
 // Row-tile split: pixel lp of the packed local buffer -> global image row i, column j and global pixel index (false: outside the image)
 __device__ __forceinline__ bool local_to_global(const RenderParams& p, uint32_t lp, uint32_t& gp, uint32_t& i, uint32_t& j) {
-  if (lp >= p.npix) return false;
-  i = lp / p.width; j = lp - i * p.width;
+  // a work group is a 16 x 8 pixel tile of the (local) image and 32 consecutive indices inside it form an 8 x 4 block, so that
+  // the primary rays a warp starts together are neighbours in both directions (they share the top of the tree walk)
+  const uint32_t g = lp / kGroupPixels, w = lp - g * kGroupPixels;
+  const uint32_t ty = g / p.tiles_x, tx = g - ty * p.tiles_x;
+  j = tx * 16u + ((w & 7u) | ((w >> 2) & 8u));
+  i = ty * 8u + (((w >> 3) & 3u) | ((w >> 4) & 4u));
+  if (j >= p.width || i * p.width >= p.npix) return false;
   if (p.tile_count > 1u) {
-    const uint32_t t = i / p.tile_rows, w = i - t * p.tile_rows;
-    i = (t * p.tile_count + p.tile_index) * p.tile_rows + w;
+    const uint32_t t = i / p.tile_rows, r = i - t * p.tile_rows;
+    i = (t * p.tile_count + p.tile_index) * p.tile_rows + r;
     if (i >= p.height) return false;
   }
   gp = i * p.width + j;
