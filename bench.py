@@ -36,7 +36,7 @@ WORKLOADS = {
     "suzanne_on_ground_1080p_256spp": (1920, 1.7777777777777777, 256, 20, 0, None),  # configs[2]
     "dragon_standin_1080p_256spp": (1920, 1.7777777777777777, 256, 20, 5, None),     # configs[3]: dragon.obj is missing from the
 }                                                                                    # reference mount; 968*4^5 = 991,232-triangle stand-in
-SUZANNE = ROOT / "tests" / "golden" / "suzanne.obj"
+SUZANNE = ROOT / "assets" / "suzanne.obj"
 
 
 def build_scene(rtw, name, wl):

@@ -6,7 +6,8 @@
  * message in rtw_last_error() when no CUDA device / kernel image is available.
  *
  * Plain C types only (pointers + sizes + PODs); caller owns every host buffer; the library owns device memory.
- * All calls are blocking unless stated otherwise and are not re-entrant per device.
+ * All calls are blocking unless stated otherwise; the host-buffer entry points are serialised per device, rtw_render_device is
+ * re-entrant (see there).
  *
  * Reference interface replaced by each entry point:
  *   rtw_render / rtw_render_multi_gpu  do_work lambda + thread fan-out + sum   render.cpp:150-180
@@ -15,7 +16,9 @@
  *                                      random-utils.cpp:6-41)
  *   rtw_scene_upload                   Scene::get_root_bvh / BVHNode ctor       render.cpp:73-110,131-133
  *   rtw_primary_hits                   BVHNode::hit on camera rays (parity mode; no reference entry point)
- *   rtw_finalize_rgb8                  write_color                             render.cpp:11-20
+ *   rtw_render_rgb8 / ..._multi_gpu_rgb8  the same + write_color on the device   render.cpp:150-186
+ *   rtw_finalize_rgb8[_device]         write_color                             render.cpp:11-20
+ *   rtw_scene_hash                     (identity of a Scene for checkpoints; the reference has no resumable render)
  *   rtw_release_cached_buffers         (the reference frees its per-thread images at scope exit, render.cpp:151,176)
  */
 #ifndef RTW_B200_H
@@ -26,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RTW_ABI_VERSION 2
+#define RTW_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define RTW_API __attribute__((visibility("default")))
@@ -42,7 +45,10 @@ enum rtw_mat_kind { RTW_LAMBERTIAN = 0, RTW_METAL = 1, RTW_DIELECTRIC = 2 };
  * the per-lane state machine for meshes.  BVH_PERLANE forces the latter (A/B measurements). */
 enum rtw_kernel { RTW_KERNEL_AUTO = 0, RTW_KERNEL_SPHERES_SMEM = 1, RTW_KERNEL_BVH = 2, RTW_KERNEL_BVH_PERLANE = 3 };
 enum rtw_bvh_variant { RTW_BVH_NONE = 0, RTW_BVH_PERLANE = 1, RTW_BVH_WAVEFRONT = 2 };
-enum rtw_flags { RTW_FLAG_STATS = 1, RTW_FLAG_SPLIT_ROWS = 2 };
+/* STATS: count tests / node visits (slower).  SPLIT_ROWS: multi-GPU row-tile split instead of the sample split.
+ * NO_SCENE_CACHE: the host-buffer entry points re-flatten, re-build and re-upload the scene even when it is the one the device
+ * already holds from the previous call (what the first call of a process pays; bench.py's end-to-end leg uses it). */
+enum rtw_flags { RTW_FLAG_STATS = 1, RTW_FLAG_SPLIT_ROWS = 2, RTW_FLAG_NO_SCENE_CACHE = 4 };
 
 /* One primitive, in scene insertion order (index in the array == primitive id used for parity).
  * Mirrors the constructor arguments of Sphere / MovingSphere / Triangle (oo-primitives.h:28,49,76). */
@@ -102,7 +108,7 @@ typedef struct rtw_stats {
   int32_t kernel_used;                        /* rtw_kernel actually launched (SPHERES_SMEM or BVH) */
   int32_t launches;                           /* kernels of this library launched by the call */
   int32_t bvh_variant;                        /* rtw_bvh_variant when kernel_used == RTW_KERNEL_BVH */
-  int32_t reserved;
+  int32_t scene_cache_hit;                    /* host-buffer entry points: 1 = the device(s) already held this scene (no flatten / upload) */
 } rtw_stats;
 
 typedef struct rtw_scene rtw_scene; /* device-resident flattened scene (SoA tables, BVH, materials, camera) */
@@ -116,17 +122,30 @@ RTW_API int rtw_scene_upload(const rtw_scene_desc* desc, int32_t device, rtw_sce
 RTW_API void rtw_scene_free(rtw_scene* scene);
 
 /* One-shot render with HOST buffers: upload, render samples [sample_begin,sample_end), download.
- * accum_rgba: width*height*4 floats, (sum r, sum g, sum b, number of samples) per pixel, row 0 = top. */
+ * accum_rgba: width*height*4 floats, (sum r, sum g, sum b, number of samples) per pixel, row 0 = top.
+ * The device keeps the flattened scene and its BVH between calls, keyed on a 64-bit hash of the caller's arrays (rtw_scene_hash):
+ * a repeated call with an unchanged scene (progressive slices, animation of the sample range) skips flatten, build and upload. */
 RTW_API int rtw_render(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, float* accum_rgba, rtw_stats* stats);
+/* The same render, finished on the device: rgb8[3 * pixel + c] = int(256 * clamp(sqrt(sum_c / spp), 0, 0.999)) (write_color,
+ * render.cpp:11-20, in double from the exact integer sums) with spp = sample_end - sample_begin; 3 bytes per pixel come back
+ * instead of 16. */
+RTW_API int rtw_render_rgb8(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, uint8_t* rgb8, rtw_stats* stats);
 
-/* rtw_render keeps its per-device accumulation buffers between calls; this frees them. */
+/* Starts creating the CUDA contexts of devices first_device .. first_device + ngpus - 1 on background threads and returns at
+ * once; the host-buffer entry points wait for them.  Lets a caller overlap the 0.3-1 s per GPU a cold process pays for its
+ * contexts with its own scene construction (and the GPUs with each other).  Optional. */
+RTW_API int rtw_prewarm(int32_t first_device, int32_t ngpus);
+/* The host-buffer entry points keep per-device state (scene, accumulation buffers, stream) between calls; this frees it. */
 RTW_API void rtw_release_cached_buffers(void);
+/* 64-bit hash of a scene description (primitives, materials, camera): the key of the scene cache, also stored in checkpoints. */
+RTW_API int rtw_scene_hash(const rtw_scene_desc* desc, uint64_t* hash);
 
 /* Device-resident render.  accum_fx: width*height*4 int64 on the scene's device; the kernel ADDS
  * fixed-point radiance (1 unit = 2^-32) per channel and 1 per finished path to channel 3, so shards rendered by
  * different calls / GPUs combine with an exact integer sum (ncclSum on int64) independent of order.
  * Work is enqueued on `cuda_stream` (a cudaStream_t, may be NULL); the call returns without synchronising unless
- * `stats` is non-NULL, in which case it synchronises the stream and fills it. */
+ * `stats` is non-NULL, in which case it synchronises the stream and fills it.  Every launch gets its own work-queue / statistics
+ * block: up to 64 renders of the same rtw_scene may be in flight at once, from any threads and on any streams. */
 RTW_API int rtw_render_device(const rtw_scene* scene, const rtw_render_cfg* cfg, int64_t* accum_fx, void* cuda_stream,
                       rtw_stats* stats);
 /* accum_fx (int64 x4 per pixel, device) -> accum_rgba (float x4 per pixel, device), on `cuda_stream`. */
@@ -140,16 +159,24 @@ RTW_API int32_t rtw_row_tile_local_rows(int32_t height, int32_t tile_rows, int32
 RTW_API int rtw_untile_accum(const int64_t* gathered, int64_t* accum_fx, int32_t width, int32_t height, int32_t tile_rows,
                      int32_t count, int32_t device, void* cuda_stream);
 
-/* Single-process multi-GPU render: samples split evenly over devices 0..ngpus-1 (requires ngpus | spp), one
- * ncclReduce(sum) of the accumulation buffers onto device 0 over NVLink, then one download. */
+/* Single-process multi-GPU render: samples split as evenly as possible over devices 0..ngpus-1 (the first spp % ngpus devices
+ * render one sample more; sample indices stay global, so the image does not depend on ngpus).  The int64 buffers are combined
+ * over NVLink peer memory: device g sums the g-th slice of every device's buffer with peer loads, converts and downloads that
+ * slice itself (needs peer access between the devices).  Bit-identical to the one-GPU result.
+ * With cfg->flags & RTW_FLAG_SPLIT_ROWS every GPU renders ALL samples of its interleaved row tiles (cfg->row_tile_rows rows each,
+ * default 8) and downloads them straight into their rows of the host image: no exchange between GPUs at all. */
 RTW_API int rtw_render_multi_gpu(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, int32_t ngpus, float* accum_rgba,
                          rtw_stats* stats);
-/* The same with cfg->flags & RTW_FLAG_SPLIT_ROWS: every GPU renders ALL samples of its interleaved row tiles (cfg->row_tile_rows
- * rows each, default 8) and the packed buffers are gathered on device 0 (ncclSend/ncclRecv), no summation. */
+RTW_API int rtw_render_multi_gpu_rgb8(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, int32_t ngpus, uint8_t* rgb8,
+                              rtw_stats* stats);
 
 /* write_color (render.cpp:11-20) on the device: rgb8 = int(256 * clamp(sqrt(sum / spp), 0, 0.999)).
  * accum_rgba and rgb8 are HOST buffers (npixels*4 floats in, npixels*3 bytes out). */
 RTW_API int rtw_finalize_rgb8(const float* accum_rgba, int64_t npixels, int32_t spp, int32_t device, uint8_t* rgb8);
+/* The same from a DEVICE-resident int64 accumulation buffer into a DEVICE rgb8 buffer, on `cuda_stream`, without the float rounding
+ * of the sums in between: what rtw_render_rgb8 runs. */
+RTW_API int rtw_finalize_rgb8_device(const int64_t* accum_fx, int64_t npixels, int32_t spp, int32_t device, void* cuda_stream,
+                             uint8_t* rgb8);
 
 /* Deterministic primary-ray mode: aperture 0, shutter [time,time], rays through pixel centres.
  * precision 32: the production fp32 intersection routines (kernel = SPHERES_SMEM or BVH as in rtw_render);

@@ -22,7 +22,9 @@ PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
 LIB_PATH = PKG_DIR / "librtw_b200.so"
 HOST_LIB_PATH = PKG_DIR / "librtweekend_host.so"
+HOST_VARIANT_LIB_PATH = PKG_DIR / "librtweekend_host_variant.so"   # built with -DRTWEEKEND_USE_VARIANT_PRIMITIVES
 EXE_PATH = PKG_DIR / "rtweekend"
+EXE_VARIANT_PATH = PKG_DIR / "rtweekend_variant"
 HEADER_PATH = REPO_ROOT / "include" / "rtw_b200.h"
 
 RTW_SPHERE, RTW_MOVING_SPHERE, RTW_TRIANGLE = 0, 1, 2
@@ -31,6 +33,7 @@ KERNEL_AUTO, KERNEL_SPHERES_SMEM, KERNEL_BVH, KERNEL_BVH_PERLANE = 0, 1, 2, 3
 BVH_NONE, BVH_PERLANE, BVH_WAVEFRONT = 0, 1, 2
 FLAG_STATS = 1
 FLAG_SPLIT_ROWS = 2
+FLAG_NO_SCENE_CACHE = 4
 
 
 class RtwError(RuntimeError):
@@ -83,7 +86,7 @@ class Stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("sphere_tests", C.c_uint64),
                 ("sphere_candidates", C.c_uint64), ("tri_tests", C.c_uint64), ("node_visits", C.c_uint64),
                 ("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
-                ("kernel_used", C.c_int32), ("launches", C.c_int32), ("bvh_variant", C.c_int32), ("reserved", C.c_int32)]
+                ("kernel_used", C.c_int32), ("launches", C.c_int32), ("bvh_variant", C.c_int32), ("scene_cache_hit", C.c_int32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -104,13 +107,18 @@ ABI = {
     "rtw_scene_upload": (C.c_int, [C.POINTER(SceneDesc), C.c_int32, C.POINTER(_VP)]),
     "rtw_scene_free": (None, [_VP]),
     "rtw_render": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(RenderCfg), _VP, C.POINTER(Stats)]),
+    "rtw_render_rgb8": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(RenderCfg), _VP, C.POINTER(Stats)]),
+    "rtw_prewarm": (C.c_int, [C.c_int32, C.c_int32]),
     "rtw_release_cached_buffers": (None, []),
+    "rtw_scene_hash": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(C.c_uint64)]),
     "rtw_render_device": (C.c_int, [_VP, C.POINTER(RenderCfg), _VP, _VP, C.POINTER(Stats)]),
     "rtw_accum_to_float": (C.c_int, [_VP, _VP, C.c_int64, C.c_int32, _VP]),
     "rtw_row_tile_local_rows": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
     "rtw_untile_accum": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _VP]),
     "rtw_render_multi_gpu": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(RenderCfg), C.c_int32, _VP, C.POINTER(Stats)]),
+    "rtw_render_multi_gpu_rgb8": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(RenderCfg), C.c_int32, _VP, C.POINTER(Stats)]),
     "rtw_finalize_rgb8": (C.c_int, [_VP, C.c_int64, C.c_int32, C.c_int32, _VP]),
+    "rtw_finalize_rgb8_device": (C.c_int, [_VP, C.c_int64, C.c_int32, C.c_int32, _VP, _VP]),
     "rtw_primary_hits": (C.c_int, [C.POINTER(SceneDesc), C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32,
                                    C.c_int32, _VP, _VP, _VP, _VP]),
     "rtw_debug_scatter": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(Material), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
@@ -121,6 +129,7 @@ ABI = {
 
 _lib = None
 _host = None
+_host_variant = None
 
 
 def build(force: bool = False) -> None:
@@ -146,40 +155,53 @@ def lib() -> C.CDLL:
     return _lib
 
 
+def _load_host(path: Path) -> C.CDLL:
+    lib()  # dependency
+    if not path.exists():
+        raise RtwError(f"{path} is missing: run __graft_entry__.build()")
+    H = C.CDLL(str(path))
+    H.rtwh_last_error.restype = C.c_char_p
+    H.rtwh_random_double.restype = C.c_double
+    H.rtwh_seed.argtypes = [C.c_uint]
+    H.rtwh_scene_cover.restype = _VP
+    H.rtwh_scene_cover.argtypes = [C.c_int, C.c_double, C.c_int]
+    H.rtwh_scene_obj.restype = _VP
+    H.rtwh_scene_obj.argtypes = [C.c_char_p, C.c_double]
+    H.rtwh_scene_mesh_on_ground.restype = _VP
+    H.rtwh_scene_mesh_on_ground.argtypes = [C.c_char_p, C.c_double]
+    H.rtwh_scene_free.argtypes = [_VP]
+    H.rtwh_scene_nprims.restype = C.c_longlong
+    H.rtwh_scene_nprims.argtypes = [_VP]
+    H.rtwh_scene_nmats.restype = C.c_longlong
+    H.rtwh_scene_nmats.argtypes = [_VP]
+    H.rtwh_scene_flatten.argtypes = [_VP, _VP, _VP, C.POINTER(SceneDesc)]
+    H.rtwh_camera.argtypes = [C.c_double * 3, C.c_double * 3, C.c_double * 3, C.c_double, C.c_double, C.c_double,
+                              C.c_double, C.c_double, C.c_double, C.POINTER(Camera)]
+    H.rtwh_render_to_file.argtypes = [_VP, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int,
+                                      C.c_ulonglong, C.c_int]
+    H.rtwh_config_string.argtypes = [C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+    H.rtwh_image_height.argtypes = [C.c_int, C.c_double]
+    H.rtwh_effective_spp.argtypes = [C.c_int, C.c_int]
+    H.rtwh_make_mesh.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_uint, C.c_double, C.POINTER(C.c_longlong)]
+    H.rtwh_write_ppm.argtypes = [_VP, C.c_int, C.c_int, C.c_int, C.c_char_p]
+    H.rtwh_primitive_model.restype = C.c_char_p
+    return H
+
+
 def host() -> C.CDLL:
-    """librtweekend_host.so: the product's own scene builders / flatten / render()."""
+    """librtweekend_host.so: the product's own scene builders / flatten / render() (virtual primitive model)."""
     global _host
     if _host is None:
-        lib()  # dependency
-        if not HOST_LIB_PATH.exists():
-            raise RtwError(f"{HOST_LIB_PATH} is missing: run __graft_entry__.build()")
-        H = C.CDLL(str(HOST_LIB_PATH))
-        H.rtwh_last_error.restype = C.c_char_p
-        H.rtwh_random_double.restype = C.c_double
-        H.rtwh_seed.argtypes = [C.c_uint]
-        H.rtwh_scene_cover.restype = _VP
-        H.rtwh_scene_cover.argtypes = [C.c_int, C.c_double, C.c_int]
-        H.rtwh_scene_obj.restype = _VP
-        H.rtwh_scene_obj.argtypes = [C.c_char_p, C.c_double]
-        H.rtwh_scene_mesh_on_ground.restype = _VP
-        H.rtwh_scene_mesh_on_ground.argtypes = [C.c_char_p, C.c_double]
-        H.rtwh_scene_free.argtypes = [_VP]
-        H.rtwh_scene_nprims.restype = C.c_longlong
-        H.rtwh_scene_nprims.argtypes = [_VP]
-        H.rtwh_scene_nmats.restype = C.c_longlong
-        H.rtwh_scene_nmats.argtypes = [_VP]
-        H.rtwh_scene_flatten.argtypes = [_VP, _VP, _VP, C.POINTER(SceneDesc)]
-        H.rtwh_camera.argtypes = [C.c_double * 3, C.c_double * 3, C.c_double * 3, C.c_double, C.c_double, C.c_double,
-                                  C.c_double, C.c_double, C.c_double, C.POINTER(Camera)]
-        H.rtwh_render_to_file.argtypes = [_VP, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int,
-                                          C.c_ulonglong, C.c_int]
-        H.rtwh_config_string.argtypes = [C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
-        H.rtwh_image_height.argtypes = [C.c_int, C.c_double]
-        H.rtwh_effective_spp.argtypes = [C.c_int, C.c_int]
-        H.rtwh_make_mesh.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_uint, C.c_double, C.POINTER(C.c_longlong)]
-        H.rtwh_write_ppm.argtypes = [_VP, C.c_int, C.c_int, C.c_int, C.c_char_p]
-        _host = H
+        _host = _load_host(HOST_LIB_PATH)
     return _host
+
+
+def host_variant() -> C.CDLL:
+    """The same host library compiled with -DRTWEEKEND_USE_VARIANT_PRIMITIVES (std::variant primitive store)."""
+    global _host_variant
+    if _host_variant is None:
+        _host_variant = _load_host(HOST_VARIANT_LIB_PATH)
+    return _host_variant
 
 
 def _check(rc: int, what: str) -> None:
@@ -224,8 +246,8 @@ def make_camera(lookfrom, lookat, vup, vfov, aspect, aperture, focus_dist=None, 
     return out
 
 
-def _from_handle(h, params) -> Scene:
-    H = host()
+def _from_handle(h, params, H=None) -> Scene:
+    H = H or host()
     if not h:
         raise RtwError(H.rtwh_last_error().decode())
     try:
@@ -239,22 +261,23 @@ def _from_handle(h, params) -> Scene:
     return Scene(prims, mats, cam, params)
 
 
-def cover_scene(nsqrt: int = 11, aspect: float = 1.5, moving: bool = True, host_seed: int | None = 5489) -> Scene:
+def cover_scene(nsqrt: int = 11, aspect: float = 1.5, moving: bool = True, host_seed: int | None = 5489, H=None) -> Scene:
     """rtweekend::lots_of_balls (host/scenes.cpp; reference main.cpp:23-83).  host_seed=5489 is the state a fresh
-    reference process starts from."""
-    H = host()
+    reference process starts from.  H: the host library to build with (default: the virtual primitive model)."""
+    H = H or host()
     if host_seed is not None:
         H.rtwh_seed(host_seed)
     params = dict(lookfrom=(13, 2, 3), lookat=(0, 0, 0), vup=(0, 1, 0), vfov=20.0, aspect=aspect, aperture=0.1,
                   focus_dist=10.0, t0=0.0, t1=1.0)
-    return _from_handle(H.rtwh_scene_cover(nsqrt, aspect, int(moving)), params)
+    return _from_handle(H.rtwh_scene_cover(nsqrt, aspect, int(moving)), params, H)
 
 
-def obj_scene(path: str, aspect: float = 1.5) -> Scene:
+def obj_scene(path: str, aspect: float = 1.5, H=None) -> Scene:
     """rtweekend::foo (host/scenes.cpp; reference main.cpp:85-136)."""
+    H = H or host()
     params = dict(lookfrom=(1, 0, -1), lookat=(0, 0, 0), vup=(0, 1, 0), vfov=35.0, aspect=aspect, aperture=0.01,
                   focus_dist=-1.0, t0=0.0, t1=1.0)
-    return _from_handle(host().rtwh_scene_obj(str(path).encode(), aspect), params)
+    return _from_handle(H.rtwh_scene_obj(str(path).encode(), aspect), params, H)
 
 
 def mesh_on_ground_scene(path: str, aspect: float = 1.5) -> Scene:
@@ -305,6 +328,26 @@ def render(scene: Scene, width: int, height: int, spp: int, max_child_rays: int 
     st = Stats()
     _check(lib().rtw_render(C.byref(d), C.byref(cfg), out.ctypes.data_as(_VP), C.byref(st)), "rtw_render")
     return out, st.as_dict()
+
+
+def render_rgb8(scene: Scene, width: int, height: int, spp: int, max_child_rays: int = 20, ngpus: int = 1, **kw):
+    """rtw_render_rgb8 / rtw_render_multi_gpu_rgb8: the quantised picture (write_color on the device).  Returns (rgb[H,W,3] uint8, stats)."""
+    cfg = make_cfg(width, height, spp, max_child_rays, **kw)
+    d = scene.desc()
+    out = np.zeros((height, width, 3), np.uint8)
+    st = Stats()
+    if ngpus > 1:
+        _check(lib().rtw_render_multi_gpu_rgb8(C.byref(d), C.byref(cfg), ngpus, out.ctypes.data_as(_VP), C.byref(st)), "rtw_render_multi_gpu_rgb8")
+    else:
+        _check(lib().rtw_render_rgb8(C.byref(d), C.byref(cfg), out.ctypes.data_as(_VP), C.byref(st)), "rtw_render_rgb8")
+    return out, st.as_dict()
+
+
+def scene_hash(scene: Scene) -> int:
+    d = scene.desc()
+    h = C.c_uint64(0)
+    _check(lib().rtw_scene_hash(C.byref(d), C.byref(h)), "rtw_scene_hash")
+    return h.value
 
 
 def render_multi_gpu(scene: Scene, width: int, height: int, spp: int, ngpus: int, max_child_rays: int = 20, **kw):

@@ -6,7 +6,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 OUT=../librtw_b200.so
 FLAGS="${RTW_EXTRA:-} -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -ccbin /usr/bin/g++"
 newer=0
-for f in rtw_kernels.cu rtw_abi.cu rtw_multi.cu rtw_device.cuh rtw_internal.h rtw_bvh.h ../../include/rtw_b200.h build.sh; do
+for f in rtw_kernels.cu rtw_abi.cu rtw_multi.cu rtw_device.cuh rtw_internal.h rtw_host.h rtw_bvh.h ../../include/rtw_b200.h build.sh; do
   if [ ! -e "$OUT" ] || [ "$f" -nt "$OUT" ]; then newer=1; fi
 done
 if [ "$newer" = 0 ] && [ "${1:-}" != "-f" ]; then echo "librtw_b200.so up to date"; exit 0; fi

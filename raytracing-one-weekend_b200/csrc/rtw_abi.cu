@@ -16,46 +16,10 @@
 #include <vector>
 
 #include "rtw_bvh.h"
-#include "rtw_internal.h"
+#include "rtw_host.h"
 
 namespace {
-
 thread_local std::string g_last_error;
-
-int fail(const std::string& msg) {
-  g_last_error = msg;
-  return 1;
-}
-int fail_cuda(const char* what, cudaError_t e) {
-  g_last_error = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
-  return 2;
-}
-#define RTW_CUDA(call)                                     \
-  do {                                                     \
-    cudaError_t e__ = (call);                              \
-    if (e__ != cudaSuccess) return fail_cuda(#call, e__);  \
-  } while (0)
-
-template <typename T>
-struct DevBuf {
-  T* p = nullptr;
-  size_t n = 0;
-  DevBuf() = default;
-  DevBuf(const DevBuf&) = delete;
-  DevBuf& operator=(const DevBuf&) = delete;
-  ~DevBuf() { if (p) cudaFree(p); }
-  cudaError_t alloc(size_t count) {
-    if (p) { cudaFree(p); p = nullptr; }
-    n = count;
-    if (count == 0) return cudaSuccess;
-    return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
-  }
-  cudaError_t upload(const std::vector<T>& v, cudaStream_t s = nullptr) {
-    cudaError_t e = alloc(v.size());
-    if (e != cudaSuccess || v.empty()) return e;
-    return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
-  }
-};
 
 float __int_as_float_host(int v) {
   float f;
@@ -67,37 +31,29 @@ double now_ms() {
   using namespace std::chrono;
   return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
-
 }  // namespace
 
-struct rtw_scene {
-  int device = 0;
-  int sm_count = 0;
-  DevBuf<unsigned char> arena;  // every table of the scene in ONE allocation, filled by ONE host-to-device copy
-  unsigned char* arena_ptr = nullptr;  // = arena.p, or memory borrowed from rtw_render's per-device cache
-  unsigned long long* counters = nullptr;
-  size_t n_leaf_refs = 0;
-  rtw::DevScene dev{};
-  int64_t nprims = 0;
-  bool has_triangles = false;
-  size_t smem_bytes = 0;
-};
+namespace rtw {
+int fail(const std::string& msg) {
+  g_last_error = msg;
+  return 1;
+}
+int fail_cuda(const char* what, cudaError_t e) {
+  g_last_error = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+  return 2;
+}
+}  // namespace rtw
+using rtw::fail;
+using rtw::fail_cuda;
+using rtw::DevBuf;
+using rtw::HostFlat;
 
 namespace {
 
 // Flatten (north_star item 1): variant/virtual primitive list -> SoA tables, BVH, materials, all in one host arena whose
-// layout is the device layout.  Pure host code: no CUDA call in here (rtw_flatten_info exposes it to CPU-only tests).
-// Two passes over the primitive list, both split over host threads for large scenes: (1) classify + count + scene bound,
-// (2) write every table entry and BVH build record straight into its final place (insertion order is kept per table).
-struct HostFlat {
-  std::unique_ptr<unsigned char[]> host;
-  size_t bytes = 0;
-  size_t o_sA = 0, o_sB = 0, o_sId = 0, o_big = 0, o_tri = 0, o_triId = 0, o_nodes = 0, o_refs = 0, o_matA = 0, o_matB = 0, o_ctr = 0;
-  int32_t n_static = 0, n_moving = 0, n_big = 0, n_tri = 0, n_nodes = 0, leaf_direct = 0;
-  size_t n_leaf_refs = 0;
-  double bvh_ms = 0.0;
-};
-
+// layout is the device layout (HostFlat, rtw_host.h).  Pure host code: no CUDA call in here (rtw_flatten_info exposes it to
+// CPU-only tests).  Two passes over the primitive list, both split over host threads for large scenes: (1) classify + count +
+// scene bound, (2) write every table entry and BVH build record straight into its final place (insertion order is kept per table).
 enum : uint8_t { kClsStatic = 0, kClsMoving = 1, kClsBig = 2, kClsTri = 3, kClsBadKind = 4, kClsBadMaterial = 5 };
 
 template <typename F>
@@ -109,7 +65,9 @@ void parallel_chunks(int64_t n, int nchunks, F&& fn) {  // fn(chunk, begin, end)
   for (auto& t : tasks) t.get();
 }
 
-int flatten_host(const rtw_scene_desc* desc, HostFlat* hf) {
+}  // namespace
+
+int rtw::flatten_host(const rtw_scene_desc* desc, HostFlat* hf) {
   if (!desc || desc->nprims < 0 || desc->nmats < 0 || (desc->nprims > 0 && !desc->prims) || (desc->nmats > 0 && !desc->mats))
     return fail("rtw_scene_upload: invalid scene description");
   if (desc->nprims >= (1ll << 28)) return fail("rtw_scene_upload: too many primitives");
@@ -177,7 +135,7 @@ int flatten_host(const rtw_scene_desc* desc, HostFlat* hf) {
   hf->o_tri = reserve(n_tri * 3 * sizeof(float4)); hf->o_triId = reserve(n_tri * sizeof(int2));
   hf->o_nodes = reserve(node_cap * sizeof(rtw::PackedNode)); hf->o_refs = reserve(ref_cap * sizeof(uint32_t));
   hf->o_matA = reserve(static_cast<size_t>(desc->nmats) * sizeof(float4)); hf->o_matB = reserve(static_cast<size_t>(desc->nmats) * sizeof(float2));
-  hf->o_ctr = reserve(rtw::kCtrCount * sizeof(unsigned long long));
+  hf->o_ctr = reserve(static_cast<size_t>(rtw::kCtrSlots) * rtw::kCtrCount * sizeof(unsigned long long));
   hf->bytes = (cursor + 255) & ~size_t(255);
   hf->host.reset(new unsigned char[hf->bytes]);
   unsigned char* base = hf->host.get();
@@ -187,7 +145,7 @@ int flatten_host(const rtw_scene_desc* desc, HostFlat* hf) {
   rtw::BigSphere* big = reinterpret_cast<rtw::BigSphere*>(base + hf->o_big);
   float4* tri = reinterpret_cast<float4*>(base + hf->o_tri);
   int2* triId = reinterpret_cast<int2*>(base + hf->o_triId);
-  std::memset(base + hf->o_ctr, 0, rtw::kCtrCount * sizeof(unsigned long long));
+  std::memset(base + hf->o_ctr, 0, static_cast<size_t>(rtw::kCtrSlots) * rtw::kCtrCount * sizeof(unsigned long long));
 
   // ---- pass 2: table entries and BVH build records (small spheres: swept bounds, common-model.cpp:197-207) ----------------------
   std::vector<rtw::BvhBuilder::Item> items(n_items);
@@ -243,9 +201,6 @@ int flatten_host(const rtw_scene_desc* desc, HostFlat* hf) {
   size_t n_nodes = 0, n_refs = 0;
   if (direct) {
     n_nodes = builder.build_items_direct(items, nodes_out);
-    if (builder.max_depth() > rtw::kBvhStack)
-      return fail("rtw_scene_upload: the BVH is deeper than the kernels' traversal stack (" + std::to_string(builder.max_depth()) + " > " +
-                  std::to_string(rtw::kBvhStack) + " levels): degenerate primitive distribution");
   } else {
     std::vector<rtw::Box3> boxes(n_items);
     std::vector<uint32_t> refs(n_items);
@@ -255,6 +210,12 @@ int flatten_host(const rtw_scene_desc* desc, HostFlat* hf) {
     if (n_nodes) std::memcpy(nodes_out, builder.nodes().data(), n_nodes * sizeof(rtw::PackedNode));
     if (n_refs) std::memcpy(base + hf->o_refs, builder.leaf_refs().data(), n_refs * sizeof(uint32_t));
   }
+  // the kernels drop a push when their traversal stack is full, which would lose a subtree: refuse such a tree instead (both
+  // builders switch to median splits below kSahDepthLimit, so this only triggers on a builder bug)
+  if (builder.max_depth() > rtw::kBvhStack)
+    return fail("rtw_scene_upload: the BVH is deeper than the kernels' traversal stack (" + std::to_string(builder.max_depth()) + " > " +
+                std::to_string(rtw::kBvhStack) + " levels): degenerate primitive distribution");
+  hf->bvh_depth = builder.max_depth();
   hf->bvh_ms = now_ms() - t_bvh;
 
   float4* matA = reinterpret_cast<float4*>(base + hf->o_matA);
@@ -272,7 +233,48 @@ int flatten_host(const rtw_scene_desc* desc, HostFlat* hf) {
   return 0;
 }
 
-int flatten_and_upload(const rtw_scene_desc* desc, int device, rtw_scene* sc, DevBuf<unsigned char>* borrowed = nullptr) {
+// 64-bit key of a scene description: every byte of the primitive and material arrays and of the camera block.  Word-wise
+// multiply-xorshift mixing, four independent lanes per chunk, chunks hashed by separate host threads for big scenes and combined in
+// order (1 M primitives = 88 MB: ~3 ms on 16 threads).
+namespace {
+uint64_t mix64(uint64_t h, uint64_t w) {
+  h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+  return h ^ (h >> 29);
+}
+uint64_t hash_bytes(const void* data, size_t bytes, uint64_t seed) {
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  uint64_t h0 = seed ^ 0x243F6A8885A308D3ull, h1 = seed ^ 0x13198A2E03707344ull, h2 = seed ^ 0xA4093822299F31D0ull, h3 = seed ^ 0x082EFA98EC4E6C89ull;
+  size_t i = 0;
+  for (; i + 32 <= bytes; i += 32) {
+    uint64_t w[4];
+    std::memcpy(w, p + i, 32);
+    h0 = mix64(h0, w[0]); h1 = mix64(h1, w[1]); h2 = mix64(h2, w[2]); h3 = mix64(h3, w[3]);
+  }
+  uint64_t tail[4] = {0, 0, 0, 0};
+  std::memcpy(tail, p + i, bytes - i);
+  h0 = mix64(h0, tail[0]); h1 = mix64(h1, tail[1]); h2 = mix64(h2, tail[2]); h3 = mix64(h3, tail[3] ^ bytes);
+  return mix64(mix64(mix64(h0, h1), h2), h3);
+}
+}  // namespace
+
+uint64_t rtw::scene_key(const rtw_scene_desc* desc) {
+  if (!desc) return 1;
+  const size_t pb = desc->nprims > 0 && desc->prims ? static_cast<size_t>(desc->nprims) * sizeof(rtw_primitive) : 0;
+  const size_t mb = desc->nmats > 0 && desc->mats ? static_cast<size_t>(desc->nmats) * sizeof(rtw_material) : 0;
+  uint64_t h = hash_bytes(&desc->camera, sizeof desc->camera, static_cast<uint64_t>(desc->nprims) * 0x100000001B3ull + static_cast<uint64_t>(desc->nmats));
+  h = mix64(h, hash_bytes(desc->mats, mb, 2));
+  const int hw = static_cast<int>(std::max(1u, std::thread::hardware_concurrency()));
+  const int nchunks = pb >= (size_t(4) << 20) ? std::min(hw, 32) : 1;
+  std::vector<uint64_t> part(static_cast<size_t>(nchunks), 0);
+  const unsigned char* base = reinterpret_cast<const unsigned char*>(desc->prims);
+  parallel_chunks(static_cast<int64_t>(desc->nprims > 0 ? desc->nprims : 0), nchunks, [&](int c, int64_t begin, int64_t end) {
+    part[static_cast<size_t>(c)] = hash_bytes(base + static_cast<size_t>(begin) * sizeof(rtw_primitive), static_cast<size_t>(end - begin) * sizeof(rtw_primitive), 3 + static_cast<uint64_t>(c));
+  });
+  for (uint64_t v : part) h = mix64(h, v);
+  return h ? h : 1;
+}
+
+int rtw::upload_flat(const HostFlat& hf, const rtw_camera& c, int64_t nprims, int device, rtw_scene* sc, DevBuf<unsigned char>* borrowed, cudaStream_t stream) {
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess) return fail_cuda("cudaGetDeviceCount (no CUDA device: this library has no CPU fallback)", e);
@@ -284,36 +286,31 @@ int flatten_and_upload(const rtw_scene_desc* desc, int device, rtw_scene* sc, De
   if (cc_major < 10) return fail("rtw_b200 kernels are built for sm_100a only; this device has an older compute capability");
   sc->device = device;
   sc->sm_count = sm_count;
-
-  sc->nprims = desc ? desc->nprims : 0;
-  HostFlat hf;
-  if (int rc = flatten_host(desc, &hf)) return rc;
-  const size_t o_sA = hf.o_sA, o_sB = hf.o_sB, o_sId = hf.o_sId, o_big = hf.o_big, o_tri = hf.o_tri, o_triId = hf.o_triId, o_nodes = hf.o_nodes,
-               o_refs = hf.o_refs, o_matA = hf.o_matA, o_matB = hf.o_matB, o_ctr = hf.o_ctr;
-  if (borrowed) {  // grow-only buffer owned by the caller (rtw_render's cache): no allocation in the steady state
-    if (borrowed->n < hf.bytes) RTW_CUDA(borrowed->alloc(hf.bytes + hf.bytes / 8));
+  sc->nprims = nprims;
+  if (borrowed) {  // grow-only buffer owned by the caller (a device slot): no allocation in the steady state
+    RTW_CUDA(borrowed->reserve(hf.bytes));
     sc->arena_ptr = borrowed->p;
   } else {
     RTW_CUDA(sc->arena.alloc(hf.bytes));
     sc->arena_ptr = sc->arena.p;
   }
-  RTW_CUDA(cudaMemcpy(sc->arena_ptr, hf.host.get(), hf.bytes, cudaMemcpyHostToDevice));
+  RTW_CUDA(cudaMemcpyAsync(sc->arena_ptr, hf.host.get(), hf.bytes, cudaMemcpyHostToDevice, stream));
+  RTW_CUDA(cudaStreamSynchronize(stream));  // the host arena may go away when the caller returns
   unsigned char* base = sc->arena_ptr;
-  sc->counters = reinterpret_cast<unsigned long long*>(base + o_ctr);
+  sc->counters = reinterpret_cast<unsigned long long*>(base + hf.o_ctr);
   sc->n_leaf_refs = hf.n_leaf_refs;
 
   rtw::DevScene& d = sc->dev;
-  d.sphA = reinterpret_cast<const float4*>(base + o_sA); d.sphB = reinterpret_cast<const float4*>(base + o_sB);
-  d.sphId = reinterpret_cast<const int2*>(base + o_sId);
+  d.sphA = reinterpret_cast<const float4*>(base + hf.o_sA); d.sphB = reinterpret_cast<const float4*>(base + hf.o_sB);
+  d.sphId = reinterpret_cast<const int2*>(base + hf.o_sId);
   d.n_static = hf.n_static; d.n_moving = hf.n_moving;
-  d.big = reinterpret_cast<const rtw::BigSphere*>(base + o_big); d.n_big = hf.n_big;
-  d.tri = reinterpret_cast<const float4*>(base + o_tri); d.triId = reinterpret_cast<const int2*>(base + o_triId);
+  d.big = reinterpret_cast<const rtw::BigSphere*>(base + hf.o_big); d.n_big = hf.n_big;
+  d.tri = reinterpret_cast<const float4*>(base + hf.o_tri); d.triId = reinterpret_cast<const int2*>(base + hf.o_triId);
   d.n_tri = hf.n_tri;
-  d.nodes = reinterpret_cast<const float4*>(base + o_nodes); d.leafRefs = reinterpret_cast<const uint32_t*>(base + o_refs);
+  d.nodes = reinterpret_cast<const float4*>(base + hf.o_nodes); d.leafRefs = reinterpret_cast<const uint32_t*>(base + hf.o_refs);
   d.n_nodes = hf.n_nodes;
   d.leaf_direct = hf.leaf_direct;
-  d.matA = reinterpret_cast<const float4*>(base + o_matA); d.matB = reinterpret_cast<const float2*>(base + o_matB);
-  const rtw_camera& c = desc->camera;
+  d.matA = reinterpret_cast<const float4*>(base + hf.o_matA); d.matB = reinterpret_cast<const float2*>(base + hf.o_matB);
   for (int k = 0; k < 3; ++k) {
     d.cam.origin[k] = (float)c.origin[k]; d.cam.lower_left[k] = (float)c.lower_left[k];
     d.cam.horizontal[k] = (float)c.horizontal[k]; d.cam.vertical[k] = (float)c.vertical[k];
@@ -324,6 +321,61 @@ int flatten_and_upload(const rtw_scene_desc* desc, int device, rtw_scene* sc, De
   sc->smem_bytes = 16 + (static_cast<size_t>(hf.n_static + hf.n_moving) + 1) * 32;
   return 0;
 }
+
+// Context creation takes 0.3-1 s per GPU on a cold process: rtw_prewarm starts it on background threads (one per device) so that it
+// overlaps the caller's scene construction and, for several GPUs, each other; the host-buffer entry points join them first.
+namespace {
+std::mutex g_warm_mutex;
+std::vector<std::thread> g_warm_threads;
+uint64_t g_warm_started = 0;   // bit d: device d has been (or is being) warmed
+}  // namespace
+void rtw::prewarm_join() {
+  std::lock_guard<std::mutex> lock(g_warm_mutex);
+  for (auto& t : g_warm_threads) t.join();
+  g_warm_threads.clear();
+}
+
+// ---- per-device slots -----------------------------------------------------------------------------------------------------------
+namespace {
+std::mutex g_slots_mutex;
+rtw::DeviceSlot* g_slots[64] = {};
+}  // namespace
+
+rtw::DeviceSlot* rtw::device_slot(int device) {
+  if (device < 0 || device >= 64) { fail("device ordinal out of range"); return nullptr; }
+  std::lock_guard<std::mutex> lock(g_slots_mutex);
+  if (!g_slots[device]) { g_slots[device] = new DeviceSlot(); g_slots[device]->device = device; }
+  return g_slots[device];
+}
+
+int rtw::slot_prepare(DeviceSlot* s) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess) return fail_cuda("cudaGetDeviceCount (no CUDA device: this library has no CPU fallback)", e);
+  if (s->device >= ndev) return fail("render: device ordinal out of range");
+  RTW_CUDA(cudaSetDevice(s->device));
+  if (!s->stream) RTW_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  if (!s->rendered) RTW_CUDA(cudaEventCreateWithFlags(&s->rendered, cudaEventDisableTiming));
+  return 0;
+}
+
+int rtw::slot_set_scene(DeviceSlot* s, const rtw_scene_desc* desc, uint64_t key, bool use_cache, HostFlat* flat, std::mutex* flat_mutex, bool* hit) {
+  if (hit) *hit = false;
+  if (use_cache && s->key != 0 && s->key == key) { if (hit) *hit = true; return 0; }
+  s->key = 0;
+  {
+    std::unique_lock<std::mutex> lock;
+    if (flat_mutex) lock = std::unique_lock<std::mutex>(*flat_mutex);   // several GPUs of one call share ONE flatten
+    if (!flat->host) {
+      if (int rc = flatten_host(desc, flat)) return rc;
+    }
+  }
+  if (int rc = upload_flat(*flat, desc->camera, desc->nprims, s->device, &s->scene, &s->arena, s->stream)) return rc;
+  s->key = key;
+  return 0;
+}
+
+namespace {
 
 // Which kernel a scene gets.  AUTO is always a BVH kernel: since the wavefront kernel (K2w) it is the faster one at every table
 // size (1080p, 64 spp, Mpaths/s, K1 vs K2w: 8 primitives 11 803 / 15 088, 20: 10 042 / 14 068, 40: 8 077 / 13 398, 66: 6 111 / 11 680,
@@ -352,7 +404,7 @@ int fill_params(const rtw_scene* sc, const rtw_render_cfg* cfg, int mode, unsign
   if (static_cast<long long>(cfg->width) * cfg->height >= (1ll << 31)) return fail("render: image too large");
   p->sc = sc->dev;
   p->accum = accum;
-  p->counters = sc->counters;
+  p->counters = sc->counters;   // rtw_render_device picks the launch's own block
   p->width = static_cast<uint32_t>(cfg->width); p->height = static_cast<uint32_t>(cfg->height);
   p->npix = p->width * p->height;
   p->tile_rows = 1; p->tile_count = 1; p->tile_index = 0;
@@ -409,7 +461,7 @@ int rtw_flatten_info(const rtw_scene_desc* desc, rtw_flatten_report* out) {
   if (!out) return fail("rtw_flatten_info: null output");
   HostFlat hf;
   const double t0 = now_ms();
-  if (int rc = flatten_host(desc, &hf)) return rc;
+  if (int rc = rtw::flatten_host(desc, &hf)) return rc;
   out->n_static_spheres = hf.n_static; out->n_moving_spheres = hf.n_moving; out->n_big_spheres = hf.n_big; out->n_triangles = hf.n_tri;
   out->n_bvh_nodes = hf.n_nodes; out->leaf_direct = hf.leaf_direct; out->arena_bytes = static_cast<int64_t>(hf.bytes);
   out->flatten_ms = now_ms() - t0; out->bvh_build_ms = hf.bvh_ms;
@@ -454,10 +506,19 @@ int rtw_flatten_info(const rtw_scene_desc* desc, rtw_flatten_report* out) {
 int rtw_scene_upload(const rtw_scene_desc* desc, int32_t device, rtw_scene** out) {
   if (!out) return fail("rtw_scene_upload: null output");
   *out = nullptr;
+  HostFlat hf;
+  if (int rc = rtw::flatten_host(desc, &hf)) return rc;
   rtw_scene* sc = new rtw_scene();
-  const int rc = flatten_and_upload(desc, device, sc);
+  const int rc = rtw::upload_flat(hf, desc->camera, desc->nprims, device, sc, nullptr, nullptr);
   if (rc != 0) { delete sc; return rc; }
   *out = sc;
+  return 0;
+}
+
+int rtw_scene_hash(const rtw_scene_desc* desc, uint64_t* out) {
+  if (!desc || !out) return fail("rtw_scene_hash: null argument");
+  if (desc->nprims < 0 || desc->nmats < 0 || (desc->nprims > 0 && !desc->prims) || (desc->nmats > 0 && !desc->mats)) return fail("rtw_scene_hash: invalid scene description");
+  *out = rtw::scene_key(desc);
   return 0;
 }
 
@@ -475,26 +536,26 @@ int rtw_render_device(const rtw_scene* scene, const rtw_render_cfg* cfg, int64_t
   if (int rc = choose_mode(scene, cfg->kernel, &mode)) return rc;
   rtw::RenderParams p{};
   if (int rc = fill_params(scene, cfg, mode, reinterpret_cast<unsigned long long*>(accum_fx), &p)) return rc;
+  // this launch's own counter block (work-queue cursor + statistics): renders of one scene may overlap on other streams / threads
+  p.counters = scene->counters + static_cast<size_t>(scene->launch_seq.fetch_add(1, std::memory_order_relaxed) % rtw::kCtrSlots) * rtw::kCtrCount;
   const int rpl = cfg->rays_per_lane;
   const bool want_stats = (cfg->flags & RTW_FLAG_STATS) != 0;
-  RTW_CUDA(cudaMemsetAsync(scene->counters, 0, rtw::kCtrCount * sizeof(unsigned long long), stream));
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  RTW_CUDA(cudaMemsetAsync(p.counters, 0, rtw::kCtrCount * sizeof(unsigned long long), stream));
+  rtw::EventPair ev;
   if (stats) {
-    RTW_CUDA(cudaEventCreate(&e0));
-    RTW_CUDA(cudaEventCreate(&e1));
-    RTW_CUDA(cudaEventRecord(e0, stream));
+    RTW_CUDA(ev.create());
+    RTW_CUDA(cudaEventRecord(ev.a, stream));
   }
   int variant = RTW_BVH_NONE;
   cudaError_t le = rtw::launch_render(p, mode, rpl, cfg->kernel == RTW_KERNEL_BVH_PERLANE, want_stats, scene->sm_count, stream, &variant);
   if (le != cudaSuccess) return fail_cuda("launch k_render", le);
   if (stats) {
-    RTW_CUDA(cudaEventRecord(e1, stream));
+    RTW_CUDA(cudaEventRecord(ev.b, stream));
     unsigned long long h[rtw::kCtrCount];
-    RTW_CUDA(cudaMemcpyAsync(h, scene->counters, sizeof h, cudaMemcpyDeviceToHost, stream));
+    RTW_CUDA(cudaMemcpyAsync(h, p.counters, sizeof h, cudaMemcpyDeviceToHost, stream));
     RTW_CUDA(cudaStreamSynchronize(stream));
     float ms = 0.f;
-    RTW_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    RTW_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
     std::memset(stats, 0, sizeof *stats);
     read_counters(h, stats);
     stats->kernel_ms = ms;
@@ -531,63 +592,105 @@ int rtw_accum_to_float(const int64_t* accum_fx, float* accum_rgba, int64_t npixe
   return 0;
 }
 
-// Per-device accumulation buffers of the host-buffer entry point, kept across calls (grow-only) so that a render costs one
-// small arena allocation, one H2D copy, the kernels and one D2H copy.  Released by rtw_release_cached_buffers().
-namespace {
-struct RenderCache {
-  DevBuf<long long> fx;
-  DevBuf<float> out;
-  DevBuf<unsigned char> arena;
-  size_t npix = 0;
-};
-std::mutex g_cache_mutex;
-RenderCache* g_cache[64] = {};
-}  // namespace
+int rtw_finalize_rgb8_device(const int64_t* accum_fx, int64_t npixels, int32_t spp, int32_t device, void* cuda_stream, uint8_t* rgb8) {
+  if (!accum_fx || !rgb8 || npixels <= 0 || spp <= 0) return fail("rtw_finalize_rgb8_device: invalid argument");
+  RTW_CUDA(cudaSetDevice(device));
+  cudaError_t e = rtw::launch_finalize_rgb8_fx(reinterpret_cast<const long long*>(accum_fx), rgb8, npixels, spp, static_cast<cudaStream_t>(cuda_stream));
+  if (e != cudaSuccess) return fail_cuda("launch k_finalize_rgb8_fx", e);
+  return 0;
+}
+
+int rtw_prewarm(int32_t first_device, int32_t ngpus) {
+  if (first_device < 0 || ngpus < 1 || first_device + ngpus > 64) return fail("rtw_prewarm: bad device range");
+  std::lock_guard<std::mutex> lock(g_warm_mutex);
+  for (int d = first_device; d < first_device + ngpus; ++d) {
+    if (g_warm_started >> d & 1) continue;
+    g_warm_started |= 1ull << d;
+    g_warm_threads.emplace_back([d] {
+      if (cudaSetDevice(d) == cudaSuccess) cudaFree(nullptr);   // creates the primary context; errors surface in the render call
+      cudaGetLastError();
+    });
+  }
+  return 0;
+}
 
 void rtw_release_cached_buffers(void) {
-  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  std::lock_guard<std::mutex> lock(g_slots_mutex);
   for (int d = 0; d < 64; ++d) {
-    if (!g_cache[d]) continue;
+    rtw::DeviceSlot* s = g_slots[d];
+    if (!s) continue;
+    std::lock_guard<std::mutex> busy(s->m);
     cudaSetDevice(d);
-    delete g_cache[d];
-    g_cache[d] = nullptr;
+    if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->rendered) cudaEventDestroy(s->rendered);
+    s->arena.alloc(0); s->fx.alloc(0); s->out_f32.alloc(0); s->out_u8.alloc(0);
+    s->stream = nullptr; s->rendered = nullptr; s->key = 0;
   }
 }
 
-int rtw_render(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, float* accum_rgba, rtw_stats* stats) {
-  if (!desc || !cfg || !accum_rgba) return fail("rtw_render: null argument");
+// Host-buffer render on one GPU.  The device slot keeps the uploaded scene (keyed on a hash of the caller's arrays) and the
+// accumulation buffers between calls: a repeated call with the same scene costs the hash, the kernels and one download.
+// out_f32 != nullptr: (sum r, sum g, sum b, samples) as floats, 16 bytes per pixel; out_u8 != nullptr: write_color on the device
+// from the exact int64 sums, 3 bytes per pixel.
+static int render_host(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, float* out_f32, uint8_t* out_u8, rtw_stats* stats) {
+  if (!desc || !cfg || (!out_f32 && !out_u8)) return fail("rtw_render: null argument");
   if (cfg->width < 2 || cfg->height < 2) return fail("render: width and height must be >= 2 (pixel mapping divides by W-1, H-1)");
   if (cfg->row_tile_count > 1) return fail("rtw_render: the row-tile split goes through rtw_render_device or rtw_render_multi_gpu");
   const double t_start = now_ms();
-  std::lock_guard<std::mutex> lock(g_cache_mutex);  // also serialises host-buffer renders per process (not re-entrant per device)
-  if (cfg->device < 0 || cfg->device >= 64) return fail("rtw_render: device ordinal out of range");
-  if (!g_cache[cfg->device]) g_cache[cfg->device] = new RenderCache();
-  RenderCache& rc_ = *g_cache[cfg->device];
-  rtw_scene scene_obj;
-  rtw_scene* sc = &scene_obj;
-  if (int rc = flatten_and_upload(desc, cfg->device, sc, &rc_.arena)) return rc;
+  rtw::prewarm_join();
+  rtw::DeviceSlot* slot = rtw::device_slot(cfg->device);
+  if (!slot) return fail("rtw_render: device ordinal out of range");
+  std::lock_guard<std::mutex> lock(slot->m);   // host-buffer renders are serialised per device
+  if (int rc = rtw::slot_prepare(slot)) return rc;
+  HostFlat hf;
+  bool hit = false;
+  const bool use_cache = (cfg->flags & RTW_FLAG_NO_SCENE_CACHE) == 0;
+  if (desc->nprims < 0 || desc->nmats < 0 || (desc->nprims > 0 && !desc->prims) || (desc->nmats > 0 && !desc->mats)) return fail("rtw_scene_upload: invalid scene description");
+  const uint64_t key = rtw::scene_key(desc);
+  if (int rc = rtw::slot_set_scene(slot, desc, key, use_cache, &hf, nullptr, &hit)) return rc;
   const double t_up = now_ms();
   const size_t npix = static_cast<size_t>(cfg->width) * static_cast<size_t>(cfg->height);
-  if (rc_.npix < npix) {
-    RTW_CUDA(rc_.fx.alloc(npix * 4));
-    RTW_CUDA(rc_.out.alloc(npix * 4));
-    rc_.npix = npix;
-  }
-  RTW_CUDA(cudaMemsetAsync(rc_.fx.p, 0, npix * 4 * sizeof(long long)));
+  RTW_CUDA(slot->fx.reserve(npix * 4));
+  cudaStream_t stream = slot->stream;
+  RTW_CUDA(cudaMemsetAsync(slot->fx.p, 0, npix * 4 * sizeof(long long), stream));
   rtw_stats st{};
-  if (int rc = rtw_render_device(sc, cfg, reinterpret_cast<int64_t*>(rc_.fx.p), nullptr, &st)) return rc;
-  if (int rc = rtw_accum_to_float(reinterpret_cast<const int64_t*>(rc_.fx.p), rc_.out.p, static_cast<int64_t>(npix), cfg->device, nullptr)) return rc;
+  if (int rc = rtw_render_device(&slot->scene, cfg, reinterpret_cast<int64_t*>(slot->fx.p), stream, &st)) return rc;
   const double t_d0 = now_ms();
-  RTW_CUDA(cudaMemcpy(accum_rgba, rc_.out.p, npix * 4 * sizeof(float), cudaMemcpyDeviceToHost));
+  int launches = 1;
+  if (out_f32) {
+    RTW_CUDA(slot->out_f32.reserve(npix * 4));
+    if (int rc = rtw_accum_to_float(reinterpret_cast<const int64_t*>(slot->fx.p), slot->out_f32.p, static_cast<int64_t>(npix), cfg->device, stream)) return rc;
+    RTW_CUDA(cudaMemcpyAsync(out_f32, slot->out_f32.p, npix * 4 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    ++launches;
+  }
+  if (out_u8) {
+    RTW_CUDA(slot->out_u8.reserve(npix * 3));
+    if (int rc = rtw_finalize_rgb8_device(reinterpret_cast<const int64_t*>(slot->fx.p), static_cast<int64_t>(npix), cfg->sample_end - cfg->sample_begin,
+                                          cfg->device, stream, slot->out_u8.p)) return rc;
+    RTW_CUDA(cudaMemcpyAsync(out_u8, slot->out_u8.p, npix * 3, cudaMemcpyDeviceToHost, stream));
+    ++launches;
+  }
+  RTW_CUDA(cudaStreamSynchronize(stream));
   const double t_end = now_ms();
   if (stats) {
     *stats = st;
     stats->h2d_ms = t_up - t_start;
     stats->d2h_ms = t_end - t_d0;
     stats->total_ms = t_end - t_start;
-    stats->launches = 2;
+    stats->launches = launches;
+    stats->scene_cache_hit = hit ? 1 : 0;
   }
   return 0;
+}
+
+int rtw_render(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, float* accum_rgba, rtw_stats* stats) {
+  if (!accum_rgba) return fail("rtw_render: null argument");
+  return render_host(desc, cfg, accum_rgba, nullptr, stats);
+}
+
+int rtw_render_rgb8(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, uint8_t* rgb8, rtw_stats* stats) {
+  if (!rgb8) return fail("rtw_render_rgb8: null argument");
+  return render_host(desc, cfg, nullptr, rgb8, stats);
 }
 
 int rtw_finalize_rgb8(const float* accum_rgba, int64_t npixels, int32_t spp, int32_t device, uint8_t* rgb8) {
@@ -721,6 +824,3 @@ int rtw_fp32_peak(int32_t device, double seconds, double* tflops, double* sm_mhz
 }
 
 }  // extern "C"
-
-// error hook for the other translation units of the library
-extern "C" int rtw_set_error_(const char* msg) { return fail(msg ? msg : "unknown error"); }

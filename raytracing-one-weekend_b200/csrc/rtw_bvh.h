@@ -69,7 +69,7 @@ class BvhBuilder {
       return;
     }
     nodes_.push_back(PackedNode{});
-    build_node(0, 0, n, rb);
+    build_node(0, 0, n, rb, 0);
   }
 
   // a child that is never entered (inverted box); its code must still decode harmlessly
@@ -293,16 +293,17 @@ class BvhBuilder {
   }
 
   // returns child code for [begin,end): either a leaf code or the index of a freshly built inner node
-  int32_t build_child(size_t begin, size_t end, const Box3& box) {
+  int32_t build_child(size_t begin, size_t end, const Box3& box, int depth) {
     if (end - begin <= static_cast<size_t>(kMaxLeaf)) return make_leaf(begin, end);
     const int32_t idx = static_cast<int32_t>(nodes_.size());
     nodes_.push_back(PackedNode{});
-    build_node(idx, begin, end, box);
+    build_node(idx, begin, end, box, depth);
     return idx;
   }
 
-  void build_node(int32_t idx, size_t begin, size_t end, const Box3& box) {
+  void build_node(int32_t idx, size_t begin, size_t end, const Box3& box, int depth) {
     (void)box;
+    note_depth(depth + 1);
     // centroid bounds
     float clo[3], chi[3];
     for (int k = 0; k < 3; ++k) { clo[k] = std::numeric_limits<float>::infinity(); chi[k] = -clo[k]; }
@@ -332,8 +333,17 @@ class BvhBuilder {
       }
     }
     size_t mid;
-    if (best_axis < 0) {
-      mid = begin + (end - begin) / 2;  // all centroids coincide: split the list in half
+    if (best_axis < 0 || depth >= kSahDepthLimit) {
+      // all centroids coincide, or SAH keeps peeling a few primitives per level on a pathological distribution: split the list
+      // in half, which bounds the depth by kSahDepthLimit + log2(n) < kBvhStack like the single-primitive-leaf builder does
+      mid = begin + (end - begin) / 2;
+      if (best_axis >= 0) {
+        int ax = 0;
+        if (chi[1] - clo[1] > chi[ax] - clo[ax]) ax = 1;
+        if (chi[2] - clo[2] > chi[ax] - clo[ax]) ax = 2;
+        std::nth_element(order_.begin() + begin, order_.begin() + mid, order_.begin() + end,
+                         [&](uint32_t a, uint32_t b) { return cent_[3 * a + ax] < cent_[3 * b + ax]; });
+      }
     } else {
       const float ext = chi[best_axis] - clo[best_axis];
       const float scale = kBins / ext;
@@ -348,8 +358,8 @@ class BvhBuilder {
       if (mid == begin || mid == end) mid = begin + (end - begin) / 2;
     }
     const Box3 lb = range_box(begin, mid), rb = range_box(mid, end);
-    const int32_t lc = build_child(begin, mid, lb);
-    const int32_t rc = build_child(mid, end, rb);
+    const int32_t lc = build_child(begin, mid, lb, depth + 1);
+    const int32_t rc = build_child(mid, end, rb, depth + 1);
     PackedNode nd{};
     set_child(nd, 0, lb, lc);
     set_child(nd, 1, rb, rc);

@@ -13,6 +13,7 @@ constexpr uint32_t kGroupPixels = 128;  // pixels per work unit: a 16 x 8 tile o
 constexpr double kBigRadius = 100.0;    // |r| >= this: sphere leaves the fp32 tables and is tested in fp64
 
 enum : int { kCtrWork = 0, kCtrRays = 1, kCtrPaths = 2, kCtrSphereTests = 3, kCtrCandidates = 4, kCtrNodes = 5, kCtrTriTests = 6, kCtrCount = 8 };
+constexpr int kCtrSlots = 64;  // counter blocks per uploaded scene: one per launch in flight (rtw_host.h)
 
 struct SmemLayout {  // byte offsets into dynamic shared memory and sizes of the staged tables (filled by launch_render)
   uint32_t nodes, refs, sa, sb, tri, records;
@@ -92,6 +93,7 @@ cudaError_t launch_untile(const long long* gathered, long long* full, uint32_t w
                           uint32_t local_rows, cudaStream_t stream);
 cudaError_t launch_accum_to_float(const long long* fx, float* out, long long npix, cudaStream_t stream);
 cudaError_t launch_finalize_rgb8(const float* acc, uint8_t* rgb, long long npix, int spp, cudaStream_t stream);
+cudaError_t launch_finalize_rgb8_fx(const long long* fx, uint8_t* rgb, long long npix, int spp, cudaStream_t stream);
 cudaError_t launch_debug_scatter(long long n, const int* kind, const float* fuzz, const float* ior, const float* dir_in, const float* normal,
                                  const uint8_t* front, const float* ball, const float* coin, float* out_dir, float* out_att,
                                  const float* albedo, uint8_t* scattered, cudaStream_t stream);

@@ -1197,6 +1197,19 @@ __global__ void k_finalize_rgb8(const float4* __restrict__ acc, uint8_t* __restr
   }
 }
 
+// write_color straight from the exact int64 fixed-point sums (no float rounding of the sum in between): what the drop-in prints
+__global__ void k_finalize_rgb8_fx(const long long* __restrict__ fx, uint8_t* __restrict__ rgb, long long npix, double spp) {
+  const long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (k >= npix) return;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    // sum * 2^-32 is exact in double (sums stay below 2^53 units up to 2 M samples per pixel); then c / spp and sqrt as render.cpp:14
+    const double c = sqrt(static_cast<double>(fx[4 * k + ch]) * (1.0 / 4294967296.0) / spp);
+    const double cl = c < 0.0 ? 0.0 : (c > 0.999 ? 0.999 : c);
+    rgb[3 * k + ch] = static_cast<uint8_t>(static_cast<int>(256 * cl));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Unit hooks
 // ---------------------------------------------------------------------------------------------------------
@@ -1378,6 +1391,10 @@ cudaError_t launch_accum_to_float(const long long* fx, float* out, long long npi
 cudaError_t launch_finalize_rgb8(const float* acc, uint8_t* rgb, long long npix, int spp, cudaStream_t stream) {
   k_finalize_rgb8<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(acc), rgb, npix,
                                                                                   static_cast<double>(spp));
+  return cudaGetLastError();
+}
+cudaError_t launch_finalize_rgb8_fx(const long long* fx, uint8_t* rgb, long long npix, int spp, cudaStream_t stream) {
+  k_finalize_rgb8_fx<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, stream>>>(fx, rgb, npix, static_cast<double>(spp));
   return cudaGetLastError();
 }
 cudaError_t launch_debug_scatter(long long n, const int* kind, const float* fuzz, const float* ior, const float* dir_in, const float* normal,

@@ -1,191 +1,226 @@
-// rtw_multi.cu -- single-process multi-GPU driver behind rtw_render_multi_gpu (include/rtw_b200.h).
-// Replaces the reference's thread fan-out + image sum (render.cpp:169-180): samples-per-pixel are
-// split over the GPUs (global sample index keys the Philox stream, so the union of samples does not depend on the
-// split), each GPU renders into its own int64 fixed-point accumulation buffer, and ONE ncclReduce(sum, int64)
-// over NVLink combines them on device 0.  Integer sums are exact, so the result is bit-identical to one GPU.
-// NCCL is loaded with dlopen at first use so that processes which already carry their own NCCL (PyTorch) never
-// see a second copy just because they loaded this library.
-#include <dlfcn.h>
-#include <unistd.h>
-
+// rtw_multi.cu -- single-process multi-GPU driver behind rtw_render_multi_gpu / rtw_render_multi_gpu_rgb8 (include/rtw_b200.h).
+// Replaces the reference's thread fan-out + image sum (render.cpp:169-180): samples-per-pixel are split over the GPUs
+// (the global sample index keys the Philox stream, so the union of samples does not depend on the split), each GPU renders into
+// its own int64 fixed-point accumulation buffer, and the buffers are combined over NVLink peer memory by ONE kernel per GPU:
+// GPU g owns the g-th slice of the image, reads that slice of every GPU's buffer with peer loads (a reduce-scatter by direct
+// loads through NVSwitch), sums the integers, converts (float sums, or write_color -> rgb8) and downloads its slice into the
+// caller's host buffer over its own PCIe link.  Integer sums are exact, so the result is bit-identical to one GPU.
+// No communicator, no library: the only set-up is cudaDeviceEnablePeerAccess, done once per device pair.  (The one-process-per-GPU
+// launch of bench.py / torchrun combines the same buffers with one NCCL reduce instead.)
+// The row-tile alternative needs no exchange at all: every GPU converts and downloads its own tiles.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
-
 #include <cstring>
 #include <string>
 #include <thread>
 #include <vector>
 
-#include "rtw_internal.h"
+#include "rtw_host.h"
 
 namespace {
 
-typedef struct ncclComm* ncclComm_t;
-enum { kNcclInt64 = 4, kNcclSum = 0 };
-
-struct NcclApi {
-  void* lib = nullptr;
-  int (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
-  int (*CommDestroy)(ncclComm_t) = nullptr;
-  int (*GroupStart)() = nullptr;
-  int (*GroupEnd)() = nullptr;
-  int (*Reduce)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
-  int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
-  int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
-  const char* (*GetErrorString)(int) = nullptr;
-  std::string error;
-  bool load() {
-    if (lib) return true;
-    const char* names[] = {"libnccl.so.2", "libnccl.so"};
-    for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
-    if (!lib) { error = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return false; }
-#define RTW_SYM(field, name)                                           \
-  field = reinterpret_cast<decltype(field)>(dlsym(lib, name));         \
-  if (!field) { error = std::string("NCCL symbol missing: ") + name; return false; }
-    RTW_SYM(CommInitAll, "ncclCommInitAll");
-    RTW_SYM(CommDestroy, "ncclCommDestroy");
-    RTW_SYM(GroupStart, "ncclGroupStart");
-    RTW_SYM(GroupEnd, "ncclGroupEnd");
-    RTW_SYM(Reduce, "ncclReduce");
-    RTW_SYM(Send, "ncclSend");
-    RTW_SYM(Recv, "ncclRecv");
-    RTW_SYM(GetErrorString, "ncclGetErrorString");
-#undef RTW_SYM
-    return true;
-  }
+constexpr int kMaxGpus = 16;
+struct PeerBufs {
+  const longlong4* p[kMaxGpus];
+  int n;
 };
-NcclApi g_nccl;
 
-}  // namespace
+// One thread per pixel of this GPU's slice: sum the n accumulation buffers (n - 1 of them in peer memory), then either the float
+// accumulation pixel or write_color (render.cpp:11-20) of the exact sum.  out index = pixel - pix0 (slice-local).
+__global__ void __launch_bounds__(256) k_combine_peers(const PeerBufs b, long long pix0, long long count, float4* __restrict__ out_f32,
+                                                      uint8_t* __restrict__ out_u8, double spp) {
+  const long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (k >= count) return;
+  long long r = 0, g = 0, bl = 0, w = 0;
+  for (int i = 0; i < b.n; ++i) {
+    const longlong4 v = b.p[i][pix0 + k];
+    r += v.x; g += v.y; bl += v.z; w += v.w;
+  }
+  const double s = 1.0 / 4294967296.0;
+  if (out_f32) out_f32[k] = make_float4(static_cast<float>(r * s), static_cast<float>(g * s), static_cast<float>(bl * s), static_cast<float>(w));
+  if (out_u8) {
+    const double c[3] = {sqrt(r * s / spp), sqrt(g * s / spp), sqrt(bl * s / spp)};
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const double cl = c[ch] < 0.0 ? 0.0 : (c[ch] > 0.999 ? 0.999 : c[ch]);
+      out_u8[3 * k + ch] = static_cast<uint8_t>(static_cast<int>(256 * cl));
+    }
+  }
+}
 
-extern "C" int rtw_set_error_(const char* msg);  // defined below (thread-local error lives in rtw_abi.cu)
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
 
-extern "C" int rtw_render_multi_gpu(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, int32_t ngpus, float* accum_rgba,
-                                    rtw_stats* stats) {
-  if (!desc || !cfg || !accum_rgba) return rtw_set_error_("rtw_render_multi_gpu: null argument");
-  if (ngpus < 1) return rtw_set_error_("rtw_render_multi_gpu: ngpus must be >= 1");
-  if (ngpus == 1) return rtw_render(desc, cfg, accum_rgba, stats);
+int multi_host(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, int32_t ngpus, float* out_f32, uint8_t* out_u8, rtw_stats* stats) {
+  using rtw::fail;
+  if (!desc || !cfg || (!out_f32 && !out_u8)) return fail("rtw_render_multi_gpu: null argument");
+  if (ngpus < 1) return fail("rtw_render_multi_gpu: ngpus must be >= 1");
+  if (ngpus == 1) return out_f32 ? rtw_render(desc, cfg, out_f32, stats) : rtw_render_rgb8(desc, cfg, out_u8, stats);
   int ndev = 0;
   if (rtw_device_count(&ndev) != 0) return 2;
-  if (ngpus > ndev) return rtw_set_error_("rtw_render_multi_gpu: more GPUs requested than present");
+  if (ngpus > ndev) return fail("rtw_render_multi_gpu: more GPUs requested than present");
+  if (ngpus > kMaxGpus) return fail("rtw_render_multi_gpu: at most 16 GPUs");
   const int S = cfg->sample_end - cfg->sample_begin;
   const bool rows = (cfg->flags & RTW_FLAG_SPLIT_ROWS) != 0;
   const int tile_rows = cfg->row_tile_rows > 0 ? cfg->row_tile_rows : 8;
-  if (S <= 0 || (!rows && S % ngpus != 0)) return rtw_set_error_("rtw_render_multi_gpu: samples must split evenly over the GPUs (reference analogue: render.cpp:174)");
-  if (cfg->width < 2 || cfg->height < 2) return rtw_set_error_("render: width and height must be >= 2");
-  if (!g_nccl.load()) return rtw_set_error_(g_nccl.error.c_str());
+  if (S <= 0 || cfg->sample_begin < 0) return fail("render: empty sample range");
+  if (cfg->width < 2 || cfg->height < 2) return fail("render: width and height must be >= 2");
+  if (desc->nprims < 0 || desc->nmats < 0 || (desc->nprims > 0 && !desc->prims) || (desc->nmats > 0 && !desc->mats)) return fail("rtw_scene_upload: invalid scene description");
+  const double t_start = now_ms();
+  rtw::prewarm_join();
 
   const size_t npix = static_cast<size_t>(cfg->width) * static_cast<size_t>(cfg->height);
-  // row-tile split: every GPU fills a packed buffer of local_rows rows; device 0 additionally holds the gathered buffers
-  const size_t local_pix = rows ? static_cast<size_t>(rtw_row_tile_local_rows(cfg->height, tile_rows, ngpus)) * static_cast<size_t>(cfg->width) : npix;
-  long long* gathered = nullptr;
-  std::vector<rtw_scene*> scenes(ngpus, nullptr);
-  std::vector<long long*> fx(ngpus, nullptr);
-  std::vector<cudaStream_t> streams(ngpus, nullptr);
-  std::vector<ncclComm_t> comms(ngpus, nullptr);
-  std::vector<int> devs(ngpus);
+  const int local_rows = rows ? rtw_row_tile_local_rows(cfg->height, tile_rows, ngpus) : cfg->height;
+  const size_t local_pix = static_cast<size_t>(local_rows) * static_cast<size_t>(cfg->width);
+  const uint64_t key = rtw::scene_key(desc);
+  const bool use_cache = (cfg->flags & RTW_FLAG_NO_SCENE_CACHE) == 0;
+
+  std::vector<rtw::DeviceSlot*> slots(ngpus, nullptr);
+  for (int g = 0; g < ngpus; ++g) {
+    slots[g] = rtw::device_slot(g);
+    if (!slots[g]) return 1;
+  }
+  // every GPU's slot stays locked for the whole call (in device order: no deadlock with a concurrent multi-GPU call)
+  std::vector<std::unique_lock<std::mutex>> locks;
+  for (int g = 0; g < ngpus; ++g) locks.emplace_back(slots[g]->m);
+
+  rtw::HostFlat flat;       // flattened at most once, by whichever GPU thread misses its cache first
+  std::mutex flat_mutex;
   std::vector<int> rcs(ngpus, 0);
   std::vector<std::string> errs(ngpus);
   std::vector<rtw_stats> sts(ngpus);
-  for (int g = 0; g < ngpus; ++g) devs[g] = g;
+  std::vector<char> hits(ngpus, 0);
+  std::vector<double> t_scene(ngpus, 0.0);
 
-  auto cleanup = [&]() {
-    for (int g = 0; g < ngpus; ++g) {
-      cudaSetDevice(g);
-      if (comms[g]) g_nccl.CommDestroy(comms[g]);
-      if (fx[g]) cudaFree(fx[g]);
-      if (streams[g]) cudaStreamDestroy(streams[g]);
-      if (scenes[g]) rtw_scene_free(scenes[g]);
+  // one host thread per GPU: context, peer access, scene (cached), zero, render its shard (waits for its kernel)
+  auto work = [&](int g) {
+    rtw::DeviceSlot* s = slots[g];
+    auto bail = [&](int rc) { rcs[g] = rc ? rc : 1; errs[g] = rtw_last_error(); };
+    if (int rc = rtw::slot_prepare(s)) return bail(rc);
+    if (!rows) {
+      for (int q = 0; q < ngpus; ++q) {
+        if (q == g || (s->peer_enabled_mask >> q & 1)) continue;
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, g, q);
+        if (!can) { fail("rtw_render_multi_gpu: GPUs " + std::to_string(g) + " and " + std::to_string(q) + " have no peer access (NVLink / NVSwitch needed for the sample split; use the row split)"); return bail(1); }
+        const cudaError_t e = cudaDeviceEnablePeerAccess(q, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { rtw::fail_cuda("cudaDeviceEnablePeerAccess", e); return bail(2); }
+        cudaGetLastError();
+        s->peer_enabled_mask |= 1 << q;
+      }
     }
+    bool hit = false;
+    if (int rc = rtw::slot_set_scene(s, desc, key, use_cache, &flat, &flat_mutex, &hit)) return bail(rc);
+    hits[g] = hit ? 1 : 0;
+    t_scene[g] = now_ms();
+    if (cudaSuccess != s->fx.reserve(std::max(npix, local_pix) * 4)) { fail("rtw_render_multi_gpu: device allocation failed"); return bail(2); }
+    if (cudaSuccess != cudaMemsetAsync(s->fx.p, 0, (rows ? local_pix : npix) * 4 * sizeof(long long), s->stream)) { fail("cudaMemsetAsync failed"); return bail(2); }
+    rtw_render_cfg c = *cfg;
+    c.device = g;
+    if (rows) {
+      c.row_tile_rows = tile_rows; c.row_tile_count = ngpus; c.row_tile_index = g;
+    } else {
+      // samples split as evenly as possible: the first S % ngpus GPUs render one more (the global sample index keys Philox)
+      const int q = S / ngpus, r = S % ngpus;
+      c.sample_begin = cfg->sample_begin + g * q + std::min(g, r);
+      c.sample_end = c.sample_begin + q + (g < r ? 1 : 0);
+    }
+    std::memset(&sts[g], 0, sizeof(rtw_stats));
+    if (c.sample_end > c.sample_begin) {
+      if (int rc = rtw_render_device(&s->scene, &c, reinterpret_cast<int64_t*>(s->fx.p), s->stream, &sts[g])) return bail(rc);
+    } else if (cudaStreamSynchronize(s->stream) != cudaSuccess) { fail("stream sync failed"); return bail(2); }
   };
-
-  // NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION/INFO is set; stdout is the image (P3 text) for the
-  // drop-in render(), so route fd 1 to stderr while the communicators are created.
-  std::fflush(stdout);
-  const int saved_stdout = dup(1);
-  if (saved_stdout >= 0) dup2(2, 1);
-  int nrc = g_nccl.CommInitAll(comms.data(), ngpus, devs.data());
-  if (saved_stdout >= 0) { std::fflush(stdout); dup2(saved_stdout, 1); close(saved_stdout); }
-  if (nrc != 0) { cleanup(); return rtw_set_error_((std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(nrc)).c_str()); }
-
-  // one host thread per GPU: upload, zero, render its sample shard
-  std::vector<std::thread> th;
-  for (int g = 0; g < ngpus; ++g) {
-    th.emplace_back([&, g]() {
-      rtw_render_cfg c = *cfg;
-      c.device = g;
-      if (rows) {
-        c.row_tile_rows = tile_rows; c.row_tile_count = ngpus; c.row_tile_index = g;
-      } else {
-        c.sample_begin = cfg->sample_begin + g * (S / ngpus);
-        c.sample_end = c.sample_begin + S / ngpus;
-      }
-      rcs[g] = rtw_scene_upload(desc, g, &scenes[g]);
-      if (rcs[g]) { errs[g] = rtw_last_error(); return; }
-      if (cudaStreamCreate(&streams[g]) != cudaSuccess || cudaMalloc(reinterpret_cast<void**>(&fx[g]), std::max(npix, local_pix) * 4 * sizeof(long long)) != cudaSuccess ||
-          cudaMemsetAsync(fx[g], 0, local_pix * 4 * sizeof(long long), streams[g]) != cudaSuccess) {
-        rcs[g] = 2; errs[g] = "device allocation failed"; return;
-      }
-      rcs[g] = rtw_render_device(scenes[g], &c, reinterpret_cast<int64_t*>(fx[g]), streams[g], &sts[g]);
-      if (rcs[g]) errs[g] = rtw_last_error();
-    });
+  {
+    std::vector<std::thread> th;
+    for (int g = 1; g < ngpus; ++g) th.emplace_back(work, g);
+    work(0);
+    for (auto& t : th) t.join();
   }
-  for (auto& t : th) t.join();
   for (int g = 0; g < ngpus; ++g)
-    if (rcs[g]) { cleanup(); return rtw_set_error_(("GPU " + std::to_string(g) + ": " + errs[g]).c_str()); }
+    if (rcs[g]) return fail("GPU " + std::to_string(g) + ": " + errs[g]);
+  const double t_rendered = now_ms();
 
-  if (!rows) {
-    // the one collective of the path: sum of the accumulation buffers onto device 0 (in place on the root)
-    g_nccl.GroupStart();
-    for (int g = 0; g < ngpus; ++g) {
-      cudaSetDevice(g);
-      nrc = g_nccl.Reduce(fx[g], fx[g], npix * 4, kNcclInt64, kNcclSum, 0, comms[g], streams[g]);
-      if (nrc != 0) break;
-    }
-    const int nrc2 = g_nccl.GroupEnd();
-    if (nrc != 0 || nrc2 != 0) { cleanup(); return rtw_set_error_((std::string("ncclReduce: ") + g_nccl.GetErrorString(nrc ? nrc : nrc2)).c_str()); }
-  } else {
-    // row-tile alternative: gather the packed buffers on device 0 (send/recv pairs in one group), then put the tiles in place
-    cudaSetDevice(0);
-    if (cudaMalloc(reinterpret_cast<void**>(&gathered), static_cast<size_t>(ngpus) * local_pix * 4 * sizeof(long long)) != cudaSuccess) {
-      cleanup(); return rtw_set_error_("cudaMalloc (gather buffer) failed");
-    }
-    g_nccl.GroupStart();
-    for (int g = 0; g < ngpus && nrc == 0; ++g) {
-      cudaSetDevice(g);
-      nrc = g_nccl.Send(fx[g], local_pix * 4, kNcclInt64, 0, comms[g], streams[g]);
-      if (nrc == 0) { cudaSetDevice(0); nrc = g_nccl.Recv(gathered + static_cast<size_t>(g) * local_pix * 4, local_pix * 4, kNcclInt64, g, comms[0], streams[0]); }
-    }
-    const int nrc2 = g_nccl.GroupEnd();
-    if (nrc != 0 || nrc2 != 0) { cudaSetDevice(0); cudaFree(gathered); cleanup(); return rtw_set_error_((std::string("ncclSend/Recv: ") + g_nccl.GetErrorString(nrc ? nrc : nrc2)).c_str()); }
-    cudaSetDevice(0);
-    if (rtw_untile_accum(reinterpret_cast<const int64_t*>(gathered), reinterpret_cast<int64_t*>(fx[0]), cfg->width, cfg->height, tile_rows, ngpus, 0, streams[0]) != 0) {
-      cudaFree(gathered); cleanup(); return 2;
+  // ---- combine + convert + download: every GPU handles its own part of the image ------------------------------------------------------
+  const double spp = static_cast<double>(S);
+  int launches = 0;
+  for (int g = 0; g < ngpus; ++g) {
+    rtw::DeviceSlot* s = slots[g];
+    RTW_CUDA(cudaSetDevice(g));
+    if (!rows) {
+      const long long pix0 = static_cast<long long>(npix * g / ngpus), pix1 = static_cast<long long>(npix * (g + 1) / ngpus), cnt = pix1 - pix0;
+      if (cnt <= 0) continue;
+      PeerBufs pb{};
+      pb.n = ngpus;
+      for (int q = 0; q < ngpus; ++q) pb.p[q] = reinterpret_cast<const longlong4*>(slots[(g + q) % ngpus]->fx.p);  // own buffer first, peers staggered
+      if (out_f32) RTW_CUDA(s->out_f32.reserve(static_cast<size_t>(cnt) * 4));
+      if (out_u8) RTW_CUDA(s->out_u8.reserve(static_cast<size_t>(cnt) * 3));
+      k_combine_peers<<<static_cast<unsigned>((cnt + 255) / 256), 256, 0, s->stream>>>(pb, pix0, cnt, out_f32 ? reinterpret_cast<float4*>(s->out_f32.p) : nullptr,
+                                                                                      out_u8 ? s->out_u8.p : nullptr, spp);
+      RTW_CUDA(cudaGetLastError());
+      ++launches;
+      if (out_f32) RTW_CUDA(cudaMemcpyAsync(out_f32 + 4 * pix0, s->out_f32.p, static_cast<size_t>(cnt) * 4 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+      if (out_u8) RTW_CUDA(cudaMemcpyAsync(out_u8 + 3 * pix0, s->out_u8.p, static_cast<size_t>(cnt) * 3, cudaMemcpyDeviceToHost, s->stream));
+    } else {
+      // packed local tiles -> converted in place order, then one copy per tile into its rows of the host image
+      if (out_f32) {
+        RTW_CUDA(s->out_f32.reserve(local_pix * 4));
+        if (int rc = rtw_accum_to_float(reinterpret_cast<const int64_t*>(s->fx.p), s->out_f32.p, static_cast<int64_t>(local_pix), g, s->stream)) return rc;
+      }
+      if (out_u8) {
+        RTW_CUDA(s->out_u8.reserve(local_pix * 3));
+        if (int rc = rtw_finalize_rgb8_device(reinterpret_cast<const int64_t*>(s->fx.p), static_cast<int64_t>(local_pix), S, g, s->stream, s->out_u8.p)) return rc;
+      }
+      ++launches;
+      const int tiles_local = local_rows / tile_rows;
+      for (int k = 0; k < tiles_local; ++k) {
+        const long long row0 = (static_cast<long long>(k) * ngpus + g) * tile_rows;
+        if (row0 >= cfg->height) break;
+        const size_t nrows = static_cast<size_t>(std::min<long long>(tile_rows, cfg->height - row0));
+        const size_t src = static_cast<size_t>(k) * tile_rows * cfg->width, dst = static_cast<size_t>(row0) * cfg->width, n = nrows * cfg->width;
+        if (out_f32) RTW_CUDA(cudaMemcpyAsync(out_f32 + 4 * dst, s->out_f32.p + 4 * src, n * 4 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+        if (out_u8) RTW_CUDA(cudaMemcpyAsync(out_u8 + 3 * dst, s->out_u8.p + 3 * src, n * 3, cudaMemcpyDeviceToHost, s->stream));
+      }
     }
   }
-  for (int g = 0; g < ngpus; ++g) { cudaSetDevice(g); cudaStreamSynchronize(streams[g]); }
-
-  cudaSetDevice(0);
-  float* out = nullptr;
-  int rc = 0;
-  if (cudaMalloc(reinterpret_cast<void**>(&out), npix * 4 * sizeof(float)) != cudaSuccess) rc = rtw_set_error_("cudaMalloc failed");
-  if (!rc) rc = rtw_accum_to_float(reinterpret_cast<const int64_t*>(fx[0]), out, static_cast<int64_t>(npix), 0, streams[0]);
-  if (!rc && cudaMemcpyAsync(accum_rgba, out, npix * 4 * sizeof(float), cudaMemcpyDeviceToHost, streams[0]) != cudaSuccess) rc = rtw_set_error_("D2H failed");
-  if (!rc && cudaStreamSynchronize(streams[0]) != cudaSuccess) rc = rtw_set_error_("stream sync failed");
-  if (out) cudaFree(out);
-  if (gathered) cudaFree(gathered);
-  if (stats && !rc) {
+  for (int g = 0; g < ngpus; ++g) {
+    RTW_CUDA(cudaSetDevice(g));
+    RTW_CUDA(cudaStreamSynchronize(slots[g]->stream));
+  }
+  const double t_end = now_ms();
+  if (stats) {
     std::memset(stats, 0, sizeof *stats);
+    double t_up = t_start;
+    int all_hit = 1;
     for (int g = 0; g < ngpus; ++g) {
       stats->paths += sts[g].paths; stats->rays += sts[g].rays;
       stats->sphere_tests += sts[g].sphere_tests; stats->sphere_candidates += sts[g].sphere_candidates;
       stats->tri_tests += sts[g].tri_tests; stats->node_visits += sts[g].node_visits;
       if (sts[g].kernel_ms > stats->kernel_ms) stats->kernel_ms = sts[g].kernel_ms;  // max over GPUs
+      t_up = std::max(t_up, t_scene[g]);
+      all_hit &= hits[g];
     }
     stats->kernel_used = sts[0].kernel_used;
     stats->bvh_variant = sts[0].bvh_variant;
-    stats->launches = ngpus + 1 + (rows ? 1 : 0);
+    stats->launches = ngpus + launches;
+    stats->h2d_ms = t_up - t_start;          // contexts + peer access + flatten + upload on the slowest GPU
+    stats->d2h_ms = t_end - t_rendered;      // combine + convert + download
+    stats->total_ms = t_end - t_start;
+    stats->scene_cache_hit = all_hit;
   }
-  cleanup();
-  return rc;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int rtw_render_multi_gpu(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, int32_t ngpus, float* accum_rgba, rtw_stats* stats) {
+  if (!accum_rgba) return rtw::fail("rtw_render_multi_gpu: null argument");
+  return multi_host(desc, cfg, ngpus, accum_rgba, nullptr, stats);
+}
+
+extern "C" int rtw_render_multi_gpu_rgb8(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, int32_t ngpus, uint8_t* rgb8, rtw_stats* stats) {
+  if (!rgb8) return rtw::fail("rtw_render_multi_gpu_rgb8: null argument");
+  return multi_host(desc, cfg, ngpus, nullptr, rgb8, stats);
 }

@@ -35,6 +35,13 @@ Handle* guarded(F&& f) {
 }  // namespace
 
 RTWH_API const char* rtwh_last_error() { return g_err.c_str(); }
+RTWH_API const char* rtwh_primitive_model() {   // which of the two primitive models this library was compiled with (primitive-model.h)
+#ifdef RTWEEKEND_USE_VARIANT_PRIMITIVES
+  return "variant";
+#else
+  return "oo";
+#endif
+}
 RTWH_API void rtwh_seed(unsigned seed) { rt::seed_host_rng(seed); }
 RTWH_API double rtwh_random_double() { return rt::random_double(); }
 RTWH_API void rtwh_set_obj_all_shapes(int on) { rt::device_options().obj_all_shapes = on != 0; }

@@ -127,6 +127,8 @@ int main(int argc, char* argv[]) {
   }
 
   if (dry_run) { std::cout << cfg; return 0; }
+  // the CUDA contexts come up on background threads while the scene is built (a cold process pays 0.3-1 s per GPU for them)
+  if (make_mesh.empty()) rtw_prewarm(dev.ngpus > 1 ? 0 : dev.device, dev.ngpus);
 
   if (!make_mesh.empty()) {
     if (!cfg.model) { std::cerr << "--make-mesh needs -l <base.obj>\n"; return 105; }

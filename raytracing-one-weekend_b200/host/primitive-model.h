@@ -1,75 +1,10 @@
-// primitive-model.h -- Sphere / MovingSphere / Triangle and their store.
-// One model instead of the reference's two interchangeable ones (oo-primitives.h, variant-primitives.h selected by
-// primitive-model.h:1-4): constructor signatures and accessor names match both (oo-primitives.h:28,49,76,37-43,60-67) and the
-// store offers the same add<T>(args...) -> T&.  A primitive here is nothing but its flat C-ABI record (rtw_primitive) plus the
-// material it points at: intersection and bounding boxes are computed on the device and in the BVH builder, so the host classes
-// only have to remember their constructor arguments in the form Scene::flatten() hands to rtw_render.
+// primitive-model.h -- selects the primitive container, exactly like the reference's selector (primitive-model.h:1-5):
+// the std::variant model with -DRTWEEKEND_USE_VARIANT_PRIMITIVES, the virtual model otherwise.  Both expose the same
+// names (Sphere, MovingSphere, Triangle, PrimitiveStore_t, MaterialStore_t, detail::flat, detail::material_of) and
+// flatten to identical rtw_primitive arrays (tests/test_host.py::test_variant_and_oo_models_flatten_identically).
 #pragma once
-#include <cstdint>
-#include <vector>
-
-#include "common-model.h"
-
-namespace rtweekend::detail {
-
-class Primitive {
- public:
-  virtual ~Primitive() = default;
-  [[nodiscard]] const Material& material() const { return *material_; }
-  // kind + geometry as the C ABI wants them; the material index is filled in by Scene::flatten
-  [[nodiscard]] const rtw_primitive& flat() const { return record_; }
-
- protected:
-  Primitive(rtw_prim_kind kind, const Material& m) : material_{&m} { record_.kind = kind; }
-  static void store(double (&dst)[3], const point& p) { dst[0] = p.x; dst[1] = p.y; dst[2] = p.z; }
-  static point load(const double (&src)[3]) { return point{src[0], src[1], src[2]}; }
-  rtw_primitive record_{};
-
- private:
-  const Material* material_;
-};
-
-// record_.a = record_.b = centre
-class Sphere final : public Primitive {
- public:
-  Sphere(point center, double radius, const Material& material) : Primitive{RTW_SPHERE, material} {
-    store(record_.a, center); store(record_.b, center); record_.radius = radius;
-  }
-  [[nodiscard]] point center() const { return load(record_.a); }
-  [[nodiscard]] double radius() const { return record_.radius; }
-};
-
-// record_.a = centre when the shutter opens (time 0), record_.b = centre when it closes (time 1), oo-primitives.h:51-52
-class MovingSphere final : public Primitive {
- public:
-  MovingSphere(point c0, point c1, double radius, const Material& material) : Primitive{RTW_MOVING_SPHERE, material} {
-    store(record_.a, c0); store(record_.b, c1); record_.radius = radius;
-  }
-  [[nodiscard]] point center() const { return load(record_.a); }
-  [[nodiscard]] point center(time_t time) const {
-    const point from = load(record_.a), to = load(record_.b);
-    return from + time * (to - from);
-  }
-  [[nodiscard]] double radius() const { return record_.radius; }
-};
-
-// record_.a/b/c = the three vertices in the order given (the winding decides the culled side)
-class Triangle final : public Primitive {
- public:
-  Triangle(point a, point b, point c, const Material& material) : Primitive{RTW_TRIANGLE, material} {
-    store(record_.a, a); store(record_.b, b); store(record_.c, c);
-  }
-  [[nodiscard]] point a() const { return load(record_.a); }
-  [[nodiscard]] point b() const { return load(record_.b); }
-  [[nodiscard]] point c() const { return load(record_.c); }
-};
-
-}  // namespace rtweekend::detail
-
-namespace rtweekend {
-using PrimitiveStore_t = detail::OOStore<detail::Primitive>;
-using MaterialStore_t = detail::OOStore<detail::Material>;
-using detail::MovingSphere;
-using detail::Sphere;
-using detail::Triangle;
-}  // namespace rtweekend
+#ifdef RTWEEKEND_USE_VARIANT_PRIMITIVES
+#include "variant-primitives.h"
+#else
+#include "oo-primitives.h"
+#endif

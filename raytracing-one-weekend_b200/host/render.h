@@ -35,7 +35,7 @@ struct DeviceOptions {
   bool split_rows = false;  // multi-GPU: interleaved row tiles + one gather instead of the sample split + one reduce
   int tile_rows = 8;        // rows per tile of the row split
   bool obj_all_shapes = false;  // -l: take the faces of every shape of the OBJ file, not only shapes[0] as the reference does
-  bool binary_ppm = false;  // P6 (binary) instead of the reference's P3 text; quantised on the device (rtw_finalize_rgb8)
+  bool binary_ppm = false;  // P6 (binary) instead of the reference's P3 text (the pixels are quantised on the device either way)
   std::string checkpoint;   // progressive rendering: file holding the accumulation buffer + sample cursor (see render_progressive)
   int checkpoint_every = 0; // samples per slice between checkpoint writes (0: one slice)
 };
@@ -69,15 +69,25 @@ struct Accum {
   std::vector<float> rgba;             // width*height*4: sum r, sum g, sum b, samples
   rtw_stats stats{};
 };
+struct Image8 {                        // the picture as the reference prints it: write_color (render.cpp:11-20) per channel
+  int width = 0, height = 0, spp = 0;
+  std::vector<std::uint8_t> rgb;       // width*height*3, top row first
+  rtw_stats stats{};
+};
 
 int image_height(const Config& cfg);      // int(width / aspect), render.cpp:137
 int effective_spp(const Config& cfg);     // spp / nthreads * nthreads, render.cpp:174,185
-Accum render_accum(const Scene& world, const Config& cfg);
-void write_ppm(std::ostream& out, const Accum& img);  // render.cpp:11-20,182-186
-void write_ppm_binary(std::ostream& out, const Accum& img, int device = 0);  // same pixels as P6, write_color evaluated on the device
+Accum render_accum(const Scene& world, const Config& cfg);   // linear accumulation buffer (float sums) on the host
+Image8 render_rgb8(const Scene& world, const Config& cfg);   // write_color evaluated on the device from the exact sums: 3 bytes per pixel come back
+void write_ppm(std::ostream& out, const Accum& img);  // render.cpp:11-20,182-186 evaluated on the host from the float sums
+void write_ppm(std::ostream& out, const Image8& img); // P3 text of an already quantised image (same format)
+void write_ppm_binary(std::ostream& out, const Image8& img);  // the same pixels as binary P6
+Image8 quantise(const Accum& img, int device = 0);    // write_color on the device for a host-resident accumulation buffer (rtw_finalize_rgb8)
 // Progressive / resumable accumulation: renders the samples [cursor, spp) in slices of `every`, adding into the
 // buffer stored in `path` (created when absent) and rewriting it after every slice.  Samples are keyed by their global index, so
 // a render resumed from its checkpoint produces the same bytes as the uninterrupted progressive render with the same slice size.
+// Honours DeviceOptions::ngpus; the scene stays on the device(s) between slices (one flatten + BVH build per render); the
+// checkpoint is bound to the scene (rtw_scene_hash), the image size, the depth and the seed.
 Accum render_progressive(const Scene& world, const Config& cfg, const std::string& path, int every);
 void render(const Scene& world, const Config& cfg);   // P3 text on stdout, progress on stderr
 
@@ -86,6 +96,9 @@ std::ostream& operator<<(std::ostream& o, const Config& c);
 
 namespace rtweekend {
 using detail::Accum;
+using detail::Image8;
+using detail::render_rgb8;
+using detail::quantise;
 using detail::Config;
 using detail::device_options;
 using detail::DeviceOptions;

@@ -3,7 +3,7 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 rtw = importlib.import_module("raytracing-one-weekend_b200")
 n = C.c_longlong(0)
-rtw.host().rtwh_make_mesh(b'tests/golden/suzanne.obj', b'/tmp/standin5.obj', 5, 20221018, 0.08, C.byref(n))
+rtw.host().rtwh_make_mesh(b'assets/suzanne.obj', b'/tmp/standin5.obj', 5, 20221018, 0.08, C.byref(n))
 t0 = time.perf_counter(); scene = rtw.mesh_on_ground_scene('/tmp/standin5.obj', 1.7777777777777777); print(f"scene build (OBJ parse + host model + flatten) {time.perf_counter()-t0:.2f} s, {len(scene.prims)} prims")
 import numpy as np
 out = np.zeros((1080, 1920, 4), np.float32)

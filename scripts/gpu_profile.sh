@@ -17,7 +17,7 @@ python -c "
 import importlib,ctypes as C,sys
 sys.path.insert(0,'.')
 rtw=importlib.import_module('raytracing-one-weekend_b200')
-n=C.c_longlong(0); rtw.host().rtwh_make_mesh(b'tests/golden/suzanne.obj', b'/tmp/standin5.obj', 5, 20221018, 0.08, C.byref(n)); print('tris', n.value)
+n=C.c_longlong(0); rtw.host().rtwh_make_mesh(b'assets/suzanne.obj', b'/tmp/standin5.obj', 5, 20221018, 0.08, C.byref(n)); print('tris', n.value)
 "
 prof k2_dragon --kernel bvh --scene /tmp/standin5.obj --spp 4 --depth 20
 prof k2_suzanne --kernel bvh --scene suzanne --spp 8 --depth 20

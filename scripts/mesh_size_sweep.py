@@ -13,7 +13,7 @@ variant = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 R = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 aspect = 1.7777777777777777
 for k in range(R + 1):
-    path = str(ROOT / "tests/golden/suzanne.obj")
+    path = str(ROOT / "assets/suzanne.obj")
     if k > 0:
         out = f"/tmp/suz_r{k}.obj"
         n = C.c_longlong(0)

@@ -22,7 +22,7 @@ aspect = 1.7777777777777777
 if a.scene == "cover":
     scene = rtw.cover_scene(11, aspect)
 elif a.scene == "suzanne":
-    scene = rtw.mesh_on_ground_scene(str(Path(__file__).resolve().parents[1] / "tests/golden/suzanne.obj"), aspect)
+    scene = rtw.mesh_on_ground_scene(str(Path(__file__).resolve().parents[1] / "assets/suzanne.obj"), aspect)
 else:
     scene = rtw.mesh_on_ground_scene(a.scene, aspect)
 H = rtw.image_height(a.width, aspect)

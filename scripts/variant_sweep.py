@@ -25,11 +25,11 @@ aspect = 1.7777777777777777
 if a.scene == "cover":
     scene = rtw.cover_scene(11, aspect)
 elif a.scene == "suzanne":
-    scene = rtw.mesh_on_ground_scene(str(Path(__file__).resolve().parents[1] / "tests/golden/suzanne.obj"), aspect)
+    scene = rtw.mesh_on_ground_scene(str(Path(__file__).resolve().parents[1] / "assets/suzanne.obj"), aspect)
 elif a.scene == "standin":  # 991,232-triangle stand-in for dragon.obj (5 subdivision rounds of suzanne)
     import ctypes as C
     n = C.c_longlong(0)
-    if rtw.host().rtwh_make_mesh(str(Path(__file__).resolve().parents[1] / "tests/golden/suzanne.obj").encode(), b"/tmp/standin5.obj", 5, 20221018, 0.08, C.byref(n)) != 0:
+    if rtw.host().rtwh_make_mesh(str(Path(__file__).resolve().parents[1] / "assets/suzanne.obj").encode(), b"/tmp/standin5.obj", 5, 20221018, 0.08, C.byref(n)) != 0:
         raise RuntimeError(rtw.host().rtwh_last_error().decode())
     scene = rtw.mesh_on_ground_scene("/tmp/standin5.obj", aspect)
 else:

@@ -55,4 +55,4 @@ def golden():
     return load
 
 
-SUZANNE = GOLDEN / "suzanne.obj"
+SUZANNE = ROOT / "assets" / "suzanne.obj"

@@ -23,7 +23,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
-SUZANNE = str(ROOT / "tests" / "golden" / "suzanne.obj")
+SUZANNE = str(ROOT / "assets" / "suzanne.obj")
 
 
 # ------------------------------------------------------------------------------------------------------------------

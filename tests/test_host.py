@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 ROOT = Path(__file__).resolve().parents[1]
-SUZANNE = str(ROOT / "tests" / "golden" / "suzanne.obj")
+SUZANNE = str(ROOT / "assets" / "suzanne.obj")
 
 
 def test_library_exports_every_declared_symbol(rtw):

@@ -9,7 +9,7 @@ import hashlib
 import numpy as np
 import pytest
 
-SUZANNE = str(__import__("pathlib").Path(__file__).resolve().parent / "golden" / "suzanne.obj")
+SUZANNE = str(__import__("pathlib").Path(__file__).resolve().parents[1] / "assets" / "suzanne.obj")
 
 
 def test_host_rng_matches_libstdcxx(port):
