@@ -120,6 +120,11 @@ RTW_API int rtw_device_count(int* count);
 /* Flatten + upload (sphere tables, SAH BVH for meshes/mixed scenes, materials, camera) to `device`. */
 RTW_API int rtw_scene_upload(const rtw_scene_desc* desc, int32_t device, rtw_scene** out);
 RTW_API void rtw_scene_free(rtw_scene* scene);
+/* Replace the contents of an uploaded scene by a new description (re-flatten, re-build, one H2D copy into the same allocation when
+ * it fits).  No render of `scene` may be in flight. */
+RTW_API int rtw_scene_update(rtw_scene* scene, const rtw_scene_desc* desc);
+/* Number of CUDA kernels this library has launched in this process so far (every <<<>>> is counted where it is issued). */
+RTW_API unsigned long long rtw_kernel_launches(void);
 
 /* One-shot render with HOST buffers: upload, render samples [sample_begin,sample_end), download.
  * accum_rgba: width*height*4 floats, (sum r, sum g, sum b, number of samples) per pixel, row 0 = top.

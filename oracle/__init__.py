@@ -142,12 +142,20 @@ class OracleScene:
         self.o._f("scene_camera")(self.h, C.byref(c))
         return c
 
-    def primary_hits(self, width, height, time=0.0):
+    def primary_hits(self, width, height, time=0.0, nthreads=1):
         n = width * height
         pid = np.zeros(n, np.int32)
         t = np.zeros(n)
         nrm = np.zeros((n, 3))
         front = np.zeros(n, np.uint8)
+        if nthreads > 1 and self.o.p == "rtwo_":   # the port can split the rows over threads (big meshes, brute force)
+            fn = self.o._f("primary_hits_mt")
+            fn.argtypes = [_VP, C.c_int, C.c_int, C.c_double, C.c_int, _VP, _VP, _VP, _VP]
+            fn.restype = None
+            fn(self.h, width, height, time, nthreads, pid.ctypes.data_as(_VP), t.ctypes.data_as(_VP), nrm.ctypes.data_as(_VP),
+               front.ctypes.data_as(_VP))
+            self.bvh_vs_bruteforce_disagreements = 0
+            return pid.reshape(height, width), t.reshape(height, width), nrm.reshape(height, width, 3), front.reshape(height, width)
         fn = self.o._f("primary_hits")
         fn.argtypes = [_VP, C.c_int, C.c_int, C.c_double, _VP, _VP, _VP, _VP]
         fn.restype = C.c_int

@@ -533,26 +533,54 @@ static v3 ray_color(const rtwo_scene* s, const ray* r, int max_depth, rsrc* rs, 
 /* ------------------------------------------------------------------------------------------------ */
 /* Public drivers                                                                                     */
 /* ------------------------------------------------------------------------------------------------ */
-void rtwo_primary_hits(const rtwo_scene* s, int width, int height, double time, int32_t* id, double* t,
-                       double* nrm, uint8_t* front) {
-  rtwo_camera_params cp = s->cp;
-  cp.aperture = 0.0; cp.t0 = time; cp.t1 = time;
-  camera cam = make_camera(&cp);
-  for (int i = 0; i < height; ++i) {
-    int from_top_i = height - i - 1;
-    for (int j = 0; j < width; ++j) {
-      double u = (j + 0.5) / (width - 1);
-      double v = (from_top_i + 0.5) / (height - 1);
-      ray r = camera_ray(&cam, u, v, V(0, 0, 0), time);
-      size_t k = (size_t)i * (size_t)width + (size_t)j;
+typedef struct {
+  const rtwo_scene* s; const camera* cam; int width, height, row0, row1; double time;
+  int32_t* id; double* t; double* nrm; uint8_t* front;
+} primary_job;
+
+static void* primary_worker(void* arg) {
+  primary_job* jb = (primary_job*)arg;
+  for (int i = jb->row0; i < jb->row1; ++i) {
+    int from_top_i = jb->height - i - 1;
+    for (int j = 0; j < jb->width; ++j) {
+      double u = (j + 0.5) / (jb->width - 1);
+      double v = (from_top_i + 0.5) / (jb->height - 1);
+      ray r = camera_ray(jb->cam, u, v, V(0, 0, 0), jb->time);
+      size_t k = (size_t)i * (size_t)jb->width + (size_t)j;
       hitrec h;
-      if (closest_hit(s, &r, &h)) {
-        id[k] = h.prim; t[k] = h.t; nrm[3 * k] = h.n.x; nrm[3 * k + 1] = h.n.y; nrm[3 * k + 2] = h.n.z; front[k] = (uint8_t)h.front;
+      if (closest_hit(jb->s, &r, &h)) {
+        jb->id[k] = h.prim; jb->t[k] = h.t; jb->nrm[3 * k] = h.n.x; jb->nrm[3 * k + 1] = h.n.y; jb->nrm[3 * k + 2] = h.n.z;
+        jb->front[k] = (uint8_t)h.front;
       } else {
-        id[k] = -1; t[k] = 0; nrm[3 * k] = nrm[3 * k + 1] = nrm[3 * k + 2] = 0; front[k] = 0;
+        jb->id[k] = -1; jb->t[k] = 0; jb->nrm[3 * k] = jb->nrm[3 * k + 1] = jb->nrm[3 * k + 2] = 0; jb->front[k] = 0;
       }
     }
   }
+  return NULL;
+}
+
+/* rows split over nthreads (the rays are independent; brute force over a million triangles needs the cores) */
+void rtwo_primary_hits_mt(const rtwo_scene* s, int width, int height, double time, int nthreads, int32_t* id, double* t,
+                          double* nrm, uint8_t* front) {
+  rtwo_camera_params cp = s->cp;
+  cp.aperture = 0.0; cp.t0 = time; cp.t1 = time;
+  camera cam = make_camera(&cp);
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 256) nthreads = 256;
+  if (nthreads > height) nthreads = height > 0 ? height : 1;
+  primary_job jobs[256]; pthread_t th[256];
+  for (int k = 0; k < nthreads; ++k) {
+    primary_job jb = {s, &cam, width, height, (int)((long long)height * k / nthreads), (int)((long long)height * (k + 1) / nthreads), time,
+                      id, t, nrm, front};
+    jobs[k] = jb;
+    pthread_create(&th[k], NULL, primary_worker, &jobs[k]);
+  }
+  for (int k = 0; k < nthreads; ++k) pthread_join(th[k], NULL);
+}
+
+void rtwo_primary_hits(const rtwo_scene* s, int width, int height, double time, int32_t* id, double* t,
+                       double* nrm, uint8_t* front) {
+  rtwo_primary_hits_mt(s, width, height, time, 1, id, t, nrm, front);
 }
 
 /* render.cpp:152-163, one thread */

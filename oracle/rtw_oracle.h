@@ -63,6 +63,8 @@ void rtwo_scene_camera(const rtwo_scene* s, rtwo_camera_params* out);
 void rtwo_scene_camera_derived(const rtwo_scene* s, double out[21]);
 
 /* --- deterministic primary-ray mode (aperture 0, shutter [time,time], pixel centres) --- */
+void rtwo_primary_hits_mt(const rtwo_scene* s, int width, int height, double time, int nthreads, int32_t* id, double* t,
+                          double* nrm, uint8_t* front);
 void rtwo_primary_hits(const rtwo_scene* s, int width, int height, double time, int32_t* id, double* t,
                        double* nrm, uint8_t* front);
 

@@ -106,6 +106,8 @@ ABI = {
     "rtw_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "rtw_scene_upload": (C.c_int, [C.POINTER(SceneDesc), C.c_int32, C.POINTER(_VP)]),
     "rtw_scene_free": (None, [_VP]),
+    "rtw_scene_update": (C.c_int, [_VP, C.POINTER(SceneDesc)]),
+    "rtw_kernel_launches": (C.c_ulonglong, []),
     "rtw_render": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(RenderCfg), _VP, C.POINTER(Stats)]),
     "rtw_render_rgb8": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(RenderCfg), _VP, C.POINTER(Stats)]),
     "rtw_prewarm": (C.c_int, [C.c_int32, C.c_int32]),
@@ -207,6 +209,11 @@ def host_variant() -> C.CDLL:
 def _check(rc: int, what: str) -> None:
     if rc != 0:
         raise RtwError(f"{what} failed ({rc}): {lib().rtw_last_error().decode()}")
+
+
+def kernel_launches() -> int:
+    """Kernels launched by librtw_b200.so in this process so far (counted at every launch site)."""
+    return int(lib().rtw_kernel_launches())
 
 
 def device_count() -> int:
@@ -440,6 +447,17 @@ class DeviceScene:
         _check(lib().rtw_render_device(self._h, C.byref(cfg), _VP(ptr), _VP(stream_ptr),
                                        C.byref(st) if want_stats else None), "rtw_render_device")
         return st.as_dict() if want_stats else None
+
+    def update(self, scene: Scene):
+        """rtw_scene_update: new host arrays -> the same device allocation (flatten + BVH build + one H2D copy)."""
+        self.scene = scene
+        d = scene.desc()
+        _check(lib().rtw_scene_update(self._h, C.byref(d)), "rtw_scene_update")
+
+    def finalize_rgb8(self, accum_fx, rgb8, npixels, spp, stream_ptr=0):
+        """rtw_finalize_rgb8_device: int64 sums -> uint8 rgb (both device tensors)."""
+        _check(lib().rtw_finalize_rgb8_device(_VP(accum_fx.data_ptr()), npixels, spp, self.device, _VP(stream_ptr), _VP(rgb8.data_ptr())),
+               "rtw_finalize_rgb8_device")
 
     def accum_to_float(self, accum_fx, out_f32, npixels, stream_ptr=0):
         _check(lib().rtw_accum_to_float(_VP(accum_fx.data_ptr()), _VP(out_f32.data_ptr()), npixels, self.device,

@@ -424,6 +424,7 @@ int fill_params(const rtw_scene* sc, const rtw_render_cfg* cfg, int mode, unsign
   const unsigned long long warps = static_cast<unsigned long long>(sc->sm_count) * 4ull * (rtw::kRenderThreads / 32);
   unsigned long long su = (static_cast<unsigned long long>(S) * n_groups) / (16ull * warps);
   su = std::min<unsigned long long>(std::max<unsigned long long>(su, 1ull), 8ull);
+  if (const char* e = std::getenv("RTW_SU")) su = std::max(1, std::atoi(e));   // tuning knob (samples per work unit)
   su = std::min<unsigned long long>(su, S);
   p->su = static_cast<uint32_t>(su);
   p->n_chunks = (S + p->su - 1) / p->su;
@@ -521,6 +522,16 @@ int rtw_scene_hash(const rtw_scene_desc* desc, uint64_t* out) {
   *out = rtw::scene_key(desc);
   return 0;
 }
+
+int rtw_scene_update(rtw_scene* scene, const rtw_scene_desc* desc) {
+  if (!scene || !desc) return fail("rtw_scene_update: null argument");
+  HostFlat hf;
+  if (int rc = rtw::flatten_host(desc, &hf)) return rc;
+  // same device, same allocation when the new tables fit (grow-only): no cudaMalloc in the steady state
+  return rtw::upload_flat(hf, desc->camera, desc->nprims, scene->device, scene, &scene->arena, nullptr);
+}
+
+unsigned long long rtw_kernel_launches(void) { return rtw::launch_count(); }
 
 void rtw_scene_free(rtw_scene* scene) {
   if (!scene) return;

@@ -99,5 +99,7 @@ cudaError_t launch_debug_scatter(long long n, const int* kind, const float* fuzz
                                  const float* albedo, uint8_t* scattered, cudaStream_t stream);
 cudaError_t launch_debug_samples(long long n, uint64_t seed, float* ball, float* disk, float* uni, cudaStream_t stream);
 cudaError_t launch_ffma_peak(float* out, int blocks, int iters, cudaStream_t stream);
+void count_launch();                 // other translation units report their own kernels
+unsigned long long launch_count();
 
 }  // namespace rtw

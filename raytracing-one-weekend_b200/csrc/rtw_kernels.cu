@@ -18,6 +18,8 @@
 //
 // Radiance is accumulated as int64 fixed point (2^-32) with RED.ADD.64: integer sums are exact, so the image
 // does not depend on scheduling order or on how samples are sharded over GPUs.
+#include <atomic>
+
 #include "rtw_internal.h"
 
 namespace rtw {
@@ -1255,6 +1257,8 @@ __global__ void __launch_bounds__(256) k_ffma_peak(float* out, int iters, float 
 // ---------------------------------------------------------------------------------------------------------
 // Launchers (host)
 // ---------------------------------------------------------------------------------------------------------
+std::atomic<unsigned long long> g_kernel_launches{0};   // every <<<>>> of this library (rtw_kernel_launches)
+#define RTW_COUNT_LAUNCH() g_kernel_launches.fetch_add(1, std::memory_order_relaxed)
 template <int R, bool STATS>
 static cudaError_t launch_sweep_t(const RenderParams& p, int sm_count, size_t smem, cudaStream_t stream, int* blocks_out) {
   auto kern = k_render_sweep<R, STATS>;
@@ -1270,6 +1274,7 @@ static cudaError_t launch_sweep_t(const RenderParams& p, int sm_count, size_t sm
   if (want < blocks) blocks = want < 1 ? 1 : want;
   if (blocks_out) *blocks_out = static_cast<int>(blocks);
   kern<<<static_cast<unsigned>(blocks), kRenderThreads, smem, stream>>>(p);
+  RTW_COUNT_LAUNCH();
   return cudaGetLastError();
 }
 
@@ -1286,6 +1291,7 @@ static cudaError_t launch_bvh_t(const RenderParams& p, int sm_count, size_t smem
   unsigned long long blocks = static_cast<unsigned long long>(sm_count) * per_sm;
   if (want < blocks) blocks = want < 1 ? 1 : want;
   kern<<<static_cast<unsigned>(blocks), kRenderThreads, smem, stream>>>(p);
+  RTW_COUNT_LAUNCH();
   return cudaGetLastError();
 }
 
@@ -1302,6 +1308,7 @@ static cudaError_t launch_wf_t(const RenderParams& p, int sm_count, size_t smem,
   unsigned long long blocks = static_cast<unsigned long long>(sm_count) * per_sm;
   if (want < blocks) blocks = want < 1 ? 1 : want;
   kern<<<static_cast<unsigned>(blocks), NW * 32, smem, stream>>>(p);
+  RTW_COUNT_LAUNCH();
   return cudaGetLastError();
 }
 
@@ -1367,6 +1374,7 @@ cudaError_t launch_primary_f32(const PrimaryParams& p, int mode, cudaStream_t st
   } else {
     k_primary_f32<1><<<blocks, kRenderThreads, 0, stream>>>(p);
   }
+  RTW_COUNT_LAUNCH();
   return cudaGetLastError();
 }
 
@@ -1374,6 +1382,7 @@ cudaError_t launch_primary_f64(const rtw_primitive* prims, int nprims, const rtw
                                int32_t* prim_id, double* t, double* normal, uint8_t* front, cudaStream_t stream) {
   const unsigned npix = width * height;
   k_primary_f64<<<(npix + 255) / 256, 256, 0, stream>>>(prims, nprims, cam, width, height, time, prim_id, t, normal, front);
+  RTW_COUNT_LAUNCH();
   return cudaGetLastError();
 }
 
@@ -1382,19 +1391,23 @@ cudaError_t launch_untile(const long long* gathered, long long* full, uint32_t w
   const uint32_t npix = width * height;
   k_untile<<<(npix + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const longlong4*>(gathered), reinterpret_cast<longlong4*>(full), width, height,
                                                    tile_rows, count, local_rows);
+  RTW_COUNT_LAUNCH();
   return cudaGetLastError();
 }
 cudaError_t launch_accum_to_float(const long long* fx, float* out, long long npix, cudaStream_t stream) {
   k_accum_to_float<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, stream>>>(fx, reinterpret_cast<float4*>(out), npix);
+  RTW_COUNT_LAUNCH();
   return cudaGetLastError();
 }
 cudaError_t launch_finalize_rgb8(const float* acc, uint8_t* rgb, long long npix, int spp, cudaStream_t stream) {
   k_finalize_rgb8<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(acc), rgb, npix,
                                                                                   static_cast<double>(spp));
+  RTW_COUNT_LAUNCH();
   return cudaGetLastError();
 }
 cudaError_t launch_finalize_rgb8_fx(const long long* fx, uint8_t* rgb, long long npix, int spp, cudaStream_t stream) {
   k_finalize_rgb8_fx<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, stream>>>(fx, rgb, npix, static_cast<double>(spp));
+  RTW_COUNT_LAUNCH();
   return cudaGetLastError();
 }
 cudaError_t launch_debug_scatter(long long n, const int* kind, const float* fuzz, const float* ior, const float* dir_in, const float* normal,
@@ -1402,16 +1415,22 @@ cudaError_t launch_debug_scatter(long long n, const int* kind, const float* fuzz
                                  const float* albedo, uint8_t* scattered, cudaStream_t stream) {
   k_debug_scatter<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(n, kind, fuzz, ior, dir_in, normal, front, ball, coin, out_dir,
                                                                                out_att, albedo, scattered);
+  RTW_COUNT_LAUNCH();
   return cudaGetLastError();
 }
 cudaError_t launch_debug_samples(long long n, uint64_t seed, float* ball, float* disk, float* uni, cudaStream_t stream) {
   k_debug_samples<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
       n, make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)), ball, disk, uni);
+  RTW_COUNT_LAUNCH();
   return cudaGetLastError();
 }
 cudaError_t launch_ffma_peak(float* out, int blocks, int iters, cudaStream_t stream) {
   k_ffma_peak<<<blocks, 256, 0, stream>>>(out, iters, 0.999999f, 1e-7f);
+  RTW_COUNT_LAUNCH();
   return cudaGetLastError();
 }
+
+void count_launch() { RTW_COUNT_LAUNCH(); }
+unsigned long long launch_count() { return g_kernel_launches.load(std::memory_order_relaxed); }
 
 }  // namespace rtw

@@ -160,6 +160,7 @@ int multi_host(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, int32_t ng
       k_combine_peers<<<static_cast<unsigned>((cnt + 255) / 256), 256, 0, s->stream>>>(pb, pix0, cnt, out_f32 ? reinterpret_cast<float4*>(s->out_f32.p) : nullptr,
                                                                                       out_u8 ? s->out_u8.p : nullptr, spp);
       RTW_CUDA(cudaGetLastError());
+      rtw::count_launch();
       ++launches;
       if (out_f32) RTW_CUDA(cudaMemcpyAsync(out_f32 + 4 * pix0, s->out_f32.p, static_cast<size_t>(cnt) * 4 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
       if (out_u8) RTW_CUDA(cudaMemcpyAsync(out_u8 + 3 * pix0, s->out_u8.p, static_cast<size_t>(cnt) * 3, cudaMemcpyDeviceToHost, s->stream));

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (one launch) into the handful of metrics the design argues from.
-    python scripts/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/r01_xxx.txt"""
+    python scripts/ncu_summary.py gpurun_out/prof.ncu-rep [gpurun_out/plain_run.log] > profiles/r02_xxx.txt
+The optional second argument is the log of the same command run WITHOUT ncu (scripts/profile_render.py): its `# launch:` line (paths and
+rays of the profiled launch) is copied into the summary so that bench.py can turn instruction counts into per-ray figures."""
 import csv
 import io
 import subprocess
@@ -23,12 +25,16 @@ KEYS = [
     "sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "l1tex__t_bytes.sum.per_second", "lts__t_bytes.sum.per_second",
-    "lts__t_sectors_op_red.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second",
+    "lts__t_sectors_op_red.sum", "lts__t_sectors_op_atom.sum", "lts__t_sectors.sum", "lts__t_requests_srcunit_tex_op_red.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second",
     "dram__bytes_write.sum.per_second", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__throughput.avg.pct_of_peak_sustained_elapsed",
 ]
 print(f"# {rep}")
+if len(sys.argv) > 2:
+    for ln in open(sys.argv[2]):
+        if ln.startswith("# launch:"):
+            print(ln.rstrip())
 for k in KEYS:
     if k in m:
         print(f"{k:85s} {m[k][0]:>22s} {m[k][1]}")

@@ -30,6 +30,7 @@ k = {"auto": rtw.KERNEL_AUTO, "spheres": rtw.KERNEL_SPHERES_SMEM, "bvh": rtw.KER
 for i in range(2):
     acc, st = rtw.render(scene, a.width, H, a.spp, a.depth, kernel=k, rays_per_lane=a.rays_per_lane, stats=a.stats)
 p, r = st["paths"], st["rays"]
+print(f"# launch: scene={a.scene if '/' not in a.scene else 'standin'} kernel={a.kernel} width={a.width} height={H} spp={a.spp} depth={a.depth} paths={p} rays={r}")
 print(f"{a.scene} {a.kernel} rpl={a.rays_per_lane} {a.width}x{H}x{a.spp}: kernel {st['kernel_ms']:.2f} ms, {p / st['kernel_ms'] / 1e3:.1f} Mpaths/s, "
       f"{r / st['kernel_ms'] / 1e3:.1f} Mrays/s, rays/path {r / p:.3f}"
       + (f", per ray: sphere tests {st['sphere_tests'] / r:.2f} candidates {st['sphere_candidates'] / r:.2f} nodes {st['node_visits'] / r:.2f} tris {st['tri_tests'] / r:.2f}" if a.stats else ""))

@@ -28,8 +28,16 @@ def _linear_worker(args):
     kind, width, height, spp, depth, seed, aspect = args
     ref = oracle.ref()
     # the scene is built from the default-seeded stream (as a fresh reference process would), THEN the stream is reseeded
-    sc = ref.scene_cover(11, aspect, True, seed=5489) if kind == "cover" else \
-        ref.scene_cover(11, aspect, False, seed=5489) if kind == "cover_static" else ref.scene_obj(SUZANNE, aspect, seed=5489)
+    if kind == "suzanne_on_ground":
+        # BASELINE config 3 as SURVEY 8(d) defines it (3b): the reference has no such scene builder (Q14), so the product's own
+        # builder lays out the primitives and the REFERENCE renders them through its public Scene API (ref_scene_custom)
+        import importlib
+        rtw = importlib.import_module("raytracing-one-weekend_b200")
+        ms = rtw.mesh_on_ground_scene(SUZANNE, aspect)
+        sc = ref.scene_custom(ms.prims, ms.mats.view(oracle.MAT_DTYPE), oracle.camera_params(**ms.params))
+    else:
+        sc = ref.scene_cover(11, aspect, True, seed=5489) if kind == "cover" else \
+            ref.scene_cover(11, aspect, False, seed=5489) if kind == "cover_static" else ref.scene_obj(SUZANNE, aspect, seed=5489)
     s, q, _ = sc.render_linear(width, height, spp, depth, seed=seed)
     return s, q
 
@@ -48,11 +56,21 @@ def converged(kind, width, height, spp_total, depth, aspect, nproc=8):
 
 
 def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="", help="regenerate only the converged fixture of this name")
+    only = ap.parse_args().only
     import oracle
     oracle.build()
     ref = oracle.ref()
     meta_common = {"generator": "tests/golden/make_golden.py", "source": "oracle/_ref (reference sources unmodified, glm/CLI11/tinyobj/fmt shims)"}
 
+    if not only:
+        primary_and_default(ref, oracle, meta_common)
+    converged_fixtures(meta_common, only)
+
+
+def primary_and_default(ref, oracle, meta_common):
     # 1. the reference executable's own output, default configuration, one thread (bit-reproducible: SURVEY Q9)
     ppm = subprocess.run([str(oracle.REF_EXE), "-t", "1"], capture_output=True, check=True).stdout
     md5 = hashlib.md5(ppm).hexdigest()
@@ -79,14 +97,20 @@ def main():
                         meta=json.dumps({**meta_common, "scene": "foo(suzanne.obj)", "time": 0.0}))
     print("primary hits done")
 
+
+def converged_fixtures(meta_common, only):
     # 3. converged linear-domain statistics (mean and per-sample variance per pixel and channel)
     converged_sets = [("cover_converged_120x80", "cover", 120, 80, 1024, 20, 1.5),
                       ("cover_static_converged_96x54", "cover_static", 96, 54, 512, 50, 1.7777777777777777),
                       ("suzanne_converged_96x64", "suzanne", 96, 64, 512, 20, 1.5),
                       # BASELINE config 2's scene, camera and depth (cover, 16:9, depth 50, motion blur) at a fifth of its resolution
                       # and its full 1024 spp: the largest reference render that stays a small fixture (variance stored as float16)
-                      ("cover_converged_384x216_depth50", "cover", 384, 216, 1024, 50, 1.7777777777777777)]
+                      ("cover_converged_384x216_depth50", "cover", 384, 216, 1024, 50, 1.7777777777777777),
+                      # BASELINE config 3 (3b of SURVEY 8(d)): suzanne on the r=1000 ground, 16:9, depth 20, at a sixth of its resolution
+                      ("suzanne_on_ground_converged_320x180", "suzanne_on_ground", 320, 180, 1024, 20, 1.7777777777777777)]
     for name, kind, w, h, spp, depth, aspect in converged_sets:
+        if only and name != only:
+            continue
         mean, var, n = converged(kind, w, h, spp, depth, aspect)
         if w * h > 20000:
             var = var.astype(np.float16)

@@ -70,6 +70,27 @@ def check_primary(got, want, fp64, unit_normals=True, max_knife_edge=0, cosines=
     return n_mism
 
 
+# The production fp32 tracers may pick the other of two surfaces whose hit parameters agree to within fp32 rounding (check_primary
+# demands |dt|/t < 1e-4 for every such pixel).  The counts are deterministic (no random numbers in primary-ray mode); the bounds
+# below are the counts observed on B200 for the committed kernels (recorded by every run in gpurun_out/knife_edge_counts.json and
+# copied to profiles/), not guesses: a kernel change that produces more ties than these fails the test.
+KNIFE_EDGE_BOUND = {"cover_1080p": 8, "suzanne_200x133": 2, "standin_62k_128x72": 3, "standin_991k_128x72": 4, "grid_6k_96x64": 2, "grid_57k_48x32": 2,
+                    "suzanne_on_ground_320x180": 3}
+_knife_edge_log = {}
+
+
+def record_knife_edge(name, count, pixels):
+    import json
+    _knife_edge_log[name] = {"mismatching_pixels": int(count), "pixels": int(pixels)}
+    out = ROOT / "gpurun_out"
+    try:
+        out.mkdir(exist_ok=True)
+        (out / "knife_edge_counts.json").write_text(json.dumps(_knife_edge_log, indent=1, sort_keys=True))
+    except OSError:
+        pass
+    print(f"knife-edge pixels {name}: {count} of {pixels}")
+
+
 def incidence_cosines(rtw, scene, width, height, normals):
     """|cos| between the (aperture-0) camera ray through each pixel centre and the oracle's unit normal."""
     c = scene.camera
@@ -126,7 +147,10 @@ def test_primary_hits_suzanne_vs_golden(gpu, golden, precision):
     g = golden("suzanne_primary_200x133.npz")
     scene = gpu.obj_scene(SUZANNE)
     got = gpu.primary_hits(scene, 200, 133, 0.0, precision)
-    check_primary(got, (g["id"], g["t"], g["normal"], g["front"]), fp64=(precision == 64), unit_normals=False, max_knife_edge=2)
+    n = check_primary(got, (g["id"], g["t"], g["normal"], g["front"]), fp64=(precision == 64), unit_normals=False,
+                      max_knife_edge=KNIFE_EDGE_BOUND["suzanne_200x133"])
+    if precision == 32:
+        record_knife_edge("suzanne_200x133/bvh", n, 200 * 133)
 
 
 def test_primary_hits_full_hd_vs_oracle(gpu, oracle_mod, port):
@@ -140,8 +164,8 @@ def test_primary_hits_full_hd_vs_oracle(gpu, oracle_mod, port):
     cosines = incidence_cosines(gpu, scene, W, H, want[2])
     check_primary(gpu.primary_hits(scene, W, H, 0.25, 64), want, fp64=True)
     for kernel in (gpu.KERNEL_SPHERES_SMEM, gpu.KERNEL_BVH):
-        n = check_primary(gpu.primary_hits(scene, W, H, 0.25, 32, kernel), want, fp64=False, max_knife_edge=8, cosines=cosines)
-        print("knife-edge pixels at 1080p:", n)
+        n = check_primary(gpu.primary_hits(scene, W, H, 0.25, 32, kernel), want, fp64=False, max_knife_edge=KNIFE_EDGE_BOUND["cover_1080p"], cosines=cosines)
+        record_knife_edge(f"cover_1080p/{'spheres' if kernel == gpu.KERNEL_SPHERES_SMEM else 'bvh'}", n, W * H)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -465,14 +489,27 @@ def test_host_executable_binary_output_and_resume(gpu, tmp_path):
 
 
 def test_multi_gpu_in_process(gpu):
+    """rtw_render_multi_gpu: sample split + peer-memory combine, and the row-tile split, both bit-identical to one GPU; samples that
+    do not divide by the GPU count are spread (the reference analogue truncates, render.cpp:174); the rgb8 variant agrees too."""
     if gpu.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    n = min(gpu.device_count(), 8)
     scene = gpu.cover_scene()
     one, _ = gpu.render(scene, 200, 133, 32, 20, seed=8)
-    two, st = gpu.render_multi_gpu(scene, 200, 133, 32, 2, 20, seed=8)
-    assert np.array_equal(one, two) and st["paths"] == 200 * 133 * 32
-    rows, st = gpu.render_multi_gpu(scene, 200, 133, 32, 2, 20, seed=8, flags=gpu.FLAG_SPLIT_ROWS, row_tiles=(8, 0, 0))
-    assert np.array_equal(one, rows) and st["paths"] == 200 * 133 * 32
+    for g in sorted({2, n}):
+        two, st = gpu.render_multi_gpu(scene, 200, 133, 32, g, 20, seed=8)
+        assert np.array_equal(one, two) and st["paths"] == 200 * 133 * 32
+        rows, st = gpu.render_multi_gpu(scene, 200, 133, 32, g, 20, seed=8, flags=gpu.FLAG_SPLIT_ROWS, row_tiles=(8, 0, 0))
+        assert np.array_equal(one, rows) and st["paths"] == 200 * 133 * 32 and st["scene_cache_hit"] == 1
+    odd1, _ = gpu.render(scene, 200, 133, 7, 20, seed=8)
+    odd2, st = gpu.render_multi_gpu(scene, 200, 133, 7, 2, 20, seed=8)
+    assert np.array_equal(odd1, odd2) and st["paths"] == 200 * 133 * 7
+    few, st = gpu.render_multi_gpu(scene, 200, 133, 1, 2, 20, seed=8)      # fewer samples than GPUs: one GPU idles
+    assert st["paths"] == 200 * 133 and np.all(few[..., 3] == 1)
+    rgb1, _ = gpu.render_rgb8(scene, 200, 133, 32, 20, seed=8)
+    rgb2, _ = gpu.render_rgb8(scene, 200, 133, 32, 20, ngpus=2, seed=8)
+    rgb3, _ = gpu.render_rgb8(scene, 200, 133, 32, 20, ngpus=2, seed=8, flags=gpu.FLAG_SPLIT_ROWS)
+    assert np.array_equal(rgb1, rgb2) and np.array_equal(rgb1, rgb3)
 
 
 @pytest.mark.parametrize("kernel_name", ["spheres", "bvh", "bvh-perlane"])
@@ -518,7 +555,8 @@ def test_high_poly_stand_in_mesh(gpu, port, oracle_mod, tmp_path):
     W, H = 128, 72
     want = osc.primary_hits(W, H, 0.0)
     check_primary(gpu.primary_hits(scene, W, H, 0.0, 64), want, fp64=True, unit_normals=False)
-    check_primary(gpu.primary_hits(scene, W, H, 0.0, 32), want, fp64=False, unit_normals=False, max_knife_edge=3)
+    n = check_primary(gpu.primary_hits(scene, W, H, 0.0, 32), want, fp64=False, unit_normals=False, max_knife_edge=KNIFE_EDGE_BOUND["standin_62k_128x72"])
+    record_knife_edge("standin_62k_128x72/bvh", n, W * H)
     acc, st = gpu.render(scene, 64, 36, 4, 20, seed=6, stats=True)
     ref, _, rays = port.render_philox(osc, 64, 36, 0, 4, 20, seed=6, nthreads=8)
     assert st["kernel_used"] == gpu.KERNEL_BVH and st["bvh_variant"] == gpu.BVH_PERLANE and st["tri_tests"] > 0   # meshes: per-lane kernel
@@ -538,7 +576,9 @@ def test_large_sphere_grids(gpu, port, nsqrt):
     W, H = (96, 64) if nsqrt == 40 else (48, 32)
     want = osc.primary_hits(W, H, 0.5)
     check_primary(gpu.primary_hits(scene, W, H, 0.5, 64), want, fp64=True)
-    check_primary(gpu.primary_hits(scene, W, H, 0.5, 32), want, fp64=False, max_knife_edge=2, cosines=incidence_cosines(gpu, scene, W, H, want[2]))
+    n = check_primary(gpu.primary_hits(scene, W, H, 0.5, 32), want, fp64=False, max_knife_edge=KNIFE_EDGE_BOUND["grid_6k_96x64" if nsqrt == 40 else "grid_57k_48x32"],
+                      cosines=incidence_cosines(gpu, scene, W, H, want[2]))
+    record_knife_edge(f"grid_n{nsqrt}/bvh", n, W * H)
     acc, st = gpu.render(scene, W, H, 4, 20, seed=2)
     ref, _, rays = port.render_philox(osc, W, H, 0, 4, 20, seed=2, nthreads=8)
     assert st["kernel_used"] == gpu.KERNEL_BVH
@@ -566,3 +606,151 @@ def test_bvh_kernel_crossover_by_table_size(gpu, port, nsqrt, variant):
     for (w, h, spp) in ((2, 2, 1), (3, 2, 5), (130, 2, 1), (129, 3, 33)):
         tiny, st3 = gpu.render(scene, w, h, spp, 3, seed=1, kernel=gpu.KERNEL_BVH)
         assert st3["paths"] == w * h * spp and np.all(tiny[..., 3] == spp), (w, h, spp)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE's own sizes: config 2 at 1920x1080 x 1024 spp against the reference's render of the same frame, config 3 (mesh on the
+# ground) against the reference's render, config 4's 991 232-triangle mesh against the oracle
+# ------------------------------------------------------------------------------------------------------------------
+def test_converged_cover_1080p_1024spp_vs_reference_full_size(gpu, golden):
+    """The north star's last sentence, literally: the cover scene at 1920x1080, 1024 spp, depth 50 through the host-buffer C-ABI call
+    against the UNMODIFIED reference's own 1024-spp render of the same frame (tests/golden/make_golden_fullsize.py, 64 x 16 spp on
+    oracle/_ref): PSNR >= 40 dB between the two 8-bit images, per-channel image mean within 3 sigma of the Monte Carlo noise of the two
+    renders, and no more 8x8 blocks beyond 5 sigma than noise explains."""
+    g = golden("cover_1080p_1024spp_depth50.npz")
+    m = g["meta"]
+    W, H, spp, depth = m["width"], m["height"], m["spp"], m["max_child_rays"]
+    assert (W, H, spp, depth) == (1920, 1080, 1024, 50)
+    scene = gpu.cover_scene(11, m["aspect"])
+    acc, st = gpu.render(scene, W, H, spp, depth, seed=2024)
+    assert st["paths"] == W * H * spp and st["bvh_variant"] == gpu.BVH_WAVEFRONT
+    img = gpu.quantize(acc, spp)
+    p = psnr8(img, g["rgb"])
+    mean = acc[..., :3].astype(np.float64) / spp
+    mean_ch = mean.mean(axis=(0, 1))
+    se = np.sqrt(2.0) * g["se_ch"]            # two independent 1024-spp renders of the same integrand
+    z = (mean_ch - g["mean_ch"]) / se
+    blk = mean.reshape(H // 8, 8, W // 8, 8, 3).mean(axis=(1, 3))
+    bse = np.sqrt(2.0) * np.maximum(g["blk_se"].astype(np.float64), 2e-4)   # floor: a 1024-sample variance estimate is blind to rare bright paths
+    frac5 = (np.abs(blk - g["blk_mean"]) > 5 * bse).mean()
+    print(f"config 2 full size: PSNR {p:.2f} dB, image-mean z {z}, blocks beyond 5 sigma {frac5:.2e}, kernel {st['kernel_ms']:.1f} ms")
+    assert p >= 40.0, p
+    assert np.abs(z).max() < 3.0, z
+    assert frac5 < 1e-3, frac5
+    # the device-side write_color (rtw_render_rgb8, what the drop-in prints) shows the same picture: the exact integer sums and their
+    # float roundings may only disagree where a channel sits on a quantisation boundary
+    rgb, st8 = gpu.render_rgb8(scene, W, H, spp, depth, seed=2024)
+    assert st8["scene_cache_hit"] == 1
+    d = np.abs(rgb.astype(int) - img.astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-4, ((d > 0).mean(), d.max())
+    assert psnr8(rgb, g["rgb"]) >= 40.0
+
+
+def test_converged_mesh_on_ground_vs_reference(gpu, golden):
+    """BASELINE config 3 (suzanne.obj on the r=1000 ground sphere, 16:9, depth 20): the reference's own render of that scene through
+    its public Scene API (golden suzanne_on_ground_converged_320x180, 1024 spp) against the mesh kernel."""
+    scene = gpu.mesh_on_ground_scene(SUZANNE, 1.7777777777777777)
+    p = converged_check(gpu, golden, "suzanne_on_ground_converged_320x180.npz", scene, gpu.KERNEL_AUTO)
+    assert p >= 42.0
+
+
+def test_primary_hits_mesh_on_ground_vs_oracle(gpu, port, oracle_mod):
+    scene = gpu.mesh_on_ground_scene(SUZANNE, 1.7777777777777777)
+    osc = port.scene_custom(scene.prims, scene.mats.view(oracle_mod.MAT_DTYPE), oracle_mod.camera_params(**scene.params))
+    W, H = 320, 180
+    want = osc.primary_hits(W, H, 0.0, nthreads=8)
+    check_primary(gpu.primary_hits(scene, W, H, 0.0, 64), want, fp64=True, unit_normals=False)
+    n = check_primary(gpu.primary_hits(scene, W, H, 0.0, 32), want, fp64=False, unit_normals=False, max_knife_edge=KNIFE_EDGE_BOUND["suzanne_on_ground_320x180"])
+    record_knife_edge("suzanne_on_ground_320x180/bvh", n, W * H)
+
+
+def test_benchmarked_991k_triangle_mesh_parity(gpu, port, oracle_mod, tmp_path):
+    """BASELINE config 4's own mesh (the 991 232-triangle stand-in for the missing dragon.obj, exactly what bench.py renders): primitive
+    ids exact in fp64 mode, within the recorded knife-edge count in the production fp32 mode, t / normals within tolerance, and a
+    same-stream frame against the oracle's brute force over all 991 233 primitives."""
+    import ctypes as C
+    import os
+    obj = tmp_path / "standin5.obj"
+    n = C.c_longlong(0)
+    assert gpu.host().rtwh_make_mesh(SUZANNE.encode(), str(obj).encode(), 5, 20221018, 0.08, C.byref(n)) == 0 and n.value == 991232
+    scene = gpu.mesh_on_ground_scene(str(obj), 1.7777777777777777)
+    assert len(scene.prims) == 991233
+    info = gpu.flatten_info(scene)
+    assert info["bvh_errors"] == 0 and info["n_triangles"] == 991232 and info["bvh_max_depth"] <= 64
+    osc = port.scene_custom(scene.prims, scene.mats.view(oracle_mod.MAT_DTYPE), oracle_mod.camera_params(**scene.params))
+    threads = min(os.cpu_count() or 1, 64)
+    W, H = 128, 72
+    want = osc.primary_hits(W, H, 0.0, nthreads=threads)
+    assert (want[0] > 0).mean() > 0.15      # the mesh covers a good part of the frame
+    check_primary(gpu.primary_hits(scene, W, H, 0.0, 64), want, fp64=True, unit_normals=False)
+    k = check_primary(gpu.primary_hits(scene, W, H, 0.0, 32), want, fp64=False, unit_normals=False, max_knife_edge=KNIFE_EDGE_BOUND["standin_991k_128x72"])
+    record_knife_edge("standin_991k_128x72/bvh", k, W * H)
+    acc, st = gpu.render(scene, 64, 36, 4, 20, seed=6, stats=True)
+    ref, _, rays = port.render_philox(osc, 64, 36, 0, 4, 20, seed=6, nthreads=threads)
+    assert st["kernel_used"] == gpu.KERNEL_BVH and st["tri_tests"] > 0 and st["paths"] == 64 * 36 * 4
+    got = acc[..., :3].astype(np.float64) / 4
+    assert (np.abs(got - ref / 4).max(axis=2) > 1e-3).mean() < 0.03
+    assert abs(st["rays"] - rays) / rays < 0.01
+    # the second render of the same arrays finds the scene (and its 1 M-triangle BVH) on the device
+    acc2, st2 = gpu.render(scene, 64, 36, 4, 20, seed=6)
+    assert st2["scene_cache_hit"] == 1 and st2["h2d_ms"] < 0.5 * st["h2d_ms"] and np.array_equal(acc2, acc)
+
+
+def test_scene_cache_and_rgb8_path(gpu):
+    """rtw_render keeps the flattened scene on the device between calls (keyed on rtw_scene_hash); RTW_FLAG_NO_SCENE_CACHE and any
+    change of the arrays force a rebuild; results are identical either way.  rtw_render_rgb8 returns write_color of the same sums."""
+    gpu.lib().rtw_release_cached_buffers()
+    scene = gpu.cover_scene()
+    a, sa = gpu.render(scene, 160, 106, 16, 20, seed=3)
+    b, sb = gpu.render(scene, 160, 106, 16, 20, seed=3)
+    c, sc = gpu.render(scene, 160, 106, 16, 20, seed=3, flags=gpu.FLAG_NO_SCENE_CACHE)
+    assert (sa["scene_cache_hit"], sb["scene_cache_hit"], sc["scene_cache_hit"]) == (0, 1, 0)
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+    other = gpu.cover_scene(11, 1.5, False)
+    d, sd = gpu.render(other, 160, 106, 16, 20, seed=3)
+    e, se = gpu.render(scene, 160, 106, 16, 20, seed=3)
+    assert sd["scene_cache_hit"] == 0 and se["scene_cache_hit"] == 0 and not np.array_equal(a, d) and np.array_equal(a, e)
+    rgb, _ = gpu.render_rgb8(scene, 160, 106, 16, 20, seed=3)
+    want = gpu.quantize(a, 16)
+    diff = np.abs(rgb.astype(int) - want.astype(int))
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+    # a slice of samples quantises with its own count
+    part, _ = gpu.render_rgb8(scene, 160, 106, 4, 20, seed=3, sample_begin=8)
+    acc_part, _ = gpu.render(scene, 160, 106, 4, 20, seed=3, sample_begin=8)
+    diff = np.abs(part.astype(int) - gpu.quantize(acc_part, 4).astype(int))
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+
+
+def test_concurrent_renders_of_one_uploaded_scene(gpu):
+    """rtw_render_device gives every launch its own work-queue / statistics block: renders of ONE rtw_scene in flight on different
+    streams (and issued from different host threads) neither skip nor repeat work units."""
+    import threading
+    import torch
+    scene = gpu.cover_scene()
+    W, H, S = 200, 133, 24
+    ds = gpu.DeviceScene(scene, 0)
+    ref = torch.zeros((H, W, 4), dtype=torch.int64, device="cuda:0")
+    ds.render_into(ref, W, H, S, 20, stream_ptr=torch.cuda.current_stream().cuda_stream, seed=11)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(6)]
+    bufs = [torch.zeros((H, W, 4), dtype=torch.int64, device="cuda:0") for _ in streams]
+    torch.cuda.synchronize()
+    errors = []
+
+    def go(k):
+        try:
+            with torch.cuda.stream(streams[k]):
+                bufs[k].zero_()
+            ds.render_into(bufs[k], W, H, S, 20, stream_ptr=streams[k].cuda_stream, seed=11)
+        except Exception as ex:   # noqa: BLE001
+            errors.append(ex)
+    th = [threading.Thread(target=go, args=(k,)) for k in range(len(streams))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    torch.cuda.synchronize()
+    assert not errors, errors
+    for b in bufs:
+        assert torch.equal(b, ref)
+    ds.close()

@@ -260,3 +260,47 @@ def test_flatten_tables_and_bvh_invariants(rtw, tmp_path):
     bad.prims["kind"][0] = 7
     with pytest.raises(rtw.RtwError, match="primitive kind"):
         rtw.flatten_info(bad)
+
+
+def test_variant_and_oo_models_flatten_identically(rtw):
+    """north_star keeps both primitive containers (variant-primitives.h / oo-primitives.h behind primitive-model.h): the host side
+    built with -DRTWEEKEND_USE_VARIANT_PRIMITIVES hands the same arrays to the C ABI as the default (virtual) build, scene by scene."""
+    oo, var = rtw.host(), rtw.host_variant()
+    assert oo.rtwh_primitive_model() == b"oo" and var.rtwh_primitive_model() == b"variant"
+    for args in [(11, 1.5, True), (11, 1.7777777777777777, False), (3, 1.5, True)]:
+        a, b = rtw.cover_scene(*args, H=oo), rtw.cover_scene(*args, H=var)
+        assert a.prims.tobytes() == b.prims.tobytes() and a.mats.tobytes() == b.mats.tobytes()
+        assert bytes(a.camera) == bytes(b.camera)
+        assert rtw.scene_hash(a) == rtw.scene_hash(b)
+    a, b = rtw.obj_scene(SUZANNE, H=oo), rtw.obj_scene(SUZANNE, H=var)
+    assert len(a.prims) == 968 and a.prims.tobytes() == b.prims.tobytes() and a.mats.tobytes() == b.mats.tobytes()
+    # the executables of both builds parse the same command line
+    out = [subprocess.run([str(e), "--dry-run", "-w", "320", "-s", "7"], capture_output=True, text=True) for e in (rtw.EXE_PATH, rtw.EXE_VARIANT_PATH)]
+    assert out[0].returncode == 0 and out[0].stdout == out[1].stdout and "image_width: 320" in out[0].stdout
+
+
+def test_scene_hash_follows_the_content(rtw):
+    """rtw_scene_hash keys the device scene cache and binds checkpoints to their scene: equal content, equal hash; any changed
+    double, material, camera field or primitive count, a different one."""
+    s = rtw.cover_scene()
+    h = rtw.scene_hash(s)
+    assert h == rtw.scene_hash(rtw.cover_scene()) and h != 0
+    seen = {h}
+    for mutate in (lambda q: q.prims["a"].__setitem__((17, 1), q.prims["a"][17, 1] + 1e-12),
+                   lambda q: q.prims["radius"].__setitem__(484, 1.0000001),
+                   lambda q: q.mats["albedo"].__setitem__((3, 2), 0.25),
+                   lambda q: q.prims["material"].__setitem__(5, 6),
+                   lambda q: setattr(q.camera, "t1", 0.5)):
+        q = rtw.cover_scene()
+        mutate(q)
+        seen.add(rtw.scene_hash(q))
+    q = rtw.cover_scene()
+    q.prims = q.prims[:-1].copy()
+    seen.add(rtw.scene_hash(q))
+    assert len(seen) == 7
+    big = rtw.cover_scene(120)   # 57 603 primitives: the chunked (multi-threaded) hashing path
+    assert len(big.prims) * big.prims.itemsize > (4 << 20)
+    hb = rtw.scene_hash(big)
+    assert hb == rtw.scene_hash(rtw.cover_scene(120))
+    big.prims["b"][40000, 2] += 1e-9
+    assert rtw.scene_hash(big) != hb
