@@ -42,9 +42,10 @@ enum rtw_mat_kind { RTW_LAMBERTIAN = 0, RTW_METAL = 1, RTW_DIELECTRIC = 2 };
 /* AUTO = BVH (the faster choice at every scene size measured).  SPHERES_SMEM: the brute-force shared-memory sphere sweep, the kernel
  * the FP32-FMA roofline is defined on (sphere-only scenes whose tables fit in shared memory).  BVH picks between its two kernels: the wavefront-per-warp kernel when the
  * scene tables and the per-warp path records fit in shared memory (up to ~1150 spheres) and for every larger sphere-only scene,
- * the per-lane state machine for meshes.  BVH_PERLANE forces the latter (A/B measurements). */
+ * for scenes with triangles a compressed 8-wide BVH (80-byte nodes, 8-bit child boxes) walked by the per-lane state machine
+ * (RTW_BVH_CWIDE).  BVH_PERLANE forces the per-lane state machine on sphere scenes (A/B measurements). */
 enum rtw_kernel { RTW_KERNEL_AUTO = 0, RTW_KERNEL_SPHERES_SMEM = 1, RTW_KERNEL_BVH = 2, RTW_KERNEL_BVH_PERLANE = 3 };
-enum rtw_bvh_variant { RTW_BVH_NONE = 0, RTW_BVH_PERLANE = 1, RTW_BVH_WAVEFRONT = 2 };
+enum rtw_bvh_variant { RTW_BVH_NONE = 0, RTW_BVH_PERLANE = 1, RTW_BVH_WAVEFRONT = 2, RTW_BVH_CWIDE = 3 };
 /* STATS: count tests / node visits (slower).  SPLIT_ROWS: multi-GPU row-tile split instead of the sample split.
  * NO_SCENE_CACHE: the host-buffer entry points re-flatten, re-build and re-upload the scene even when it is the one the device
  * already holds from the previous call (what the first call of a process pays; bench.py's end-to-end leg uses it). */

@@ -30,7 +30,7 @@ HEADER_PATH = REPO_ROOT / "include" / "rtw_b200.h"
 RTW_SPHERE, RTW_MOVING_SPHERE, RTW_TRIANGLE = 0, 1, 2
 RTW_LAMBERTIAN, RTW_METAL, RTW_DIELECTRIC = 0, 1, 2
 KERNEL_AUTO, KERNEL_SPHERES_SMEM, KERNEL_BVH, KERNEL_BVH_PERLANE = 0, 1, 2, 3
-BVH_NONE, BVH_PERLANE, BVH_WAVEFRONT = 0, 1, 2
+BVH_NONE, BVH_PERLANE, BVH_WAVEFRONT, BVH_CWIDE = 0, 1, 2, 3
 FLAG_STATS = 1
 FLAG_SPLIT_ROWS = 2
 FLAG_NO_SCENE_CACHE = 4

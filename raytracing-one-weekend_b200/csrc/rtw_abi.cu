@@ -124,18 +124,25 @@ int rtw::flatten_host(const rtw_scene_desc* desc, HostFlat* hf) {
 
   rtw::BvhBuilder builder;
   if (const char* e = std::getenv("RTW_BVH_LEAF")) builder.kMaxLeaf = std::min(std::max(std::atoi(e), 1), 31);  // tuning knob
-  const bool direct = builder.kMaxLeaf == 1;
-  const size_t node_cap = std::max<size_t>(n_items, 1), ref_cap = direct ? 0 : n_items;
+  // Scenes with triangles get the compressed 8-wide BVH (rtw_bvh.h CwBuilder) and leaf-ordered 48-byte primitive records; sphere-only
+  // scenes keep the binary tree with 64-byte nodes that the shared-memory kernels walk.
+  const bool cw = n_tri > 0;
+  const bool direct = builder.kMaxLeaf == 1 || cw;
+  const size_t node_cap = cw ? 0 : std::max<size_t>(n_items, 1), ref_cap = direct ? 0 : n_items;
+  const size_t n_records = cw ? n_items : n_tri;   // cw: one record per leaf primitive (triangles and small spheres)
 
   // ---- arena layout ----------------------------------------------------------------------------------------------------------------
   size_t cursor = 0;
   auto reserve = [&cursor](size_t bytes) { const size_t off = (cursor + 255) & ~size_t(255); cursor = off + bytes; return off; };
   hf->o_sA = reserve(n_small * sizeof(float4)); hf->o_sB = reserve(n_small * sizeof(float4)); hf->o_sId = reserve(n_small * sizeof(int2));
   hf->o_big = reserve(n_big * sizeof(rtw::BigSphere));
-  hf->o_tri = reserve(n_tri * 3 * sizeof(float4)); hf->o_triId = reserve(n_tri * sizeof(int2));
+  hf->o_tri = reserve(n_records * 3 * sizeof(float4)); hf->o_triId = reserve(n_records * sizeof(int2));
   hf->o_nodes = reserve(node_cap * sizeof(rtw::PackedNode)); hf->o_refs = reserve(ref_cap * sizeof(uint32_t));
   hf->o_matA = reserve(static_cast<size_t>(desc->nmats) * sizeof(float4)); hf->o_matB = reserve(static_cast<size_t>(desc->nmats) * sizeof(float2));
   hf->o_ctr = reserve(static_cast<size_t>(rtw::kCtrSlots) * rtw::kCtrCount * sizeof(unsigned long long));
+  // the wide nodes come last: their number is only known after the collapse (at most one per primitive; typically a sixth), so the
+  // arena is sized for the bound and trimmed afterwards (untouched pages of the host allocation are never committed)
+  hf->o_cw = reserve(cw ? std::max<size_t>(n_items, 1) * sizeof(rtw::CwNode) : 0);
   hf->bytes = (cursor + 255) & ~size_t(255);
   hf->host.reset(new unsigned char[hf->bytes]);
   unsigned char* base = hf->host.get();
@@ -149,6 +156,15 @@ int rtw::flatten_host(const rtw_scene_desc* desc, HostFlat* hf) {
 
   // ---- pass 2: table entries and BVH build records (small spheres: swept bounds, common-model.cpp:197-207) ----------------------
   std::vector<rtw::BvhBuilder::Item> items(n_items);
+  std::vector<uint32_t> tri_src(cw ? n_tri : 0);   // cw: triangle rank -> primitive index (the records are written in leaf order after the build)
+  auto tri_record = [](const rtw_primitive& P, float4& q0, float4& q1, float4& q2) {
+    const double e1[3] = {P.b[0] - P.a[0], P.b[1] - P.a[1], P.b[2] - P.a[2]};
+    const double e2[3] = {P.c[0] - P.a[0], P.c[1] - P.a[1], P.c[2] - P.a[2]};
+    const double nn[3] = {e1[1] * e2[2] - e2[1] * e1[2], e1[2] * e2[0] - e2[2] * e1[0], e1[0] * e2[1] - e2[0] * e1[1]};
+    q0 = make_float4((float)P.a[0], (float)P.a[1], (float)P.a[2], (float)nn[0]);
+    q1 = make_float4((float)e1[0], (float)e1[1], (float)e1[2], (float)nn[1]);
+    q2 = make_float4((float)e2[0], (float)e2[1], (float)e2[2], (float)nn[2]);
+  };
   parallel_chunks(n, nchunks, [&](int c, int64_t begin, int64_t end) {
     std::array<int64_t, 4> at = start[static_cast<size_t>(c)];
     for (int64_t i = begin; i < end; ++i) {
@@ -157,14 +173,10 @@ int rtw::flatten_host(const rtw_scene_desc* desc, HostFlat* hf) {
       const uint8_t k = cls[static_cast<size_t>(i)];
       if (k == kClsTri) {
         const size_t t = static_cast<size_t>(at[kClsTri]++);
-        const double e1[3] = {P.b[0] - P.a[0], P.b[1] - P.a[1], P.b[2] - P.a[2]};
-        const double e2[3] = {P.c[0] - P.a[0], P.c[1] - P.a[1], P.c[2] - P.a[2]};
-        const double nn[3] = {e1[1] * e2[2] - e2[1] * e1[2], e1[2] * e2[0] - e2[2] * e1[0], e1[0] * e2[1] - e2[0] * e1[1]};
-        const float4 q0 = make_float4((float)P.a[0], (float)P.a[1], (float)P.a[2], (float)nn[0]);
-        const float4 q1 = make_float4((float)e1[0], (float)e1[1], (float)e1[2], (float)nn[1]);
-        const float4 q2 = make_float4((float)e2[0], (float)e2[1], (float)e2[2], (float)nn[2]);
-        tri[3 * t] = q0; tri[3 * t + 1] = q1; tri[3 * t + 2] = q2;
-        triId[t] = make_int2(id, P.material);
+        float4 q0, q1, q2;
+        tri_record(P, q0, q1, q2);
+        if (cw) tri_src[t] = static_cast<uint32_t>(i);
+        else { tri[3 * t] = q0; tri[3 * t + 1] = q1; tri[3 * t + 2] = q2; triId[t] = make_int2(id, P.material); }
         rtw::BvhBuilder::Item& it = items[n_small + t];
         const float va[3] = {q0.x, q0.y, q0.z}, vb[3] = {q0.x + q1.x, q0.y + q1.y, q0.z + q1.z}, vc[3] = {q0.x + q2.x, q0.y + q2.y, q0.z + q2.z};
         it.box.reset(); it.box.grow(va); it.box.grow(vb); it.box.grow(vc);
@@ -199,7 +211,40 @@ int rtw::flatten_host(const rtw_scene_desc* desc, HostFlat* hf) {
   const double t_bvh = now_ms();
   rtw::PackedNode* nodes_out = reinterpret_cast<rtw::PackedNode*>(base + hf->o_nodes);
   size_t n_nodes = 0, n_refs = 0;
-  if (direct) {
+  size_t n_cw = 0;
+  int cw_depth = 0;
+  if (cw) {
+    std::vector<rtw::BinNode> bin(n_items >= 2 ? n_items - 1 : 0);
+    builder.build_items_binary(items, bin.data());
+    rtw::CwBuilder wide;
+    if (const char* e = std::getenv("RTW_CW_LEAF")) wide.max_leaf = std::min(std::max(std::atoi(e), 1), 3);  // tuning knob
+    wide.margin = 4.0 * 1.1920929e-7 * bound;
+    wide.build(bin.data(), bin.size(), n_items == 1 ? &items[0].box : nullptr, n_items == 1 ? items[0].ref : 0u);
+    n_cw = wide.nodes().size();
+    cw_depth = wide.depth();
+    if (n_cw) std::memcpy(base + hf->o_cw, wide.nodes().data(), n_cw * sizeof(rtw::CwNode));
+    hf->bytes = (hf->o_cw + std::max<size_t>(n_cw, 1) * sizeof(rtw::CwNode) + 255) & ~size_t(255);
+    // leaf-ordered records: the primitives of one leaf (and of neighbouring leaves) next to each other in memory
+    const std::vector<uint32_t>& order = wide.leaf_order();
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    parallel_chunks(static_cast<int64_t>(order.size()), nchunks, [&](int, int64_t begin, int64_t end) {
+      for (int64_t P = begin; P < end; ++P) {
+        const uint32_t ref = order[static_cast<size_t>(P)], t = ref & 0x1fffffffu;
+        if (ref >> 30) {
+          const uint32_t i = tri_src[t];
+          tri_record(desc->prims[i], tri[3 * P], tri[3 * P + 1], tri[3 * P + 2]);
+          triId[P] = make_int2(static_cast<int>(i), desc->prims[i].material);
+        } else {
+          tri[3 * P] = sA[t]; tri[3 * P + 1] = sB[t];
+          tri[3 * P + 2] = make_float4(nan, __int_as_float_host(static_cast<int>(t)), 0.0f, 0.0f);
+          triId[P] = sId[t];
+        }
+      }
+    });
+    if (cw_depth > rtw::kCwStack)
+      return fail("rtw_scene_upload: the wide BVH is deeper than the kernels' traversal stack (" + std::to_string(cw_depth) + " > " +
+                  std::to_string(rtw::kCwStack) + " levels): degenerate primitive distribution");
+  } else if (direct) {
     n_nodes = builder.build_items_direct(items, nodes_out);
   } else {
     std::vector<rtw::Box3> boxes(n_items);
@@ -215,8 +260,9 @@ int rtw::flatten_host(const rtw_scene_desc* desc, HostFlat* hf) {
   if (builder.max_depth() > rtw::kBvhStack)
     return fail("rtw_scene_upload: the BVH is deeper than the kernels' traversal stack (" + std::to_string(builder.max_depth()) + " > " +
                 std::to_string(rtw::kBvhStack) + " levels): degenerate primitive distribution");
-  hf->bvh_depth = builder.max_depth();
+  hf->bvh_depth = cw ? cw_depth : builder.max_depth();
   hf->bvh_ms = now_ms() - t_bvh;
+  hf->n_cw = static_cast<int32_t>(n_cw); hf->n_records = static_cast<int32_t>(n_records); hf->cw_has_spheres = cw && n_small > 0 ? 1 : 0;
 
   float4* matA = reinterpret_cast<float4*>(base + hf->o_matA);
   float2* matB = reinterpret_cast<float2*>(base + hf->o_matB);
@@ -306,7 +352,8 @@ int rtw::upload_flat(const HostFlat& hf, const rtw_camera& c, int64_t nprims, in
   d.n_static = hf.n_static; d.n_moving = hf.n_moving;
   d.big = reinterpret_cast<const rtw::BigSphere*>(base + hf.o_big); d.n_big = hf.n_big;
   d.tri = reinterpret_cast<const float4*>(base + hf.o_tri); d.triId = reinterpret_cast<const int2*>(base + hf.o_triId);
-  d.n_tri = hf.n_tri;
+  d.n_tri = hf.n_cw > 0 ? hf.n_records : hf.n_tri;
+  d.cwNodes = reinterpret_cast<const uint4*>(base + hf.o_cw); d.n_cw_nodes = hf.n_cw; d.cw_has_spheres = hf.cw_has_spheres;
   d.nodes = reinterpret_cast<const float4*>(base + hf.o_nodes); d.leafRefs = reinterpret_cast<const uint32_t*>(base + hf.o_refs);
   d.n_nodes = hf.n_nodes;
   d.leaf_direct = hf.leaf_direct;
@@ -420,10 +467,11 @@ int fill_params(const rtw_scene* sc, const rtw_render_cfg* cfg, int mode, unsign
   // work groups: 16 x 8 pixel tiles of the (local) image
   p->tiles_x = (p->width + 15u) / 16u;
   const unsigned long long n_groups = static_cast<unsigned long long>(p->tiles_x) * ((p->npix / p->width + 7u) / 8u);
-  // enough units to keep every resident warp busy and the tail short: aim for >= 16 units per warp
+  // enough units to keep every resident warp busy and the tail short: aim for >= 64 units per warp, at most 16 samples per unit
+  // (measured on the cover scene at 1080p, kernel ms: 128 spp su 1/2/4/8 = 36.25/35.73/35.58/35.76, 1024 spp su 4/8/16 = 291.2/282.8/281.6)
   const unsigned long long warps = static_cast<unsigned long long>(sc->sm_count) * 4ull * (rtw::kRenderThreads / 32);
-  unsigned long long su = (static_cast<unsigned long long>(S) * n_groups) / (16ull * warps);
-  su = std::min<unsigned long long>(std::max<unsigned long long>(su, 1ull), 8ull);
+  unsigned long long su = (static_cast<unsigned long long>(S) * n_groups) / (64ull * warps);
+  su = std::min<unsigned long long>(std::max<unsigned long long>(su, 1ull), 16ull);
   if (const char* e = std::getenv("RTW_SU")) su = std::max(1, std::atoi(e));   // tuning knob (samples per work unit)
   su = std::min<unsigned long long>(su, S);
   p->su = static_cast<uint32_t>(su);
@@ -467,11 +515,74 @@ int rtw_flatten_info(const rtw_scene_desc* desc, rtw_flatten_report* out) {
   out->n_bvh_nodes = hf.n_nodes; out->leaf_direct = hf.leaf_direct; out->arena_bytes = static_cast<int64_t>(hf.bytes);
   out->flatten_ms = now_ms() - t0; out->bvh_build_ms = hf.bvh_ms;
   {
-    const size_t tables = 16 + static_cast<size_t>(hf.n_nodes) * 64 + ((hf.n_leaf_refs * 4 + 15) & ~size_t(15)) +
-                          static_cast<size_t>(hf.n_static + hf.n_moving) * 32 + static_cast<size_t>(hf.n_tri) * 48;
-    const rtw::BvhPlan plan = rtw::plan_bvh(tables, hf.n_tri, hf.leaf_direct != 0, false);
+    const size_t tables = 16 + (hf.n_cw > 0 ? static_cast<size_t>(hf.n_cw) * 80 : static_cast<size_t>(hf.n_nodes) * 64) + ((hf.n_leaf_refs * 4 + 15) & ~size_t(15)) +
+                          static_cast<size_t>(hf.n_static + hf.n_moving) * 32 + static_cast<size_t>(hf.n_cw > 0 ? hf.n_records : hf.n_tri) * 48;
+    const rtw::BvhPlan plan = rtw::plan_bvh(tables, hf.n_tri, hf.leaf_direct != 0, false, hf.n_cw > 0);
     out->bvh_variant = plan.variant; out->bvh_warps_per_cta = plan.warps; out->bvh_tables_in_smem = plan.tables_in_smem ? 1 : 0;
     out->reserved2 = 0; out->bvh_smem_bytes = static_cast<int64_t>(plan.smem_bytes);
+  }
+  if (hf.n_cw > 0) {
+    // compressed wide BVH: every leaf record referenced exactly once, and every dequantised child box contains the exact bounds of
+    // everything below it (triangle vertices, swept sphere bounds), checked bottom-up
+    const rtw::CwNode* cwn = reinterpret_cast<const rtw::CwNode*>(hf.host.get() + hf.o_cw);
+    const float4* rec = reinterpret_cast<const float4*>(hf.host.get() + hf.o_tri);
+    std::vector<uint8_t> seen(static_cast<size_t>(hf.n_records), 0);
+    int64_t errors = 0;
+    int depth_max = 0;
+    struct Walk {
+      const rtw::CwNode* n; const float4* rec; std::vector<uint8_t>& seen; int64_t& errors; int& depth_max; int32_t n_cw;
+      rtw::Box3 visit(uint32_t idx, int depth) {
+        rtw::Box3 all; all.reset();
+        if (idx >= static_cast<uint32_t>(n_cw) || depth > 64) { ++errors; return all; }
+        depth_max = std::max(depth_max, depth);
+        const rtw::CwNode& nd = n[idx];
+        float p[3]; std::memcpy(p, nd.w, 12);
+        const uint32_t e = nd.w[3], imask = e >> 24;
+        uint8_t meta[8], q[6][8];
+        std::memcpy(meta, &nd.w[6], 8);
+        for (int a = 0; a < 6; ++a) std::memcpy(q[a], &nd.w[8 + 2 * a], 8);
+        uint32_t rank = 0;
+        for (int s = 0; s < 8; ++s) {
+          if (meta[s] == 0) { if (imask >> s & 1) ++errors; continue; }
+          rtw::Box3 below; below.reset();
+          const bool inner = (meta[s] & 0x18) == 0x18;
+          if (inner != ((imask >> s & 1) != 0)) ++errors;
+          if (inner) {
+            if ((meta[s] & 0x1f) != 24 + s || (meta[s] >> 5) != 1) ++errors;
+            below = visit(nd.w[4] + rank++, depth + 1);
+          } else {
+            const uint32_t unary = meta[s] >> 5, cnt = unary == 1 ? 1 : (unary == 3 ? 2 : (unary == 7 ? 3 : 0)), first = nd.w[5] + (meta[s] & 0x1f);
+            if (cnt == 0) ++errors;
+            for (uint32_t k = 0; k < cnt; ++k) {
+              const size_t P = first + k;
+              if (P >= seen.size() || seen[P]++) { ++errors; continue; }
+              const float4 q0 = rec[3 * P], q1 = rec[3 * P + 1], q2 = rec[3 * P + 2];
+              if (q2.x != q2.x) {   // sphere record: swept bounds
+                const float r = std::fabs(q1.w);
+                const float c0[3] = {q0.x, q0.y, q0.z}, c1[3] = {q0.x + q1.x, q0.y + q1.y, q0.z + q1.z};
+                for (int a = 0; a < 3; ++a) { below.lo[a] = std::min(below.lo[a], std::min(c0[a], c1[a]) - r); below.hi[a] = std::max(below.hi[a], std::max(c0[a], c1[a]) + r); }
+              } else {
+                const float va[3] = {q0.x, q0.y, q0.z}, vb[3] = {q0.x + q1.x, q0.y + q1.y, q0.z + q1.z}, vc[3] = {q0.x + q2.x, q0.y + q2.y, q0.z + q2.z};
+                below.grow(va); below.grow(vb); below.grow(vc);
+              }
+            }
+          }
+          for (int a = 0; a < 3; ++a) {
+            const double step = std::ldexp(1.0, static_cast<int>(e >> (8 * a) & 0xff) - 127);
+            const double lo = p[a] + q[a][s] * step, hi = p[a] + q[3 + a][s] * step;
+            if (!(lo <= below.lo[a] && below.hi[a] <= hi)) ++errors;
+          }
+          all.grow(below);
+        }
+        return all;
+      }
+    } walk{cwn, rec, seen, errors, depth_max, hf.n_cw};
+    walk.visit(0, 1);
+    for (uint8_t c : seen) if (c != 1) ++errors;
+    out->n_bvh_nodes = hf.n_cw;
+    out->bvh_max_depth = depth_max;
+    out->bvh_errors = errors;
+    return 0;
   }
   // structural self-check of the tree: every primitive referenced exactly once, child boxes inside the parent box
   const rtw::PackedNode* nodes = reinterpret_cast<const rtw::PackedNode*>(hf.host.get() + hf.o_nodes);

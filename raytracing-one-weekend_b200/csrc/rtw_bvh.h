@@ -7,7 +7,9 @@
 #include <cmath>
 #include <future>
 #include <cstdint>
+#include <cstring>
 #include <limits>
+#include <thread>
 #include <vector>
 
 namespace rtw {
@@ -31,6 +33,13 @@ struct PackedNode {  // 4 x float4, see DevScene::nodes: each child box as centr
 };
 constexpr float kEmptyChildCentre = 3.0e38f;  // centre of a never-entered filler child (half-extent 0)
 static_assert(sizeof(PackedNode) == 64, "node must be 64 bytes");
+
+// Binary tree with exact child boxes and subtree sizes: the input of the wide-tree collapse (CwBuilder below).  Host only.
+struct BinNode {
+  Box3 box[2];
+  int32_t child[2];   // >= 0: inner node index; < 0: ~(reference | kDirectMark) of a single primitive
+  uint32_t count[2];  // primitives below each child
+};
 
 class BvhBuilder {
  public:
@@ -76,6 +85,19 @@ class BvhBuilder {
   int32_t empty_leaf() const { return kMaxLeaf == 1 ? static_cast<int32_t>(~kDirectMark) : ~0; }
   // Same, for a caller that already holds the records and the destination of the nodes (max(n - 1, 1) entries):
   // single-primitive leaves only.  `items` is reordered.  Returns the number of nodes written.
+  // The same tree as BinNodes (exact boxes, subtree sizes) for the wide-tree collapse: n - 1 entries for n >= 2 items.
+  size_t build_items_binary(std::vector<Item>& items, BinNode* out) {
+    const size_t n = items.size();
+    if (n < 2) return 0;
+    for (Item& it : items)
+      for (int k = 0; k < 3; ++k) it.c[k] = 0.5f * (it.box.lo[k] + it.box.hi[k]);
+    items_.swap(items);
+    bin_nodes_ = out;
+    direct_node(0, 0, n, 0);
+    bin_nodes_ = nullptr;
+    items_.swap(items);
+    return n - 1;
+  }
   size_t build_items_direct(std::vector<Item>& items, PackedNode* out) {
     const size_t n = items.size();
     if (n == 0) return 0;
@@ -231,10 +253,18 @@ class BvhBuilder {
     }
     const size_t nl = mid - begin;
     const size_t left_idx = idx + 1, right_idx = idx + 1 + (nl > 1 ? nl - 1 : 0);
-    PackedNode nd{};
-    set_child(nd, 0, lb, direct_child_code(left_idx, begin, mid));
-    set_child(nd, 1, rb, direct_child_code(right_idx, mid, end));
-    (ext_nodes_ ? ext_nodes_ : nodes_.data())[idx] = nd;
+    if (bin_nodes_) {
+      BinNode bn;
+      bn.box[0] = lb; bn.box[1] = rb;
+      bn.child[0] = direct_child_code(left_idx, begin, mid); bn.child[1] = direct_child_code(right_idx, mid, end);
+      bn.count[0] = static_cast<uint32_t>(nl); bn.count[1] = static_cast<uint32_t>(n - nl);
+      bin_nodes_[idx] = bn;
+    } else {
+      PackedNode nd{};
+      set_child(nd, 0, lb, direct_child_code(left_idx, begin, mid));
+      set_child(nd, 1, rb, direct_child_code(right_idx, mid, end));
+      (ext_nodes_ ? ext_nodes_ : nodes_.data())[idx] = nd;
+    }
     // big subtrees go to other threads (disjoint item and node ranges)
     std::future<void> task;
     if (nl > 1) {
@@ -246,6 +276,7 @@ class BvhBuilder {
   }
   std::vector<Item> items_;
   PackedNode* ext_nodes_ = nullptr;
+  BinNode* bin_nodes_ = nullptr;
   std::atomic<int> max_depth_{0};
   void note_depth(int d) { int cur = max_depth_.load(std::memory_order_relaxed); while (d > cur && !max_depth_.compare_exchange_weak(cur, d, std::memory_order_relaxed)) {} }
 
@@ -364,6 +395,227 @@ class BvhBuilder {
     set_child(nd, 0, lb, lc);
     set_child(nd, 1, rb, rc);
     nodes_[idx] = nd;
+  }
+};
+
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Compressed wide BVH (after Ylitie, Karras, Laine: "Efficient Incoherent Ray Traversal on GPUs Through Compressed Wide BVHs", HPG 2017):
+// 8-wide nodes of 80 bytes holding the children's boxes quantised to 8 bits per plane on a per-node power-of-two grid, children
+// placed in slots by octant so that traversal order is a bit trick instead of a sort.  Built by collapsing the binary SAH tree above.
+// Used for every scene with triangles (the mesh path): a 991k-triangle mesh needs 63 MB of 64-byte binary nodes, 5.6 MB of these,
+// and a ray makes a third of the dependent node fetches.
+//
+// Node layout (5 x 16 bytes; word = little-endian uint32):
+//   w0..w2  p.x p.y p.z   origin of the quantisation grid (float bits)
+//   w3      e.x | e.y << 8 | e.z << 16 | imask << 24      biased exponents (grid step 2^(e-127) per axis), bit i of imask: slot i is an inner node
+//   w4      child_base    index of the first inner child (inner children are contiguous, in slot order)
+//   w5      prim_base     index of the first leaf primitive of this node (leaf primitives are contiguous, in slot order)
+//   w6,w7   meta[8]       per slot: 0 = empty; inner: 0x20 | (24 + slot); leaf: (unary count 1/3/7) << 5 | offset of its first primitive from prim_base
+//   w8,w9   qlo.x[8]   w10,w11 qlo.y[8]   w12,w13 qlo.z[8]   w14,w15 qhi.x[8]   w16,w17 qhi.y[8]   w18,w19 qhi.z[8]
+// Slot s sits on the + side of axis k iff bit k of s is set.  Child boxes are dequantised as p + q * 2^(e-127) and contain the exact
+// boxes widened by `margin` (fp32 slack of the traversal arithmetic) plus an eighth of a grid step.
+// ---------------------------------------------------------------------------------------------------------------------------------
+struct CwNode { uint32_t w[20]; };
+static_assert(sizeof(CwNode) == 80, "wide node must be 80 bytes");
+
+class CwBuilder {
+ public:
+  int max_leaf = 3;       // primitives per leaf child (1..3), same kind only
+  double margin = 0.0;    // absolute widening of every child box (4 ulp of the scene's largest coordinate)
+
+  // bin: n_items - 1 binary nodes (n_items >= 2), or none with single_ref set (n_items == 1).  Outputs the nodes in breadth-first order
+  // and the primitive references in leaf order.
+  void build(const BinNode* bin, size_t n_bin, const Box3* single_box, uint32_t single_ref) {
+    nodes_.clear(); leaf_order_.clear(); depth_ = 0;
+    bin_ = bin;
+    if (n_bin == 0) {
+      if (!single_box) return;
+      Plan pl; pl.n = 1; pl.bin[0] = -1; pl.box[0] = *single_box; pl.nprim[0] = 1; pl.prims[0][0] = single_ref;
+      for (int s = 0; s < 8; ++s) pl.slot_child[s] = s == 0 ? 0 : -1;
+      CwNode nd; encode(pl, 0, 0, nd);
+      nodes_.push_back(nd); leaf_order_.push_back(single_ref); depth_ = 1;
+      return;
+    }
+    std::vector<int32_t> level{0};          // binary roots of the wide nodes of the current level; wide index = level_base + position
+    size_t level_base = 0, prim_cursor = 0;
+    while (!level.empty()) {
+      ++depth_;
+      const size_t m = level.size();
+      std::vector<Plan> plans(m);
+      parallel_for(m, [&](size_t i) { plan_node(level[i], plans[i]); });
+      // serial prefix sums: children of one node are contiguous (next level, in node then slot order), and so are its leaf primitives
+      std::vector<uint32_t> child_base(m), prim_base(m);
+      size_t next_count = 0;
+      for (size_t i = 0; i < m; ++i) {
+        child_base[i] = static_cast<uint32_t>(level_base + m + next_count);
+        prim_base[i] = static_cast<uint32_t>(prim_cursor);
+        for (int s = 0; s < 8; ++s) {
+          if (plans[i].slot_child[s] < 0) continue;
+          const int c = plans[i].slot_child[s];
+          if (plans[i].bin[c] >= 0) ++next_count; else prim_cursor += static_cast<size_t>(plans[i].nprim[c]);
+        }
+      }
+      nodes_.resize(level_base + m);
+      leaf_order_.resize(prim_cursor);
+      std::vector<int32_t> next(next_count);
+      parallel_for(m, [&](size_t i) {
+        encode(plans[i], child_base[i], prim_base[i], nodes_[level_base + i]);
+        size_t at = child_base[i] - (level_base + m), pp = prim_base[i];
+        for (int s = 0; s < 8; ++s) {
+          const int c = plans[i].slot_child[s];
+          if (c < 0) continue;
+          if (plans[i].bin[c] >= 0) next[at++] = plans[i].bin[c];
+          else for (int k = 0; k < plans[i].nprim[c]; ++k) leaf_order_[pp++] = plans[i].prims[c][k];
+        }
+      });
+      level_base += m;
+      level.swap(next);
+    }
+  }
+  const std::vector<CwNode>& nodes() const { return nodes_; }
+  const std::vector<uint32_t>& leaf_order() const { return leaf_order_; }   // (kind << 30) | table index, in leaf order
+  int depth() const { return depth_; }
+
+ private:
+  struct Plan {
+    int n = 0;
+    int32_t bin[8];          // >= 0: binary node that roots the inner child; -1: leaf child
+    Box3 box[8];
+    int nprim[8];
+    uint32_t prims[8][3];
+    int slot_child[8];       // slot -> child index or -1
+  };
+  const BinNode* bin_ = nullptr;
+  std::vector<CwNode> nodes_;
+  std::vector<uint32_t> leaf_order_;
+  int depth_ = 0;
+
+  template <typename F>
+  static void parallel_for(size_t n, F&& fn) {
+    const size_t hw = std::max<size_t>(1, std::thread::hardware_concurrency());
+    const size_t nt = n >= 4096 ? std::min<size_t>(hw, 32) : 1;
+    if (nt <= 1) { for (size_t i = 0; i < n; ++i) fn(i); return; }
+    std::vector<std::future<void>> tasks;
+    for (size_t t = 1; t < nt; ++t) tasks.push_back(std::async(std::launch::async, [&fn, t, n, nt] { for (size_t i = n * t / nt; i < n * (t + 1) / nt; ++i) fn(i); }));
+    for (size_t i = 0; i < n / nt; ++i) fn(i);
+    for (auto& t : tasks) t.get();
+  }
+
+  static uint32_t ref_of(int32_t code) { return static_cast<uint32_t>(~code) & ~BvhBuilder::kDirectMark; }
+  // primitives below a binary child, if it can be ONE leaf (<= max_leaf primitives of one kind)
+  bool leafable(int32_t code, uint32_t count, uint32_t* out, int* n) const {
+    if (count > static_cast<uint32_t>(max_leaf)) return false;
+    *n = 0;
+    gather(code, out, n);
+    for (int k = 1; k < *n; ++k)
+      if ((out[k] >> 30) != (out[0] >> 30)) return false;
+    return true;
+  }
+  void gather(int32_t code, uint32_t* out, int* n) const {
+    if (code < 0) { out[(*n)++] = ref_of(code); return; }
+    gather(bin_[code].child[0], out, n);
+    gather(bin_[code].child[1], out, n);
+  }
+
+  void plan_node(int32_t root, Plan& pl) const {
+    struct Open { int32_t code; uint32_t count; Box3 box; bool leaf; int np; uint32_t prims[3]; };
+    Open ch[8];
+    int n = 0;
+    auto add = [&](int32_t code, uint32_t count, const Box3& box) {
+      Open& o = ch[n++];
+      o.code = code; o.count = count; o.box = box; o.np = 0;
+      o.leaf = leafable(code, count, o.prims, &o.np);
+    };
+    add(bin_[root].child[0], bin_[root].count[0], bin_[root].box[0]);
+    add(bin_[root].child[1], bin_[root].count[1], bin_[root].box[1]);
+    while (n < 8) {   // open the inner child with the largest surface area
+      int best = -1; float best_area = -1.0f;
+      for (int i = 0; i < n; ++i)
+        if (!ch[i].leaf && ch[i].box.half_area() > best_area) { best_area = ch[i].box.half_area(); best = i; }
+      if (best < 0) break;
+      const BinNode& b = bin_[ch[best].code];
+      ch[best] = ch[n - 1]; --n;
+      add(b.child[0], b.count[0], b.box[0]);
+      add(b.child[1], b.count[1], b.box[1]);
+    }
+    pl.n = n;
+    Box3 nb; nb.reset();
+    for (int i = 0; i < n; ++i) {
+      pl.bin[i] = ch[i].leaf ? -1 : ch[i].code;
+      pl.box[i] = ch[i].box;
+      pl.nprim[i] = ch[i].leaf ? ch[i].np : 0;
+      for (int k = 0; k < 3; ++k) pl.prims[i][k] = ch[i].prims[k];
+      nb.grow(ch[i].box);
+    }
+    // children -> slots: greedily the (child, slot) pair whose centroid offset points most along the slot's octant direction
+    float cost[8][8];
+    for (int i = 0; i < n; ++i)
+      for (int s = 0; s < 8; ++s) {
+        float c = 0.0f;
+        for (int k = 0; k < 3; ++k) {
+          const float off = 0.5f * (pl.box[i].lo[k] + pl.box[i].hi[k]) - 0.5f * (nb.lo[k] + nb.hi[k]);
+          c += (s >> k & 1) ? off : -off;
+        }
+        cost[i][s] = c;
+      }
+    bool child_done[8] = {false}, slot_done[8] = {false};
+    for (int s = 0; s < 8; ++s) pl.slot_child[s] = -1;
+    for (int round = 0; round < n; ++round) {
+      int bi = -1, bs = -1; float bc = -std::numeric_limits<float>::infinity();
+      for (int i = 0; i < n; ++i) {
+        if (child_done[i]) continue;
+        for (int s = 0; s < 8; ++s)
+          if (!slot_done[s] && cost[i][s] > bc) { bc = cost[i][s]; bi = i; bs = s; }
+      }
+      child_done[bi] = true; slot_done[bs] = true; pl.slot_child[bs] = bi;
+    }
+  }
+
+  void encode(const Plan& pl, uint32_t child_base, uint32_t prim_base, CwNode& nd) const {
+    std::memset(&nd, 0, sizeof nd);
+    Box3 nb; nb.reset();
+    for (int i = 0; i < pl.n; ++i) nb.grow(pl.box[i]);
+    float p[3]; int eb[3]; double step[3];
+    for (int k = 0; k < 3; ++k) {
+      const double lo = static_cast<double>(nb.lo[k]) - margin, hi = static_cast<double>(nb.hi[k]) + margin;
+      // step = smallest power of two with 249 steps covering the extent (the rest of the 255 is slack for the outward rounding), not
+      // below 8 * margin so that an eighth of a step still covers the traversal's fp32 slack; grid origin a quarter step below lo
+      const double need = std::max((hi - lo) / 249.0, std::max(8.0 * margin, 1e-30));
+      int e = static_cast<int>(std::ceil(std::log2(need)));
+      if (std::ldexp(1.0, e) < need) ++e;
+      e = std::min(std::max(e, -120), 120);
+      const double origin = lo - 0.25 * std::ldexp(1.0, e);
+      float pf = static_cast<float>(origin);
+      if (static_cast<double>(pf) > origin) pf = std::nextafter(pf, -std::numeric_limits<float>::infinity());
+      p[k] = pf; eb[k] = e + 127; step[k] = std::ldexp(1.0, e);
+    }
+    uint32_t imask = 0;
+    uint8_t meta[8] = {0}, q[6][8];
+    for (int s = 0; s < 8; ++s) { for (int a = 0; a < 3; ++a) { q[a][s] = 255; q[3 + a][s] = 0; } }
+    uint32_t inner_rank = 0, prim_off = 0;
+    for (int s = 0; s < 8; ++s) {
+      const int c = pl.slot_child[s];
+      if (c < 0) continue;
+      if (pl.bin[c] >= 0) { imask |= 1u << s; meta[s] = static_cast<uint8_t>(0x20 | (24 + s)); ++inner_rank; }
+      else {
+        const uint32_t unary = pl.nprim[c] == 1 ? 1u : (pl.nprim[c] == 2 ? 3u : 7u);
+        meta[s] = static_cast<uint8_t>((unary << 5) | prim_off);
+        prim_off += static_cast<uint32_t>(pl.nprim[c]);
+      }
+      for (int k = 0; k < 3; ++k) {
+        const double lo = (static_cast<double>(pl.box[c].lo[k]) - margin - static_cast<double>(p[k])) / step[k] - 0.125;
+        const double hi = (static_cast<double>(pl.box[c].hi[k]) + margin - static_cast<double>(p[k])) / step[k] + 0.125;
+        q[k][s] = static_cast<uint8_t>(std::min(std::max(std::floor(lo), 0.0), 255.0));
+        q[3 + k][s] = static_cast<uint8_t>(std::min(std::max(std::ceil(hi), 0.0), 255.0));
+      }
+    }
+    (void)inner_rank;
+    std::memcpy(&nd.w[0], &p[0], 4); std::memcpy(&nd.w[1], &p[1], 4); std::memcpy(&nd.w[2], &p[2], 4);
+    nd.w[3] = static_cast<uint32_t>(eb[0]) | static_cast<uint32_t>(eb[1]) << 8 | static_cast<uint32_t>(eb[2]) << 16 | imask << 24;
+    nd.w[4] = child_base; nd.w[5] = prim_base;
+    std::memcpy(&nd.w[6], meta, 8);
+    for (int a = 0; a < 6; ++a) std::memcpy(&nd.w[8 + 2 * a], q[a], 8);
   }
 };
 

@@ -19,6 +19,7 @@ namespace rtw {
 constexpr float kTMin = 0.001f;  // render.cpp:33 default tmin of BVHNode::hit
 constexpr float kInf = __builtin_huge_valf();
 constexpr int kBvhStack = 64;  // the host builder bounds the tree depth by 32 + log2(n) (rtw_bvh.h) and rtw_scene_upload checks it
+constexpr int kCwStack = 32;   // compressed wide BVH: at most one stack entry per level, rtw_scene_upload checks the depth
 
 // ---------------------------------------------------------------------------------------------------------
 // Device scene (flattened SoA; built by rtw_scene_upload)
@@ -57,6 +58,12 @@ struct DevScene {
   const uint32_t* leafRefs;  // (kind << 30) | index, kind 0 = sphere table index, 1 = triangle index
   int32_t n_nodes;
   int32_t leaf_direct;       // 1: single-primitive leaves, child code = ~reference (leafRefs unused)
+  // Scenes with triangles use a compressed 8-wide BVH instead (rtw_bvh.h: CwNode, 80 bytes = 5 x uint4 per node).  Then `tri` / `triId`
+  // hold the LEAF PRIMITIVES in leaf order (48-byte records, the up-to-3 primitives of a leaf next to each other): a triangle as
+  // above, a small sphere as (sphA entry) (sphB entry) (NaN, sphere table index as int bits, 0, 0); n_tri counts these records.
+  const uint4* cwNodes;
+  int32_t n_cw_nodes;
+  int32_t cw_has_spheres;    // 1: some leaf records are spheres (the NaN tag has to be looked at)
   // materials
   const float4* matA;  // (albedo.r, albedo.g, albedo.b, fuzz)
   const float2* matB;  // (ior, kind as int bits)
@@ -202,6 +209,90 @@ __device__ __forceinline__ void node_slabs(const float4 q0, const float4 q1, con
   cx = fmaf(q1.z, idx, -odx); cy = fmaf(q1.w, idy, -ody); cz = fmaf(q2.x, idz, -odz);
   rn = fmaxf(fmaxf(fmaf(-q2.y, ax, cx), fmaf(-q2.z, ay, cy)), fmaxf(fmaf(-q2.w, az, cz), kTMin));
   rf = fminf(fminf(fmaf(q2.y, ax, cx), fmaf(q2.z, ay, cy)), fminf(fmaf(q2.w, az, cz), tmax));
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Compressed wide BVH traversal (node layout and references: rtw_bvh.h, CwNode).  Replaces BVHNode::hit (render.cpp:52-71) for
+// scenes with triangles.  A traversal state is two 64-bit groups and a stack of node groups:
+//   ngroup = (child_base, hit bits of the inner children in bits 24..31 | imask in bits 0..7)
+//   tgroup = (prim_base, hit bits of this node's leaf primitives in bits 0..23)
+// The hit bit of the inner child in slot s sits at 24 + (s ^ oct_inv): taking the highest set bit first visits the children front to
+// back for the ray's octant without comparing distances.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {  // every byte -> 0xff if its top bit is set, else 0x00
+  uint32_t v;
+  asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(v) : "r"(x));
+  return v;
+}
+// byte j of x -> the float 256 + b / 128 (bits 0x4380bb00): one PRMT instead of a shift, a mask and an integer-to-float conversion.
+// With A = 128 * step * (1/d) and C = (p - o) * (1/d) - 256 * A the slab parameter of plane b is fma(f, A, C).
+template <int J>
+__device__ __forceinline__ float q8_to_float(uint32_t x) {
+  return __uint_as_float(__byte_perm(x, 0x43800000u, 0x7604u | (J << 4)));
+}
+__device__ __forceinline__ uint4 ldg128(const uint4* p) {
+  uint4 v;
+  asm("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t cw_oct_inv4(F3 d) {
+  const uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+  return (7u - oct) * 0x01010101u;
+}
+
+// Slab test of the (up to) 8 children of node `index` against [tmin, tmax] (Aabb::hit, common-model.h:71-84, on dequantised boxes).
+template <bool SMEM>
+__device__ __forceinline__ void cw_intersect_node(const uint4* __restrict__ nodes, uint32_t index, F3 o, float idx, float idy, float idz,
+                                                  uint32_t oct_inv4, float tmin, float tmax, uint2& ngroup, uint2& tgroup) {
+  const uint4* np = nodes + 5u * index;
+  uint4 n0, n1, n2, n3, n4;
+  if (SMEM) { n0 = np[0]; n1 = np[1]; n2 = np[2]; n3 = np[3]; n4 = np[4]; }
+  else { n0 = ldg128(np); n1 = ldg128(np + 1); n2 = ldg128(np + 2); n3 = ldg128(np + 3); n4 = ldg128(np + 4); }
+  const uint32_t e = n0.w;
+  const float ax = __uint_as_float(((e & 0xffu) + 7u) << 23) * idx;
+  const float ay = __uint_as_float(((e >> 8 & 0xffu) + 7u) << 23) * idy;
+  const float az = __uint_as_float(((e >> 16 & 0xffu) + 7u) << 23) * idz;
+  const float cx = fmaf(__uint_as_float(n0.x) - o.x, idx, -256.0f * ax);
+  const float cy = fmaf(__uint_as_float(n0.y) - o.y, idy, -256.0f * ay);
+  const float cz = fmaf(__uint_as_float(n0.z) - o.z, idz, -256.0f * az);
+  const bool nx = idx < 0.0f, ny = idy < 0.0f, nz = idz < 0.0f;
+  uint32_t hits = 0u;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const uint32_t meta4 = half ? n1.w : n1.z;
+    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+    const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+    const uint32_t bit_index4 = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+    const uint32_t lox = half ? n2.y : n2.x, loy = half ? n2.w : n2.z, loz = half ? n3.y : n3.x;
+    const uint32_t hix = half ? n3.w : n3.z, hiy = half ? n4.y : n4.x, hiz = half ? n4.w : n4.z;
+    const uint32_t nearx = nx ? hix : lox, farx = nx ? lox : hix;
+    const uint32_t neary = ny ? hiy : loy, fary = ny ? loy : hiy;
+    const uint32_t nearz = nz ? hiz : loz, farz = nz ? loz : hiz;
+#define RTW_CW_CHILD(J)                                                                                                   \
+    {                                                                                                                       \
+      const float t0 = fmaxf(fmaxf(fmaf(q8_to_float<J>(nearx), ax, cx), fmaf(q8_to_float<J>(neary), ay, cy)),              \
+                             fmaxf(fmaf(q8_to_float<J>(nearz), az, cz), tmin));                                             \
+      const float t1 = fminf(fminf(fmaf(q8_to_float<J>(farx), ax, cx), fmaf(q8_to_float<J>(fary), ay, cy)),                \
+                             fminf(fmaf(q8_to_float<J>(farz), az, cz), tmax));                                              \
+      if (t0 <= t1) hits |= ((child_bits4 >> (8 * J)) & 0xffu) << ((bit_index4 >> (8 * J)) & 0xffu);                        \
+    }
+    RTW_CW_CHILD(0) RTW_CW_CHILD(1) RTW_CW_CHILD(2) RTW_CW_CHILD(3)
+#undef RTW_CW_CHILD
+  }
+  ngroup = make_uint2(n1.x, (hits & 0xff000000u) | (e >> 24));
+  tgroup = make_uint2(n1.y, hits & 0x00ffffffu);
+}
+
+// Takes the nearest not yet visited inner child out of ngroup (pushing what remains) and returns its node index.
+__device__ __forceinline__ uint32_t cw_pop_child(uint2& ngroup, uint32_t oct_inv4, uint2* stack, int& sp) {
+  const uint32_t bit = 31u - __clz(ngroup.y);             // highest hit bit: in 24..31
+  ngroup.y &= ~(1u << bit);
+  const uint32_t imask = ngroup.y & 0xffu, base = ngroup.x;
+  if (ngroup.y & 0xff000000u) { if (sp < kCwStack) stack[sp++] = ngroup; }
+  const uint32_t slot = (bit - 24u) ^ (oct_inv4 & 0xffu);
+  return base + __popc(imask & ~(0xffffffffu << slot));
 }
 
 // sphere_hit_helper (common-model.cpp:64-91).  Same roots and the same accept rule (nearer root if inside

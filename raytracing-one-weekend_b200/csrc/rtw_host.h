@@ -52,8 +52,9 @@ struct EventPair {  // destroyed on every exit path
 struct HostFlat {
   std::unique_ptr<unsigned char[]> host;
   size_t bytes = 0;
-  size_t o_sA = 0, o_sB = 0, o_sId = 0, o_big = 0, o_tri = 0, o_triId = 0, o_nodes = 0, o_refs = 0, o_matA = 0, o_matB = 0, o_ctr = 0;
+  size_t o_sA = 0, o_sB = 0, o_sId = 0, o_big = 0, o_tri = 0, o_triId = 0, o_nodes = 0, o_refs = 0, o_matA = 0, o_matB = 0, o_ctr = 0, o_cw = 0;
   int32_t n_static = 0, n_moving = 0, n_big = 0, n_tri = 0, n_nodes = 0, leaf_direct = 0, bvh_depth = 0;
+  int32_t n_cw = 0, n_records = 0, cw_has_spheres = 0;   // compressed wide BVH (scenes with triangles): nodes, leaf-ordered records
   size_t n_leaf_refs = 0;
   double bvh_ms = 0.0;
 };

@@ -69,7 +69,11 @@ struct BvhPlan {
   bool tables_in_smem;
   size_t smem_bytes;    // dynamic shared memory of the launch
 };
-inline BvhPlan plan_bvh(size_t table_bytes, int n_tri, bool leaf_direct, bool force_perlane) {
+inline BvhPlan plan_bvh(size_t table_bytes, int n_tri, bool leaf_direct, bool force_perlane, bool cw = false) {
+  if (cw) {  // scenes with triangles: compressed wide BVH, per-lane state machine, three CTAs per SM (the 8-child slab test needs registers)
+    if (table_bytes <= kPerLaneSmemTables) return {RTW_BVH_CWIDE, 8, true, table_bytes};
+    return {RTW_BVH_CWIDE, 8, false, 0};
+  }
   const size_t wf_warp = wf_warp_bytes(kWfRecords);
   if (leaf_direct && !force_perlane) {
     if (table_bytes + 28 * wf_warp <= kSmemCap) return {RTW_BVH_WAVEFRONT, 28, true, table_bytes + 28 * wf_warp};

@@ -19,6 +19,8 @@
 // Radiance is accumulated as int64 fixed point (2^-32) with RED.ADD.64: integer sums are exact, so the image
 // does not depend on scheduling order or on how samples are sharded over GPUs.
 #include <atomic>
+#include <cstdlib>
+#include <algorithm>
 
 #include "rtw_internal.h"
 
@@ -227,6 +229,60 @@ __device__ __forceinline__ void trace_spheres(const DevScene& sc, const float4* 
   for (int r = 0; r < R; ++r)
     if (alive[r]) trace_big_spheres(sc, mk<float>(ray.ox[r], ray.oy[r], ray.oz[r]), mk<float>(ray.dx[r], ray.dy[r], ray.dz[r]),
                                     ray.tm[r], best_t[r], best_i[r]);
+}
+
+template <bool SMEM>
+__device__ __forceinline__ float4 ld4(const float4* p, int i) { return SMEM ? p[i] : __ldg(p + i); }
+template <bool SMEM>
+__device__ __forceinline__ uint32_t ld1(const uint32_t* p, int i) { return SMEM ? p[i] : __ldg(p + i); }
+
+// One leaf primitive of a compressed-wide-BVH scene: record P of the leaf-ordered table (DevScene::tri).
+template <bool SMEM, bool STATS>
+__device__ __forceinline__ void cw_test_prim(const DevScene& sc, const float4* __restrict__ prims, uint32_t P, F3 o, F3 d, float qa, float qia, float tm,
+                                             float& best_t, int& best_i, unsigned long long& n_sph, unsigned long long& n_tri) {
+  const int b = 3 * static_cast<int>(P);
+  const float4 q0 = ld4<SMEM>(prims, b), q1 = ld4<SMEM>(prims, b + 1), q2 = ld4<SMEM>(prims, b + 2);
+  if (sc.cw_has_spheres && q2.x != q2.x) {   // NaN tag: a small sphere (sphA entry, sphB entry, table index)
+    if (STATS) ++n_sph;
+    const float t = sphere_hit_fast(o, d, qa, qia, mk<float>(fmaf(tm, q1.x, q0.x), fmaf(tm, q1.y, q0.y), fmaf(tm, q1.z, q0.z)), q1.w, kTMin, best_t);
+    if (t >= 0.0f) { best_t = t; best_i = __float_as_int(q2.y); }
+  } else {
+    if (STATS) ++n_tri;
+    const float t = triangle_hit_fast(o, d, mk<float>(q0.x, q0.y, q0.z), mk<float>(q1.x, q1.y, q1.z), mk<float>(q2.x, q2.y, q2.z),
+                                        mk<float>(q0.w, q1.w, q2.w), kTMin, best_t);
+    if (t >= 0.0f) { best_t = t; best_i = kHitTri | static_cast<int>(P); }
+  }
+}
+
+// Compressed wide BVH, one ray per lane, run to completion (K3 primary-hit mode; the render kernel runs the same steps as a
+// resumable state machine).
+template <bool STATS>
+__device__ __forceinline__ void trace_cw(const DevScene& sc, F3 o, F3 d, float tm, float& best_t, int& best_i,
+                                         unsigned long long& n_nodes, unsigned long long& n_sph, unsigned long long& n_tri) {
+  best_t = kInf; best_i = kMiss;
+  const float qa = dot(d, d), qia = fast_rcp(qa);
+  const float idx = fast_rcp(d.x), idy = fast_rcp(d.y), idz = fast_rcp(d.z);
+  const uint32_t oct_inv4 = cw_oct_inv4(d);
+  uint2 stack[kCwStack];
+  int sp = 0;
+  uint2 ngroup = make_uint2(0u, sc.n_cw_nodes > 0 ? 0x80000000u : 0u), tgroup = make_uint2(0u, 0u);
+  for (;;) {
+    if (ngroup.y & 0xff000000u) {
+      const uint32_t child = cw_pop_child(ngroup, oct_inv4, stack, sp);
+      if (STATS) ++n_nodes;
+      cw_intersect_node<false>(sc.cwNodes, child, o, idx, idy, idz, oct_inv4, kTMin, best_t, ngroup, tgroup);
+    }
+    while (tgroup.y != 0u) {
+      const uint32_t k = 31u - __clz(tgroup.y);
+      tgroup.y &= ~(1u << k);
+      cw_test_prim<false, STATS>(sc, sc.tri, tgroup.x + k, o, d, qa, qia, tm, best_t, best_i, n_sph, n_tri);
+    }
+    if ((ngroup.y & 0xff000000u) == 0u) {
+      if (sp == 0) break;
+      ngroup = stack[--sp];
+    }
+  }
+  trace_big_spheres(sc, o, d, tm, best_t, best_i);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -501,21 +557,16 @@ struct BvhTables {
   const float4* tri;
 };
 
-template <bool SMEM>
-__device__ __forceinline__ float4 ld4(const float4* p, int i) { return SMEM ? p[i] : __ldg(p + i); }
-template <bool SMEM>
-__device__ __forceinline__ uint32_t ld1(const uint32_t* p, int i) { return SMEM ? p[i] : __ldg(p + i); }
-
-template <bool SMEM, bool STATS, int STEPS, int SERVICE_MIN, int MINB>
+template <bool SMEM, bool STATS, int STEPS, int SERVICE_MIN, int MINB, bool CW = false>
 __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __grid_constant__ RenderParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const DevScene& sc = p.sc;
-  BvhTables tb{sc.nodes, sc.leafRefs, sc.sphA, sc.sphB, sc.tri};
+  BvhTables tb{CW ? reinterpret_cast<const float4*>(sc.cwNodes) : sc.nodes, sc.leafRefs, sc.sphA, sc.sphB, sc.tri};
   if (SMEM) {
     // nodes, leafRefs, sphA, sphB, tri back to back (every size a multiple of 16 bytes), one mbarrier for all copies
     const uint32_t nspheres = static_cast<uint32_t>(sc.n_static + sc.n_moving);
-    const uint32_t b_nodes = static_cast<uint32_t>(sc.n_nodes) * 64u, b_refs = (p.n_leaf_refs * 4u + 15u) & ~15u, b_sph = nspheres * 16u,
-                   b_tri = static_cast<uint32_t>(sc.n_tri) * 48u;
+    const uint32_t b_nodes = CW ? static_cast<uint32_t>(sc.n_cw_nodes) * 80u : static_cast<uint32_t>(sc.n_nodes) * 64u,
+                   b_refs = (p.n_leaf_refs * 4u + 15u) & ~15u, b_sph = nspheres * 16u, b_tri = static_cast<uint32_t>(sc.n_tri) * 48u;
     unsigned char* d_nodes = smem_raw + 16;
     unsigned char* d_refs = d_nodes + b_nodes;
     unsigned char* d_sa = d_refs + b_refs;
@@ -534,7 +585,8 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
         for (uint32_t off = 0; off < bytes; off += kChunk)
           tma_bulk_g2s(dst + off, static_cast<const unsigned char*>(src) + off, min(kChunk, bytes - off), bar);
       };
-      copy(d_nodes, sc.nodes, b_nodes); copy(d_refs, sc.leafRefs, b_refs); copy(d_sa, sc.sphA, b_sph); copy(d_sb, sc.sphB, b_sph);
+      copy(d_nodes, CW ? static_cast<const void*>(sc.cwNodes) : static_cast<const void*>(sc.nodes), b_nodes);
+      copy(d_refs, sc.leafRefs, b_refs); copy(d_sa, sc.sphA, b_sph); copy(d_sb, sc.sphB, b_sph);
       copy(d_tri, sc.tri, b_tri);
     }
     uint32_t spins = 0;
@@ -552,6 +604,10 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
   const uint32_t lt = (1u << lane) - 1u;
   const uint2 key = make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32));
   enum : int { DEAD = 0, TRAV = 1, DONE = 2 };
+  // compressed wide BVH (CW): node group / primitive group / octant of the ray in flight, and the stack of node groups
+  uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
+  uint32_t oct_inv4 = 0u;
+  uint2 cw_stack[CW ? kCwStack : 1];
 
   int state = DEAD;
   F3 o = mk<float>(0.f, 0.f, 0.f), d = mk<float>(0.f, 0.f, 1.f);
@@ -561,7 +617,7 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
   // traversal state
   float idx = 0.f, idy = 0.f, idz = 0.f, odx = 0.f, ody = 0.f, odz = 0.f, qa = 1.f, qia = 1.f, best_t = kInf;
   int best_i = kMiss, node = kMiss, sp = 0;
-  int stack[kBvhStack];
+  int stack[CW ? 1 : kBvhStack];
 
   uint32_t pool_next = 0, pool_end = 0, grp = 0, s0 = 0;
   bool exhausted = false;
@@ -570,10 +626,16 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
   auto start_traversal = [&]() {
     qa = dot(d, d); qia = fast_rcp(qa);
     idx = fast_rcp(d.x); idy = fast_rcp(d.y); idz = fast_rcp(d.z);
-    odx = o.x * idx; ody = o.y * idy; odz = o.z * idz;
     best_t = kInf; best_i = kMiss; sp = 0;
-    node = sc.n_nodes > 0 ? 0 : kMiss;
-    state = node == kMiss ? DONE : TRAV;
+    if (CW) {
+      oct_inv4 = cw_oct_inv4(d);
+      ngroup = make_uint2(0u, 0x80000000u); tgroup = make_uint2(0u, 0u);   // the root as the one hit child of a virtual node
+      state = sc.n_cw_nodes > 0 ? TRAV : DONE;
+    } else {
+      odx = o.x * idx; ody = o.y * idy; odz = o.z * idz;
+      node = sc.n_nodes > 0 ? 0 : kMiss;
+      state = node == kMiss ? DONE : TRAV;
+    }
   };
 
   for (;;) {
@@ -662,6 +724,34 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
     // at once in sphere scenes (holding sphere leaves back until 4..16 lanes stand on one lost 3-8 % on the cover scene), once
     // p.leaf_min lanes stand on one in scenes with triangles (measured on the 991k-triangle mesh, Mpaths/s: 1/2/3/4/5/6/8/12 lanes =
     // 3034/3094/3176/3211/3205/3163/3017/2573; suzanne 7290 -> 7345).
+    if constexpr (CW) {
+      // one step = (a) lanes with an unvisited inner child fetch and test that node's 8 children, then (b) lanes holding leaf
+      // primitives test ONE of them -- once p.leaf_min lanes hold some or no lane has a node left to visit (the triangle test runs
+      // at a handful of lanes otherwise), then (c) lanes with neither pop a node group or finish
+#pragma unroll 1
+      for (int step = 0; step < STEPS; ++step) {
+        if (state == TRAV && tgroup.y == 0u && (ngroup.y & 0xff000000u)) {
+          const uint32_t child = cw_pop_child(ngroup, oct_inv4, cw_stack, sp);
+          if (STATS) ++n_nodes;
+          cw_intersect_node<SMEM>(reinterpret_cast<const uint4*>(tb.nodes), child, o, idx, idy, idz, oct_inv4, kTMin, best_t, ngroup, tgroup);
+        }
+        bool do_leaf = true;
+        if (p.leaf_min > 1u) {
+          const uint32_t lm = __ballot_sync(0xffffffffu, state == TRAV && tgroup.y != 0u);
+          const uint32_t im = __ballot_sync(0xffffffffu, state == TRAV && tgroup.y == 0u && (ngroup.y & 0xff000000u));
+          do_leaf = static_cast<uint32_t>(__popc(lm)) >= p.leaf_min || im == 0u;
+        }
+        if (do_leaf && state == TRAV && tgroup.y != 0u) {
+          const uint32_t k = 31u - __clz(tgroup.y);
+          tgroup.y &= ~(1u << k);
+          cw_test_prim<SMEM, STATS>(sc, tb.tri, tgroup.x + k, o, d, qa, qia, tm, best_t, best_i, n_tests, n_tri);
+        }
+        if (state == TRAV && tgroup.y == 0u && (ngroup.y & 0xff000000u) == 0u) {
+          if (sp > 0) ngroup = cw_stack[--sp];
+          else state = DONE;
+        }
+      }
+    } else {
 #pragma unroll 1
     for (int step = 0; step < STEPS; ++step) {
       if (state == TRAV && node >= 0) {
@@ -714,6 +804,7 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
         else { node = kMiss; state = DONE; }
       }
     }
+    }   // binary tree
   }
 
 #pragma unroll
@@ -1102,6 +1193,8 @@ __global__ void __launch_bounds__(kRenderThreads) k_primary_f32(const __grid_con
     float bt[1]; int bi[1];
     trace_spheres<1, false>(sc, sA, sB, ray, alive, bt, bi, c0);
     best_t = bt[0]; best_i = bi[0];
+  } else if (sc.n_cw_nodes > 0) {
+    trace_cw<false>(sc, o, d, tm, best_t, best_i, c0, c1, c2);
   } else {
     trace_bvh<false>(sc, o, d, tm, best_t, best_i, c0, c1, c2);
   }
@@ -1278,9 +1371,9 @@ static cudaError_t launch_sweep_t(const RenderParams& p, int sm_count, size_t sm
   return cudaGetLastError();
 }
 
-template <bool SMEM, bool STATS, int STEPS, int SERVICE_MIN, int MINB>
+template <bool SMEM, bool STATS, int STEPS, int SERVICE_MIN, int MINB, bool CW = false>
 static cudaError_t launch_bvh_t(const RenderParams& p, int sm_count, size_t smem, cudaStream_t stream) {
-  auto kern = k_render_bvh<SMEM, STATS, STEPS, SERVICE_MIN, MINB>;
+  auto kern = k_render_bvh<SMEM, STATS, STEPS, SERVICE_MIN, MINB, CW>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
   int per_sm = 0;
@@ -1316,7 +1409,7 @@ static cudaError_t launch_wf_t(const RenderParams& p, int sm_count, size_t smem,
 static SmemLayout smem_layout(const RenderParams& p) {
   SmemLayout so{};
   const uint32_t nspheres = static_cast<uint32_t>(p.sc.n_static + p.sc.n_moving);
-  so.b_nodes = static_cast<uint32_t>(p.sc.n_nodes) * 64u; so.b_refs = (p.n_leaf_refs * 4u + 15u) & ~15u; so.b_sph = nspheres * 16u;
+  so.b_nodes = p.sc.n_cw_nodes > 0 ? static_cast<uint32_t>(p.sc.n_cw_nodes) * 80u : static_cast<uint32_t>(p.sc.n_nodes) * 64u; so.b_refs = (p.n_leaf_refs * 4u + 15u) & ~15u; so.b_sph = nspheres * 16u;
   so.b_tri = static_cast<uint32_t>(p.sc.n_tri) * 48u;
   so.nodes = 16u; so.refs = so.nodes + so.b_nodes; so.sa = so.refs + so.b_refs; so.sb = so.sa + so.b_sph; so.tri = so.sb + so.b_sph;
   so.records = so.tri + so.b_tri;
@@ -1330,6 +1423,7 @@ cudaError_t launch_render(const RenderParams& p_in, int mode, int rays_per_lane,
   // triangle leaves (a ~50-instruction test run by ~6 of 32 lanes when tested at once) are held back until 4 lanes stand on one;
   // sphere leaves are tested at once (holding them back lost 3-8 % on the cover scene)
   p.leaf_min = p.sc.n_tri > 0 ? 4u : 1u;
+  if (const char* e = std::getenv("RTW_LEAF_MIN")) p.leaf_min = static_cast<uint32_t>(std::max(1, std::atoi(e)));   // tuning knob
   p.so = smem_layout(p);
   const size_t smem = mode == 0 ? 16 + static_cast<size_t>(p.sc.n_static + p.sc.n_moving + 1) * 32 : 0;
   if (mode == 0) {
@@ -1338,8 +1432,16 @@ cudaError_t launch_render(const RenderParams& p_in, int mode, int rays_per_lane,
     if (rays_per_lane == 4) return stats ? launch_sweep_t<4, true>(p, sm_count, smem, stream, nullptr) : launch_sweep_t<4, false>(p, sm_count, smem, stream, nullptr);
     return stats ? launch_sweep_t<2, true>(p, sm_count, smem, stream, nullptr) : launch_sweep_t<2, false>(p, sm_count, smem, stream, nullptr);
   }
-  const BvhPlan plan = plan_bvh(p.so.records, p.sc.n_tri, p.sc.leaf_direct != 0, force_perlane);   // rtw_internal.h: who gets which kernel
+  const bool cw = p.sc.n_cw_nodes > 0;
+  const BvhPlan plan = plan_bvh(p.so.records, p.sc.n_tri, p.sc.leaf_direct != 0, force_perlane, cw);   // rtw_internal.h: who gets which kernel
   if (variant) *variant = plan.variant;
+  if (plan.variant == RTW_BVH_CWIDE) {
+    // scenes with triangles: compressed 8-wide BVH walked by the per-lane state machine; tables in shared memory when they fit
+    // (steps per traversal phase / lanes that must need service: tuned on the 991k-triangle mesh and on suzanne)
+    if (plan.tables_in_smem)
+      return stats ? launch_bvh_t<true, true, 4, 20, 3, true>(p, sm_count, plan.smem_bytes, stream) : launch_bvh_t<true, false, 4, 20, 3, true>(p, sm_count, plan.smem_bytes, stream);
+    return stats ? launch_bvh_t<false, true, 4, 20, 3, true>(p, sm_count, 0, stream) : launch_bvh_t<false, false, 4, 20, 3, true>(p, sm_count, 0, stream);
+  }
   if (plan.variant == RTW_BVH_WAVEFRONT) {
     // 96 records per warp, 16 traversal steps between exchanges, shading batches of 32 (tuning record in DESIGN.md)
 #define RTW_WF_LAUNCH(SM, NW, MINB)                                                                                          \
@@ -1357,8 +1459,7 @@ cudaError_t launch_render(const RenderParams& p_in, int mode, int rays_per_lane,
 #undef RTW_WF_LAUNCH
   }
   // <steps per traversal phase, lanes that must need service before the service phase runs, CTAs per SM>: tables in shared memory
-  // (sphere scenes) 8 / 24; tables in L1/L2 (meshes) 4 / 20, measured on suzanne and the 991k-triangle mesh against (8,24):
-  // +2.8 % / +3.5 % (the whole (steps, threshold) landscape is within +-4 %: DESIGN.md)
+  // (sphere scenes) 8 / 24; tables in L1/L2 4 / 20 (the whole (steps, threshold) landscape is within +-4 %: DESIGN.md)
   if (plan.tables_in_smem)
     return stats ? launch_bvh_t<true, true, 8, 24, 4>(p, sm_count, plan.smem_bytes, stream) : launch_bvh_t<true, false, 8, 24, 4>(p, sm_count, plan.smem_bytes, stream);
   return stats ? launch_bvh_t<false, true, 4, 20, 4>(p, sm_count, 0, stream) : launch_bvh_t<false, false, 4, 20, 4>(p, sm_count, 0, stream);
