@@ -3,6 +3,7 @@
 // survey measured at 63-108 node visits per ray; only the closest-hit semantics are kept.
 #pragma once
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cmath>
 #include <future>
@@ -45,9 +46,19 @@ class BvhBuilder {
  public:
   struct Item { Box3 box; float c[3]; uint32_t ref; };  // one primitive: bounds, centroid, encoded reference
   int kMaxLeaf = 1;  // primitives per leaf (<= 31); 1 = primitive reference stored in the child code
+  size_t single_axis_below = 0;  // ranges with fewer primitives than this bin only their widest centroid axis (0: always all three)
   static constexpr int kBins = 32;   // 16 -> 32: cover scene +2 %, 991k-triangle mesh +1 % (node visits), build time unchanged
   static constexpr int kSahDepthLimit = 32;  // see direct_node
   static constexpr size_t kTaskRange = 16384; // subtrees over more primitives than this are built by their own task
+  static constexpr size_t kParallelRange = 1u << 17;  // ranges this big split their own passes over host threads
+  template <typename F>
+  static void for_chunks(size_t begin, size_t end, int nt, F&& fn) {  // fn(chunk, b, e) on nt threads
+    const size_t n = end - begin;
+    std::vector<std::future<void>> tasks;
+    for (int t = 1; t < nt; ++t) tasks.push_back(std::async(std::launch::async, [&fn, t, begin, n, nt] { fn(t, begin + n * t / nt, begin + n * (t + 1) / nt); }));
+    fn(0, begin, begin + n / nt);
+    for (auto& t : tasks) t.get();
+  }
   // references are (kind << 30) | index with index < 2^28; bit 29 marks a direct leaf so that its code ~ref is never -1
   static constexpr uint32_t kDirectMark = 1u << 29;
 
@@ -202,22 +213,65 @@ class BvhBuilder {
       }
       mid = begin + best_k;
     } else {
-      // binned SAH, all three axes in one pass over the range
+      // binned SAH, all three axes in one pass over the range.  The few ranges at the top of a big tree (more than kParallelRange
+      // primitives) are the serial critical path of the build, so their passes (centroid bounds, binning, partition) are split over
+      // host threads; everything below runs as independent subtree tasks.
+      // 32 bins per axis for big ranges, 16 below 256 primitives, 8 below 64: the per-node cost of resetting and sweeping the bins
+      // dominated the build of a million-triangle mesh (a quarter of a million ranges of 9..64 primitives)
+      const int nb = n >= 256 ? kBins : (n >= 64 ? 16 : 8);
+      const int nt = n >= kParallelRange ? static_cast<int>(std::min<size_t>(std::max<size_t>(1, std::thread::hardware_concurrency()), 16)) : 1;
       float clo[3] = {1e30f, 1e30f, 1e30f}, chi[3] = {-1e30f, -1e30f, -1e30f};
-      for (size_t i = begin; i < end; ++i)
-        for (int k = 0; k < 3; ++k) { clo[k] = std::min(clo[k], it[i].c[k]); chi[k] = std::max(chi[k], it[i].c[k]); }
+      if (nt > 1) {
+        std::vector<std::array<float, 6>> part(static_cast<size_t>(nt));
+        for_chunks(begin, end, nt, [&](int t, size_t b, size_t e) {
+          std::array<float, 6> a = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+          for (size_t i = b; i < e; ++i)
+            for (int k = 0; k < 3; ++k) { a[k] = std::min(a[k], it[i].c[k]); a[3 + k] = std::max(a[3 + k], it[i].c[k]); }
+          part[static_cast<size_t>(t)] = a;
+        });
+        for (const auto& a : part)
+          for (int k = 0; k < 3; ++k) { clo[k] = std::min(clo[k], a[k]); chi[k] = std::max(chi[k], a[3 + k]); }
+      } else {
+        for (size_t i = begin; i < end; ++i)
+          for (int k = 0; k < 3; ++k) { clo[k] = std::min(clo[k], it[i].c[k]); chi[k] = std::max(chi[k], it[i].c[k]); }
+      }
       Box3 bb[3][kBins]; uint32_t cnt[3][kBins];
       float scale[3];
       for (int ax = 0; ax < 3; ++ax) {
         const float ext = chi[ax] - clo[ax];
-        scale[ax] = ext > 0.0f ? kBins / ext : 0.0f;
-        for (int b = 0; b < kBins; ++b) { bb[ax][b].reset(); cnt[ax][b] = 0; }
+        scale[ax] = ext > 0.0f ? nb / ext : 0.0f;
+        for (int b = 0; b < nb; ++b) { bb[ax][b].reset(); cnt[ax][b] = 0; }
       }
-      for (size_t i = begin; i < end; ++i) {
-        for (int ax = 0; ax < 3; ++ax) {
-          int b = static_cast<int>((it[i].c[ax] - clo[ax]) * scale[ax]);
-          b = std::min(std::max(b, 0), kBins - 1);
-          bb[ax][b].grow(it[i].box); ++cnt[ax][b];
+      if (n < single_axis_below) {   // small ranges: only the widest centroid axis is binned (a third of the work; see DESIGN.md for what it costs)
+        int wide = 0;
+        if (chi[1] - clo[1] > chi[wide] - clo[wide]) wide = 1;
+        if (chi[2] - clo[2] > chi[wide] - clo[wide]) wide = 2;
+        for (int ax = 0; ax < 3; ++ax) if (ax != wide) scale[ax] = 0.0f;
+      }
+      if (nt > 1) {
+        struct Bins { Box3 bb[3][kBins]; uint32_t cnt[3][kBins]; };
+        std::vector<Bins> part(static_cast<size_t>(nt));
+        for_chunks(begin, end, nt, [&](int t, size_t b0, size_t e0) {
+          Bins& B = part[static_cast<size_t>(t)];
+          for (int ax = 0; ax < 3; ++ax) for (int b = 0; b < nb; ++b) { B.bb[ax][b].reset(); B.cnt[ax][b] = 0; }
+          for (size_t i = b0; i < e0; ++i)
+            for (int ax = 0; ax < 3; ++ax) {
+              if (!(scale[ax] > 0.0f)) continue;
+              int b = static_cast<int>((it[i].c[ax] - clo[ax]) * scale[ax]);
+              b = std::min(std::max(b, 0), nb - 1);
+              B.bb[ax][b].grow(it[i].box); ++B.cnt[ax][b];
+            }
+        });
+        for (const Bins& B : part)
+          for (int ax = 0; ax < 3; ++ax) for (int b = 0; b < nb; ++b) { bb[ax][b].grow(B.bb[ax][b]); cnt[ax][b] += B.cnt[ax][b]; }
+      } else {
+        for (size_t i = begin; i < end; ++i) {
+          for (int ax = 0; ax < 3; ++ax) {
+            if (!(scale[ax] > 0.0f)) continue;
+            int b = static_cast<int>((it[i].c[ax] - clo[ax]) * scale[ax]);
+            b = std::min(std::max(b, 0), nb - 1);
+            bb[ax][b].grow(it[i].box); ++cnt[ax][b];
+          }
         }
       }
       int best_axis = -1, best_split = -1; float best_cost = std::numeric_limits<float>::infinity();
@@ -225,9 +279,9 @@ class BvhBuilder {
         if (!(scale[ax] > 0.0f)) continue;
         Box3 rbox[kBins]; uint32_t rcnt[kBins];
         Box3 acc; acc.reset(); uint32_t c = 0;
-        for (int b = kBins - 1; b > 0; --b) { acc.grow(bb[ax][b]); c += cnt[ax][b]; rbox[b] = acc; rcnt[b] = c; }
+        for (int b = nb - 1; b > 0; --b) { acc.grow(bb[ax][b]); c += cnt[ax][b]; rbox[b] = acc; rcnt[b] = c; }
         acc.reset(); c = 0;
-        for (int b = 0; b < kBins - 1; ++b) {
+        for (int b = 0; b < nb - 1; ++b) {
           acc.grow(bb[ax][b]); c += cnt[ax][b];
           if (c == 0 || rcnt[b + 1] == 0) continue;
           const float cost = area_of(acc) * static_cast<float>(c) + area_of(rbox[b + 1]) * static_cast<float>(rcnt[b + 1]);
@@ -237,12 +291,34 @@ class BvhBuilder {
       if (best_axis >= 0) {
         const int ax = best_axis, sp = best_split;
         const float lo = clo[ax], sc = scale[ax];
-        Item* m = std::partition(it + begin, it + end, [=](const Item& a) {
+        auto goes_left = [=](const Item& a) {
           int b = static_cast<int>((a.c[ax] - lo) * sc);
-          b = std::min(std::max(b, 0), kBins - 1);
+          b = std::min(std::max(b, 0), nb - 1);
           return b <= sp;
-        });
-        mid = static_cast<size_t>(m - it);
+        };
+        if (nt > 1) {
+          // parallel partition: count per chunk, then every chunk scatters its items to their final places in a scratch copy
+          std::vector<size_t> nleft(static_cast<size_t>(nt), 0), nall(static_cast<size_t>(nt), 0);
+          for_chunks(begin, end, nt, [&](int t, size_t b0, size_t e0) {
+            size_t c = 0;
+            for (size_t i = b0; i < e0; ++i) c += goes_left(it[i]) ? 1 : 0;
+            nleft[static_cast<size_t>(t)] = c; nall[static_cast<size_t>(t)] = e0 - b0;
+          });
+          size_t total_left = 0;
+          for (size_t c : nleft) total_left += c;
+          std::vector<size_t> loff(static_cast<size_t>(nt)), roff(static_cast<size_t>(nt));
+          size_t l = 0, r = total_left;
+          for (int t = 0; t < nt; ++t) { loff[static_cast<size_t>(t)] = l; roff[static_cast<size_t>(t)] = r; l += nleft[static_cast<size_t>(t)]; r += nall[static_cast<size_t>(t)] - nleft[static_cast<size_t>(t)]; }
+          std::vector<Item> scratch(n);
+          for_chunks(begin, end, nt, [&](int t, size_t b0, size_t e0) {
+            size_t lo_at = loff[static_cast<size_t>(t)], hi_at = roff[static_cast<size_t>(t)];
+            for (size_t i = b0; i < e0; ++i) { if (goes_left(it[i])) scratch[lo_at++] = it[i]; else scratch[hi_at++] = it[i]; }
+          });
+          for_chunks(begin, end, nt, [&](int, size_t b0, size_t e0) { std::copy(scratch.begin() + (b0 - begin), scratch.begin() + (e0 - begin), it + b0); });
+          mid = begin + total_left;
+        } else {
+          mid = static_cast<size_t>(std::partition(it + begin, it + end, goes_left) - it);
+        }
       }
       if (best_axis < 0 || mid == begin || mid == end) {  // coincident centroids: split the list in half
         mid = begin + n / 2;

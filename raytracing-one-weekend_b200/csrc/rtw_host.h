@@ -59,6 +59,7 @@ struct HostFlat {
   double bvh_ms = 0.0;
 };
 int flatten_host(const rtw_scene_desc* desc, HostFlat* hf);          // 0 or an error code with rtw_last_error() set
+bool mesh_bvh_is_cw8();                                               // RTW_MESH_BVH=cw8: compressed 8-wide BVH for scenes with triangles
 uint64_t scene_key(const rtw_scene_desc* desc);                       // 64-bit hash of prims, mats and camera (never 0)
 
 }  // namespace rtw

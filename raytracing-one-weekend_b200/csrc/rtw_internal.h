@@ -39,6 +39,7 @@ struct RenderParams {
   // the packed local buffer (accum); Philox and the camera are keyed on the GLOBAL pixel.  tile_count <= 1: whole image.
   uint32_t tile_rows, tile_count, tile_index;
   uint32_t leaf_min;   // per-lane BVH kernel: lanes that must stand on a leaf before leaves are tested (set by launch_render)
+  uint32_t cw_steps, cw_service_min;   // compressed-wide-BVH kernel: steps per traversal phase, lanes that must need service before a service phase
 };
 
 struct PrimaryParams {

@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
   for (;;) {
     const uint32_t trav_mask = __ballot_sync(0xffffffffu, state == TRAV);
     const int n_service = 32 - __popc(trav_mask);
-    if (n_service >= SERVICE_MIN || trav_mask == 0u) {
+    if (n_service >= (CW ? static_cast<int>(p.cw_service_min) : SERVICE_MIN) || trav_mask == 0u) {
       // ---- shade lanes whose traversal finished ------------------------------------------------------------
       if (state == DONE) {
         trace_big_spheres(sc, o, d, tm, best_t, best_i);
@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
       // primitives test ONE of them -- once p.leaf_min lanes hold some or no lane has a node left to visit (the triangle test runs
       // at a handful of lanes otherwise), then (c) lanes with neither pop a node group or finish
 #pragma unroll 1
-      for (int step = 0; step < STEPS; ++step) {
+      for (uint32_t step = 0; step < p.cw_steps; ++step) {
         if (state == TRAV && tgroup.y == 0u && (ngroup.y & 0xff000000u)) {
           const uint32_t child = cw_pop_child(ngroup, oct_inv4, cw_stack, sp);
           if (STATS) ++n_nodes;
@@ -1424,6 +1424,10 @@ cudaError_t launch_render(const RenderParams& p_in, int mode, int rays_per_lane,
   // sphere leaves are tested at once (holding them back lost 3-8 % on the cover scene)
   p.leaf_min = p.sc.n_tri > 0 ? 4u : 1u;
   if (const char* e = std::getenv("RTW_LEAF_MIN")) p.leaf_min = static_cast<uint32_t>(std::max(1, std::atoi(e)));   // tuning knob
+  p.cw_steps = 4u; p.cw_service_min = 20u;
+  if (const char* e = std::getenv("RTW_CW_STEPS")) p.cw_steps = static_cast<uint32_t>(std::max(1, std::atoi(e)));
+  if (const char* e = std::getenv("RTW_CW_SERVICE")) p.cw_service_min = static_cast<uint32_t>(std::min(32, std::max(1, std::atoi(e))));
+  const int cw_minb = std::getenv("RTW_CW_MINB") ? std::atoi(std::getenv("RTW_CW_MINB")) : 3;
   p.so = smem_layout(p);
   const size_t smem = mode == 0 ? 16 + static_cast<size_t>(p.sc.n_static + p.sc.n_moving + 1) * 32 : 0;
   if (mode == 0) {
@@ -1440,6 +1444,8 @@ cudaError_t launch_render(const RenderParams& p_in, int mode, int rays_per_lane,
     // (steps per traversal phase / lanes that must need service: tuned on the 991k-triangle mesh and on suzanne)
     if (plan.tables_in_smem)
       return stats ? launch_bvh_t<true, true, 4, 20, 3, true>(p, sm_count, plan.smem_bytes, stream) : launch_bvh_t<true, false, 4, 20, 3, true>(p, sm_count, plan.smem_bytes, stream);
+    if (cw_minb == 4 && !stats) return launch_bvh_t<false, false, 4, 20, 4, true>(p, sm_count, 0, stream);
+    if (cw_minb == 2 && !stats) return launch_bvh_t<false, false, 4, 20, 2, true>(p, sm_count, 0, stream);
     return stats ? launch_bvh_t<false, true, 4, 20, 3, true>(p, sm_count, 0, stream) : launch_bvh_t<false, false, 4, 20, 3, true>(p, sm_count, 0, stream);
   }
   if (plan.variant == RTW_BVH_WAVEFRONT) {

@@ -11,7 +11,7 @@ namespace rtweekend {
 // Cover scene.  The layout IS the host random stream, so the draws happen in the order the reference's binary makes
 // them: choose_mat, then the two position draws, of which g++ evaluates the z one first (the reference writes them as
 // arguments of one constructor call, main.cpp:46, whose evaluation order the compiler picks right to left); then the
-// material's draws.  tests/test_host_scene.py pins every sphere and material against the reference build.
+// material's draws.  tests/test_host.py::test_cover_scene_matches_oracle_scene pins every sphere and material against the reference build.
 Scene lots_of_balls(const Config& cfg) {
   Scene world{Camera{point(13, 2, 3), point(0, 0, 0), vec3(0, 1, 0), 20.0, cfg.aspect_ratio, 0.1, 10.0, 0, 1}};
   auto& shop = world.boutique();

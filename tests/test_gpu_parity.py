@@ -255,7 +255,11 @@ def test_render_depth_rule(gpu, port, depth):
         assert (acc[..., :3].sum(axis=2) == 0).mean() > 0.3  # everything that hits is black
 
 
-def test_render_same_stream_suzanne_and_mixed_scene(gpu, port, oracle_mod):
+@pytest.mark.parametrize("mesh_bvh", ["binary", "cw8"])
+def test_render_same_stream_suzanne_and_mixed_scene(gpu, port, oracle_mod, monkeypatch, mesh_bvh):
+    """Triangles alone and triangles mixed with spheres of every kind, through both tree formats a mesh can get: the binary tree
+    (default) and the compressed 8-wide tree (RTW_MESH_BVH=cw8, where the small spheres live as tagged records among the triangles)."""
+    monkeypatch.setenv("RTW_MESH_BVH", mesh_bvh)
     scene, osc = gpu.obj_scene(SUZANNE), port.scene_obj(SUZANNE)
     same_stream_check(gpu, port, scene, osc, 96, 64, 8, 20, seed=4, kernel=gpu.KERNEL_AUTO, frac_tol=0.02)
     # triangles + spheres of every material + the r=1000 ground, through the same Scene API the reference exposes
@@ -543,10 +547,13 @@ def test_row_tile_split_is_bit_identical(gpu, kernel_name, tile_rows, count):
     ds.close()
 
 
-def test_high_poly_stand_in_mesh(gpu, port, oracle_mod, tmp_path):
+@pytest.mark.parametrize("mesh_bvh", ["binary", "cw8"])
+def test_high_poly_stand_in_mesh(gpu, port, oracle_mod, tmp_path, monkeypatch, mesh_bvh):
     """Config-4 path (device BVH over a large mesh in global memory) on a 62k-triangle stand-in: 968 * 4^3 triangles made
-    by the product's generator, on the r=1000 ground; ids exact in fp64, knife-edge tolerance in fp32, same-stream image."""
+    by the product's generator, on the r=1000 ground; ids exact in fp64, knife-edge tolerance in fp32, same-stream image.
+    Both tree formats: binary 64-byte nodes (default) and the compressed 8-wide tree (RTW_MESH_BVH=cw8)."""
     import ctypes as C
+    monkeypatch.setenv("RTW_MESH_BVH", mesh_bvh)
     obj = tmp_path / "standin3.obj"
     n = C.c_longlong(0)
     assert gpu.host().rtwh_make_mesh(SUZANNE.encode(), str(obj).encode(), 3, 20221018, 0.08, C.byref(n)) == 0 and n.value == 968 * 64
@@ -557,10 +564,11 @@ def test_high_poly_stand_in_mesh(gpu, port, oracle_mod, tmp_path):
     want = osc.primary_hits(W, H, 0.0)
     check_primary(gpu.primary_hits(scene, W, H, 0.0, 64), want, fp64=True, unit_normals=False)
     n = check_primary(gpu.primary_hits(scene, W, H, 0.0, 32), want, fp64=False, unit_normals=False, max_knife_edge=KNIFE_EDGE_BOUND["standin_62k_128x72"])
-    record_knife_edge("standin_62k_128x72/bvh", n, W * H)
+    record_knife_edge(f"standin_62k_128x72/{mesh_bvh}", n, W * H)
     acc, st = gpu.render(scene, 64, 36, 4, 20, seed=6, stats=True)
     ref, _, rays = port.render_philox(osc, 64, 36, 0, 4, 20, seed=6, nthreads=8)
-    assert st["kernel_used"] == gpu.KERNEL_BVH and st["bvh_variant"] == gpu.BVH_CWIDE and st["tri_tests"] > 0   # meshes: compressed wide BVH
+    assert st["kernel_used"] == gpu.KERNEL_BVH and st["tri_tests"] > 0
+    assert st["bvh_variant"] == (gpu.BVH_CWIDE if mesh_bvh == "cw8" else gpu.BVH_PERLANE)   # meshes: per-lane state machine, either tree
     got = acc[..., :3].astype(np.float64) / 4
     assert (np.abs(got - ref / 4).max(axis=2) > 1e-3).mean() < 0.03
     assert abs(st["rays"] - rays) / rays < 0.01

@@ -184,14 +184,15 @@ def test_sample_shard(rtw):
         rtw.sample_shard(20, 0, 8)
 
 
-def test_bvh_kernel_plan(rtw):
+def test_bvh_kernel_plan(rtw, monkeypatch):
     """Which BVH kernel a scene gets is host logic (plan_bvh, csrc/rtw_internal.h), reported by rtw_flatten_info: the wavefront
     kernel with 28 / 24 / 20 warps per SM while tables + path records fit in the 227 KB of shared memory, the same kernel with the
-    tables in L1/L2 for bigger sphere scenes; every scene with triangles gets the compressed 8-wide BVH walked by the per-lane state
-    machine, its tables (80-byte nodes + 48-byte leaf records) in shared memory while they fit in 72 KB."""
+    tables in L1/L2 for bigger sphere scenes, the per-lane kernel for meshes; with RTW_MESH_BVH=cw8 scenes with triangles get the
+    compressed 8-wide BVH walked by the per-lane state machine, its tables in shared memory while they fit in 72 KB."""
     def plan(scene):
         r = rtw.flatten_info(scene)
         return r["bvh_variant"], r["bvh_warps_per_cta"], r["bvh_tables_in_smem"], r["bvh_smem_bytes"]
+    monkeypatch.delenv("RTW_MESH_BVH", raising=False)
     for nsqrt, warps in ((1, 28), (11, 28), (12, 28), (13, 24), (15, 24), (16, 20), (17, 20)):
         v, w, in_smem, smem = plan(rtw.cover_scene(nsqrt))
         assert (v, w, in_smem) == (rtw.BVH_WAVEFRONT, warps, 1), nsqrt
@@ -199,21 +200,28 @@ def test_bvh_kernel_plan(rtw):
     assert plan(rtw.cover_scene(11))[3] == 215760   # cover scene: 46 416 bytes of tables + 28 x 6 048 bytes of records
     assert plan(rtw.cover_scene(18))[:3] == (rtw.BVH_WAVEFRONT, 8, 0)
     assert plan(rtw.cover_scene(40))[:3] == (rtw.BVH_WAVEFRONT, 8, 0)
-    v, w, in_smem, smem = plan(rtw.mesh_on_ground_scene(SUZANNE))
-    assert (v, w, in_smem) == (rtw.BVH_CWIDE, 8, 1) and 50_000 < smem < 60_000    # 968 triangles: ~130 wide nodes + 968 records = 57 KB
+    assert plan(rtw.mesh_on_ground_scene(SUZANNE))[:3] == (rtw.BVH_PERLANE, 8, 0)   # 968 triangles: 108 KB of tables, beyond K2's 72 KB
     cam = dict(lookfrom=(0, 0, 0), lookat=(0, 0, -1), vup=(0, 1, 0), vfov=60.0, aspect=1.0, aperture=0.0, focus_dist=1.0)
     prims = np.zeros(200, rtw.PRIM_DTYPE)
     prims["kind"] = rtw.RTW_TRIANGLE
     rng = np.random.default_rng(0)
     prims["a"] = rng.uniform(-1, 1, (200, 3)); prims["b"] = prims["a"] + 0.1; prims["c"] = prims["a"] + [0.1, 0, 0.05]
-    assert plan(rtw.custom_scene(prims, np.zeros(1, rtw.MAT_DTYPE), **cam))[:3] == (rtw.BVH_CWIDE, 8, 1)
+    small = rtw.custom_scene(prims, np.zeros(1, rtw.MAT_DTYPE), **cam)
+    assert plan(small)[:3] == (rtw.BVH_WAVEFRONT, 28, 1)   # small meshes fit the first tier
     big = np.zeros(4000, rtw.PRIM_DTYPE)
     big["kind"] = rtw.RTW_TRIANGLE
     big["a"] = rng.uniform(-1, 1, (4000, 3)); big["b"] = big["a"] + 0.01; big["c"] = big["a"] + [0.01, 0, 0.005]
-    assert plan(rtw.custom_scene(big, np.zeros(1, rtw.MAT_DTYPE), **cam))[:3] == (rtw.BVH_CWIDE, 8, 0)   # 192 KB of records: read through L1/L2
+    big = rtw.custom_scene(big, np.zeros(1, rtw.MAT_DTYPE), **cam)
+    monkeypatch.setenv("RTW_MESH_BVH", "cw8")
+    v, w, in_smem, smem = plan(rtw.mesh_on_ground_scene(SUZANNE))
+    assert (v, w, in_smem) == (rtw.BVH_CWIDE, 8, 1) and 50_000 < smem < 60_000    # 968 triangles: ~130 wide nodes + 968 records = 57 KB
+    assert plan(small)[:3] == (rtw.BVH_CWIDE, 8, 1)
+    assert plan(big)[:3] == (rtw.BVH_CWIDE, 8, 0)   # 192 KB of records: read through L1/L2
+    assert plan(rtw.cover_scene(11))[:3] == (rtw.BVH_WAVEFRONT, 28, 1)   # sphere-only scenes are not affected
+    assert rtw.scene_hash(small) != (monkeypatch.delenv("RTW_MESH_BVH") or rtw.scene_hash(small))   # the cache key knows the tree format
 
 
-def test_flatten_tables_and_bvh_invariants(rtw, tmp_path):
+def test_flatten_tables_and_bvh_invariants(rtw, tmp_path, monkeypatch):
     """north_star item 1 on the CPU: the primitive list flattened into sphere / big-sphere / triangle tables and a BVH in
     which every primitive appears exactly once (rtw_flatten_info runs the host half of rtw_scene_upload, no GPU)."""
     r = rtw.flatten_info(rtw.cover_scene())
@@ -221,32 +229,40 @@ def test_flatten_tables_and_bvh_invariants(rtw, tmp_path):
     assert r["n_bvh_nodes"] == 483 and r["leaf_direct"] == 1 and r["bvh_errors"] == 0 and r["bvh_max_depth"] <= 16
     r = rtw.flatten_info(rtw.cover_scene(11, 1.5, False))
     assert (r["n_static_spheres"], r["n_moving_spheres"], r["n_big_spheres"]) == (485, 0, 1)  # 486 static spheres
-    # scenes with triangles: compressed 8-wide BVH (80-byte nodes).  bvh_errors counts leaf records referenced zero or several times
-    # AND dequantised child boxes that fail to contain the exact bounds of everything below them (checked bottom-up on the host)
+    # meshes, default: binary tree, triangle records in tree order.  bvh_errors counts primitives referenced zero or several times
     r = rtw.flatten_info(rtw.obj_scene(SUZANNE))
-    assert r["n_triangles"] == 968 and 968 // 24 <= r["n_bvh_nodes"] <= 967 // 2 and r["bvh_errors"] == 0 and r["bvh_max_depth"] <= 8
+    assert r["n_triangles"] == 968 and r["n_bvh_nodes"] == 967 and r["bvh_errors"] == 0
     r = rtw.flatten_info(rtw.mesh_on_ground_scene(SUZANNE))
     assert r["n_triangles"] == 968 and r["n_big_spheres"] == 1 and r["bvh_errors"] == 0
-    # meshes of 1, 2, 3, 7 and 200 triangles, and triangles mixed with small spheres (sphere records in the leaf table)
-    cam = dict(lookfrom=(0, 0, 0), lookat=(0, 0, -1), vup=(0, 1, 0), vfov=60.0, aspect=1.0, aperture=0.0, focus_dist=1.0)
-    for n, nsph in ((1, 0), (2, 0), (3, 0), (7, 0), (200, 0), (1, 1), (50, 30), (5, 400)):
-        rng = np.random.default_rng(100 + n + nsph)
-        prims = np.zeros(n + nsph, rtw.PRIM_DTYPE)
-        prims["kind"][:n] = rtw.RTW_TRIANGLE
-        prims["a"] = rng.uniform(-3, 3, (n + nsph, 3)); prims["b"] = prims["a"] + rng.uniform(-0.3, 0.3, (n + nsph, 3)); prims["c"] = prims["a"] + rng.uniform(-0.3, 0.3, (n + nsph, 3))
-        prims["kind"][n:] = rng.integers(0, 2, nsph)   # static and moving spheres
-        prims["radius"][n:] = rng.uniform(0.05, 0.4, nsph)
+    for fmt in ("binary", "cw8"):
+        # RTW_MESH_BVH=cw8: compressed 8-wide BVH (80-byte nodes); there bvh_errors ALSO counts dequantised child boxes that fail to
+        # contain the exact bounds of everything below them (checked bottom-up on the host)
+        monkeypatch.setenv("RTW_MESH_BVH", fmt)
+        r = rtw.flatten_info(rtw.obj_scene(SUZANNE))
+        assert r["n_triangles"] == 968 and r["bvh_errors"] == 0
+        if fmt == "cw8":
+            assert 968 // 24 <= r["n_bvh_nodes"] <= 967 // 2 and r["bvh_max_depth"] <= 8 and r["bvh_variant"] == rtw.BVH_CWIDE
+        # meshes of 1, 2, 3, 7 and 200 triangles, and triangles mixed with small spheres
+        cam = dict(lookfrom=(0, 0, 0), lookat=(0, 0, -1), vup=(0, 1, 0), vfov=60.0, aspect=1.0, aperture=0.0, focus_dist=1.0)
+        for n, nsph in ((1, 0), (2, 0), (3, 0), (7, 0), (200, 0), (1, 1), (50, 30), (5, 400)):
+            rng = np.random.default_rng(100 + n + nsph)
+            prims = np.zeros(n + nsph, rtw.PRIM_DTYPE)
+            prims["kind"][:n] = rtw.RTW_TRIANGLE
+            prims["a"] = rng.uniform(-3, 3, (n + nsph, 3)); prims["b"] = prims["a"] + rng.uniform(-0.3, 0.3, (n + nsph, 3)); prims["c"] = prims["a"] + rng.uniform(-0.3, 0.3, (n + nsph, 3))
+            prims["kind"][n:] = rng.integers(0, 2, nsph)   # static and moving spheres
+            prims["radius"][n:] = rng.uniform(0.05, 0.4, nsph)
+            r = rtw.flatten_info(rtw.custom_scene(prims, np.zeros(1, rtw.MAT_DTYPE), **cam))
+            assert r["bvh_errors"] == 0 and r["n_triangles"] == n, (fmt, n, nsph, r)
+            assert 1 <= r["n_bvh_nodes"] <= max(n + nsph - 1, 1)
+        # degenerate mesh: 3000 copies of one triangle (coincident centroids) and a sliver spanning 60 orders of magnitude
+        prims = np.zeros(3000, rtw.PRIM_DTYPE); prims["kind"] = rtw.RTW_TRIANGLE; prims["b"] = [1, 0, 0]; prims["c"] = [0, 1, 0]
         r = rtw.flatten_info(rtw.custom_scene(prims, np.zeros(1, rtw.MAT_DTYPE), **cam))
-        assert r["bvh_errors"] == 0 and r["n_triangles"] == n and r["bvh_variant"] == rtw.BVH_CWIDE, (n, nsph, r)
-        assert 1 <= r["n_bvh_nodes"] <= max(n + nsph - 1, 1)
-    # degenerate mesh: 3000 copies of one triangle (coincident centroids) and a sliver spanning 60 orders of magnitude
-    prims = np.zeros(3000, rtw.PRIM_DTYPE); prims["kind"] = rtw.RTW_TRIANGLE; prims["b"] = [1, 0, 0]; prims["c"] = [0, 1, 0]
-    r = rtw.flatten_info(rtw.custom_scene(prims, np.zeros(1, rtw.MAT_DTYPE), **cam))
-    assert r["bvh_errors"] == 0 and r["bvh_max_depth"] <= 32
-    prims = np.zeros(1500, rtw.PRIM_DTYPE); prims["kind"] = rtw.RTW_TRIANGLE
-    prims["a"][:, 0] = 1e-30 * 1.08 ** np.arange(1500); prims["b"] = prims["a"] * 1.01; prims["c"] = prims["a"] + [0, 1e-33, 0]
-    r = rtw.flatten_info(rtw.custom_scene(prims, np.zeros(1, rtw.MAT_DTYPE), **cam))
-    assert r["bvh_errors"] == 0 and r["bvh_max_depth"] <= 32
+        assert r["bvh_errors"] == 0 and r["bvh_max_depth"] <= (32 if fmt == "cw8" else 64)
+        prims = np.zeros(1500, rtw.PRIM_DTYPE); prims["kind"] = rtw.RTW_TRIANGLE
+        prims["a"][:, 0] = 1e-30 * 1.08 ** np.arange(1500); prims["b"] = prims["a"] * 1.01; prims["c"] = prims["a"] + [0, 1e-33, 0]
+        r = rtw.flatten_info(rtw.custom_scene(prims, np.zeros(1, rtw.MAT_DTYPE), **cam))
+        assert r["bvh_errors"] == 0 and r["bvh_max_depth"] <= (32 if fmt == "cw8" else 64)
+    monkeypatch.delenv("RTW_MESH_BVH")
     cam = dict(lookfrom=(0, 0, 0), lookat=(0, 0, -1), vup=(0, 1, 0), vfov=60.0, aspect=1.0, aperture=0.0, focus_dist=1.0)
     mats = np.zeros(1, rtw.MAT_DTYPE)
     for n in (0, 1, 2, 3, 9, 100):
