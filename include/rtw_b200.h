@@ -48,8 +48,11 @@ enum rtw_kernel { RTW_KERNEL_AUTO = 0, RTW_KERNEL_SPHERES_SMEM = 1, RTW_KERNEL_B
 enum rtw_bvh_variant { RTW_BVH_NONE = 0, RTW_BVH_PERLANE = 1, RTW_BVH_WAVEFRONT = 2, RTW_BVH_CWIDE = 3 };
 /* STATS: count tests / node visits (slower).  SPLIT_ROWS: multi-GPU row-tile split instead of the sample split.
  * NO_SCENE_CACHE: the host-buffer entry points re-flatten, re-build and re-upload the scene even when it is the one the device
- * already holds from the previous call (what the first call of a process pays; bench.py's end-to-end leg uses it). */
-enum rtw_flags { RTW_FLAG_STATS = 1, RTW_FLAG_SPLIT_ROWS = 2, RTW_FLAG_NO_SCENE_CACHE = 4 };
+ * already holds from the previous call (what the first call of a process pays; bench.py's end-to-end leg uses it).
+ * BVH_BUILD_GPU / BVH_BUILD_HOST: where the host-buffer entry points (and rtw_scene_upload_ex) build the BVH: linear BVH on the
+ * device (a few ms for a million triangles, ~10-20 % slower to trace) or binned SAH on the host cores.  Neither: the device for
+ * scenes of >= 200 000 primitives rendered with < 2e9 paths, the host otherwise. */
+enum rtw_flags { RTW_FLAG_STATS = 1, RTW_FLAG_SPLIT_ROWS = 2, RTW_FLAG_NO_SCENE_CACHE = 4, RTW_FLAG_BVH_BUILD_GPU = 16, RTW_FLAG_BVH_BUILD_HOST = 32 };
 
 /* One primitive, in scene insertion order (index in the array == primitive id used for parity).
  * Mirrors the constructor arguments of Sphere / MovingSphere / Triangle (oo-primitives.h:28,49,76). */
@@ -106,6 +109,7 @@ typedef struct rtw_stats {
   uint64_t tri_tests, node_visits;            /* RTW_FLAG_STATS only */
   double kernel_ms;                           /* CUDA-event time of the render kernel(s) */
   double h2d_ms, d2h_ms, total_ms;            /* host-buffer entry points */
+  double bvh_build_gpu_ms;                    /* > 0: the BVH was built on the device, time of the build kernels (inside h2d_ms) */
   int32_t kernel_used;                        /* rtw_kernel actually launched (SPHERES_SMEM or BVH) */
   int32_t launches;                           /* kernels of this library launched by the call */
   int32_t bvh_variant;                        /* rtw_bvh_variant when kernel_used == RTW_KERNEL_BVH */
@@ -120,6 +124,8 @@ RTW_API int rtw_device_count(int* count);
 
 /* Flatten + upload (sphere tables, SAH BVH for meshes/mixed scenes, materials, camera) to `device`. */
 RTW_API int rtw_scene_upload(const rtw_scene_desc* desc, int32_t device, rtw_scene** out);
+/* The same with flags: RTW_FLAG_BVH_BUILD_GPU builds the BVH on the device (default: host SAH). */
+RTW_API int rtw_scene_upload_ex(const rtw_scene_desc* desc, int32_t device, int32_t flags, rtw_scene** out);
 RTW_API void rtw_scene_free(rtw_scene* scene);
 /* Replace the contents of an uploaded scene by a new description (re-flatten, re-build, one H2D copy into the same allocation when
  * it fits).  No render of `scene` may be in flight. */
@@ -214,6 +220,10 @@ typedef struct rtw_flatten_report {
   int64_t bvh_smem_bytes;
 } rtw_flatten_report;
 RTW_API int rtw_flatten_info(const rtw_scene_desc* desc, rtw_flatten_report* out);
+/* The same structural check on an UPLOADED scene with a binary tree, whichever builder made it (the arena is read back): every
+ * primitive referenced exactly once, every stored child box contains the exact bounds of everything below it.  Fills n_bvh_nodes,
+ * bvh_max_depth, bvh_errors and bvh_build_ms (time of the device build, 0 for a host-built tree). */
+RTW_API int rtw_scene_check(const rtw_scene* scene, rtw_flatten_report* out);
 
 /* FP32 FFMA micro-benchmark: sustained TFLOP/s (2 flop per FMA) and the SM clock seen, the denominator of the
  * sphere-scene roofline (MEASURED_PEAKS.json carries only HBM and bf16 figures). */

@@ -34,6 +34,8 @@ BVH_NONE, BVH_PERLANE, BVH_WAVEFRONT, BVH_CWIDE = 0, 1, 2, 3
 FLAG_STATS = 1
 FLAG_SPLIT_ROWS = 2
 FLAG_NO_SCENE_CACHE = 4
+FLAG_BVH_BUILD_GPU = 16
+FLAG_BVH_BUILD_HOST = 32
 
 
 class RtwError(RuntimeError):
@@ -86,7 +88,7 @@ class Stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("sphere_tests", C.c_uint64),
                 ("sphere_candidates", C.c_uint64), ("tri_tests", C.c_uint64), ("node_visits", C.c_uint64),
                 ("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
-                ("kernel_used", C.c_int32), ("launches", C.c_int32), ("bvh_variant", C.c_int32), ("scene_cache_hit", C.c_int32)]
+                ("bvh_build_gpu_ms", C.c_double), ("kernel_used", C.c_int32), ("launches", C.c_int32), ("bvh_variant", C.c_int32), ("scene_cache_hit", C.c_int32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -105,6 +107,8 @@ ABI = {
     "rtw_last_error": (C.c_char_p, []),
     "rtw_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "rtw_scene_upload": (C.c_int, [C.POINTER(SceneDesc), C.c_int32, C.POINTER(_VP)]),
+    "rtw_scene_upload_ex": (C.c_int, [C.POINTER(SceneDesc), C.c_int32, C.c_int32, C.POINTER(_VP)]),
+    "rtw_scene_check": (C.c_int, [_VP, C.POINTER(FlattenReport)]),
     "rtw_scene_free": (None, [_VP]),
     "rtw_scene_update": (C.c_int, [_VP, C.POINTER(SceneDesc)]),
     "rtw_kernel_launches": (C.c_ulonglong, []),
@@ -433,12 +437,19 @@ class DeviceScene:
     """rtw_scene_upload / rtw_render_device: scene resident in HBM, accumulation into a caller-owned device buffer
     (a torch int64 tensor [H, W, 4] on the same device)."""
 
-    def __init__(self, scene: Scene, device: int = 0):
+    def __init__(self, scene: Scene, device: int = 0, gpu_build: bool = False):
+        """gpu_build: linear BVH built on the device (rtw_scene_upload_ex + RTW_FLAG_BVH_BUILD_GPU) instead of the host SAH tree."""
         self.scene = scene
         self.device = device
         self._h = _VP()
         d = scene.desc()
-        _check(lib().rtw_scene_upload(C.byref(d), device, C.byref(self._h)), "rtw_scene_upload")
+        _check(lib().rtw_scene_upload_ex(C.byref(d), device, FLAG_BVH_BUILD_GPU if gpu_build else 0, C.byref(self._h)), "rtw_scene_upload_ex")
+
+    def check(self) -> dict:
+        """rtw_scene_check: structural check of the device-resident binary tree (reads the arena back)."""
+        r = FlattenReport()
+        _check(lib().rtw_scene_check(self._h, C.byref(r)), "rtw_scene_check")
+        return r.as_dict()
 
     def render_into(self, accum_fx, width, height, spp, max_child_rays=20, stream_ptr=0, want_stats=False, **kw):
         cfg = make_cfg(width, height, spp, max_child_rays, device=self.device, **kw)

@@ -132,6 +132,9 @@ int rtw::flatten_host(const rtw_scene_desc* desc, HostFlat* hf) {
   const bool direct = builder.kMaxLeaf == 1 || cw;
   const size_t node_cap = cw ? 0 : std::max<size_t>(n_items, 1), ref_cap = direct ? 0 : n_items;
   const size_t n_records = cw ? n_items : n_tri;   // cw: one record per leaf primitive (triangles and small spheres)
+  // build on the device (rtw_build.cu): binary single-primitive-leaf tree only, at least two primitives
+  const bool gpu_build = hf->gpu_build && !cw && builder.kMaxLeaf == 1 && n_items >= 2;
+  hf->gpu_build = gpu_build;
 
   // ---- arena layout ----------------------------------------------------------------------------------------------------------------
   size_t cursor = 0;
@@ -139,14 +142,20 @@ int rtw::flatten_host(const rtw_scene_desc* desc, HostFlat* hf) {
   hf->o_sA = reserve(n_small * sizeof(float4)); hf->o_sB = reserve(n_small * sizeof(float4)); hf->o_sId = reserve(n_small * sizeof(int2));
   hf->o_big = reserve(n_big * sizeof(rtw::BigSphere));
   hf->o_tri = reserve(n_records * 3 * sizeof(float4)); hf->o_triId = reserve(n_records * sizeof(int2));
-  hf->o_nodes = reserve(node_cap * sizeof(rtw::PackedNode)); hf->o_refs = reserve(ref_cap * sizeof(uint32_t));
+  hf->o_nodes = reserve(gpu_build ? 0 : node_cap * sizeof(rtw::PackedNode)); hf->o_refs = reserve(ref_cap * sizeof(uint32_t));
   hf->o_matA = reserve(static_cast<size_t>(desc->nmats) * sizeof(float4)); hf->o_matB = reserve(static_cast<size_t>(desc->nmats) * sizeof(float2));
   hf->o_ctr = reserve(static_cast<size_t>(rtw::kCtrSlots) * rtw::kCtrCount * sizeof(unsigned long long));
   // the wide nodes come last: their number is only known after the collapse (at most one per primitive; typically a sixth), so the
   // arena is sized for the bound and trimmed afterwards (untouched pages of the host allocation are never committed)
   hf->o_cw = reserve(cw ? std::max<size_t>(n_items, 1) * sizeof(rtw::CwNode) : 0);
+  hf->upload_bytes = 0;
+  if (gpu_build) {   // the device fills the node table: it sits behind everything that is uploaded
+    hf->upload_bytes = (cursor + 255) & ~size_t(255);
+    hf->o_nodes = reserve(node_cap * sizeof(rtw::PackedNode));
+  }
   hf->bytes = (cursor + 255) & ~size_t(255);
-  hf->host.reset(new unsigned char[hf->bytes]);
+  if (!gpu_build) hf->upload_bytes = hf->bytes;
+  hf->host.reset(new unsigned char[hf->upload_bytes]);
   unsigned char* base = hf->host.get();
   float4* sA = reinterpret_cast<float4*>(base + hf->o_sA);
   float4* sB = reinterpret_cast<float4*>(base + hf->o_sB);
@@ -211,11 +220,17 @@ int rtw::flatten_host(const rtw_scene_desc* desc, HostFlat* hf) {
 
   // ---- BVH ---------------------------------------------------------------------------------------------------------------------------
   const double t_bvh = now_ms();
-  rtw::PackedNode* nodes_out = reinterpret_cast<rtw::PackedNode*>(base + hf->o_nodes);
+  rtw::PackedNode* nodes_out = gpu_build ? nullptr : reinterpret_cast<rtw::PackedNode*>(base + hf->o_nodes);
   size_t n_nodes = 0, n_refs = 0;
   size_t n_cw = 0;
   int cw_depth = 0;
-  if (cw) {
+  if (gpu_build) {
+    auto keep = std::make_shared<std::vector<rtw::BvhBuilder::Item>>();
+    keep->swap(items);
+    hf->n_gpu_items = keep->size();
+    hf->gpu_items = keep;
+    n_nodes = n_items - 1;
+  } else if (cw) {
     std::vector<rtw::BinNode> bin(n_items >= 2 ? n_items - 1 : 0);
     builder.build_items_binary(items, bin.data());
     rtw::CwBuilder wide;
@@ -226,6 +241,7 @@ int rtw::flatten_host(const rtw_scene_desc* desc, HostFlat* hf) {
     cw_depth = wide.depth();
     if (n_cw) std::memcpy(base + hf->o_cw, wide.nodes().data(), n_cw * sizeof(rtw::CwNode));
     hf->bytes = (hf->o_cw + std::max<size_t>(n_cw, 1) * sizeof(rtw::CwNode) + 255) & ~size_t(255);
+    hf->upload_bytes = hf->bytes;
     // leaf-ordered records: the primitives of one leaf (and of neighbouring leaves) next to each other in memory
     const std::vector<uint32_t>& order = wide.leaf_order();
     const float nan = std::numeric_limits<float>::quiet_NaN();
@@ -348,11 +364,24 @@ int rtw::upload_flat(const HostFlat& hf, const rtw_camera& c, int64_t nprims, in
     RTW_CUDA(sc->arena.alloc(hf.bytes));
     sc->arena_ptr = sc->arena.p;
   }
-  RTW_CUDA(cudaMemcpyAsync(sc->arena_ptr, hf.host.get(), hf.bytes, cudaMemcpyHostToDevice, stream));
+  RTW_CUDA(cudaMemcpyAsync(sc->arena_ptr, hf.host.get(), hf.upload_bytes, cudaMemcpyHostToDevice, stream));
+  sc->gpu_build_ms = 0.0;
+  if (hf.gpu_build) {
+    int depth = 0;
+    const auto* items = static_cast<const std::vector<rtw::BvhBuilder::Item>*>(hf.gpu_items.get());
+    if (int rc = gpu_build_bvh(items->data(), items->size(), sc->arena_ptr + hf.o_nodes, stream, &depth, &sc->gpu_build_ms)) return rc;
+    if (depth > rtw::kBvhStack)
+      return fail("rtw_scene_upload: the device-built BVH is deeper than the kernels' traversal stack (" + std::to_string(depth) + " > " +
+                  std::to_string(rtw::kBvhStack) + " levels): use the host builder (RTW_FLAG_BVH_BUILD_HOST)");
+    sc->bvh_depth = depth;
+  } else {
+    sc->bvh_depth = hf.bvh_depth;
+  }
   RTW_CUDA(cudaStreamSynchronize(stream));  // the host arena may go away when the caller returns
   unsigned char* base = sc->arena_ptr;
   sc->counters = reinterpret_cast<unsigned long long*>(base + hf.o_ctr);
   sc->n_leaf_refs = hf.n_leaf_refs;
+  sc->arena_bytes = hf.bytes;
 
   rtw::DevScene& d = sc->dev;
   d.sphA = reinterpret_cast<const float4*>(base + hf.o_sA); d.sphB = reinterpret_cast<const float4*>(base + hf.o_sB);
@@ -412,6 +441,17 @@ int rtw::slot_prepare(DeviceSlot* s) {
   if (!s->stream) RTW_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   if (!s->rendered) RTW_CUDA(cudaEventCreateWithFlags(&s->rendered, cudaEventDisableTiming));
   return 0;
+}
+
+// Where the BVH of a host-buffer render is built.  Explicit flags win; otherwise the device builds it for big scenes rendered with
+// few paths: the linear BVH takes ~5 ms for a million triangles against ~80 ms for the SAH tree on 16 host cores, and costs ~10-20 %
+// of trace speed, so it pays while the render itself is shorter than about half a second.
+bool rtw::choose_gpu_build(const rtw_scene_desc* desc, const rtw_render_cfg* cfg) {
+  if (cfg->flags & RTW_FLAG_BVH_BUILD_HOST) return false;
+  if (cfg->flags & RTW_FLAG_BVH_BUILD_GPU) return true;
+  if (mesh_bvh_is_cw8()) return false;
+  const double paths = static_cast<double>(cfg->width) * cfg->height * (cfg->sample_end - cfg->sample_begin);
+  return desc->nprims >= 200000 && paths < 2.0e9;
 }
 
 int rtw::slot_set_scene(DeviceSlot* s, const rtw_scene_desc* desc, uint64_t key, bool use_cache, HostFlat* flat, std::mutex* flat_mutex, bool* hit) {
@@ -635,6 +675,84 @@ int rtw_scene_upload(const rtw_scene_desc* desc, int32_t device, rtw_scene** out
   return 0;
 }
 
+int rtw_scene_upload_ex(const rtw_scene_desc* desc, int32_t device, int32_t flags, rtw_scene** out) {
+  if (!out) return fail("rtw_scene_upload_ex: null output");
+  *out = nullptr;
+  HostFlat hf;
+  hf.gpu_build = (flags & RTW_FLAG_BVH_BUILD_GPU) != 0;
+  if (int rc = rtw::flatten_host(desc, &hf)) return rc;
+  rtw_scene* sc = new rtw_scene();
+  const int rc = rtw::upload_flat(hf, desc->camera, desc->nprims, device, sc, nullptr, nullptr);
+  if (rc != 0) { delete sc; return rc; }
+  *out = sc;
+  return 0;
+}
+
+// Structural check of a device-resident BINARY tree (whichever builder made it): the arena comes back to the host, every primitive
+// must be referenced exactly once and every stored child box (centre +- half-extent) must contain the exact bounds of everything
+// below it.  out: n_bvh_nodes, bvh_max_depth, bvh_errors, bvh_build_ms (device build time, 0 for a host-built tree).
+int rtw_scene_check(const rtw_scene* scene, rtw_flatten_report* out) {
+  if (!scene || !out) return fail("rtw_scene_check: null argument");
+  std::memset(out, 0, sizeof *out);
+  const rtw::DevScene& d = scene->dev;
+  if (d.n_cw_nodes > 0) return fail("rtw_scene_check: binary trees only (the compressed wide tree is checked by rtw_flatten_info)");
+  RTW_CUDA(cudaSetDevice(scene->device));
+  std::vector<unsigned char> host(scene->arena_bytes);
+  RTW_CUDA(cudaMemcpy(host.data(), scene->arena_ptr, scene->arena_bytes, cudaMemcpyDeviceToHost));
+  auto at = [&](const void* dev_ptr) { return host.data() + (static_cast<const unsigned char*>(dev_ptr) - scene->arena_ptr); };
+  const rtw::PackedNode* nodes = reinterpret_cast<const rtw::PackedNode*>(at(d.nodes));
+  const float4* sA = reinterpret_cast<const float4*>(at(d.sphA));
+  const float4* sB = reinterpret_cast<const float4*>(at(d.sphB));
+  const float4* tri = reinterpret_cast<const float4*>(at(d.tri));
+  const size_t n_small = static_cast<size_t>(d.n_static + d.n_moving);
+  std::vector<uint8_t> seen(n_small + static_cast<size_t>(d.n_tri), 0);
+  int64_t errors = 0;
+  int depth_max = 0;
+  struct Walk {
+    const rtw::PackedNode* nodes; const float4 *sA, *sB, *tri; std::vector<uint8_t>& seen; size_t n_small; int64_t& errors; int& depth_max; int n_nodes;
+    rtw::Box3 prim_box(uint32_t ref) {
+      rtw::Box3 b; b.reset();
+      const uint32_t i = ref & 0x1fffffffu;
+      const size_t slot = (ref >> 30) ? n_small + i : i;
+      if (slot >= seen.size() || seen[slot]++) { ++errors; return b; }
+      if (ref >> 30) {
+        const float4 q0 = tri[3 * i], q1 = tri[3 * i + 1], q2 = tri[3 * i + 2];
+        const float va[3] = {q0.x, q0.y, q0.z}, vb[3] = {q0.x + q1.x, q0.y + q1.y, q0.z + q1.z}, vc[3] = {q0.x + q2.x, q0.y + q2.y, q0.z + q2.z};
+        b.grow(va); b.grow(vb); b.grow(vc);
+      } else {
+        const float4 A = sA[i], B = sB[i];
+        const float r = std::fabs(B.w);
+        const float c0[3] = {A.x, A.y, A.z}, c1[3] = {A.x + B.x, A.y + B.y, A.z + B.z};
+        for (int k = 0; k < 3; ++k) { b.lo[k] = std::min(c0[k], c1[k]) - r; b.hi[k] = std::max(c0[k], c1[k]) + r; }
+      }
+      return b;
+    }
+    rtw::Box3 visit(int32_t n, int depth) {
+      rtw::Box3 all; all.reset();
+      if (n < 0 || n >= n_nodes || depth > 200) { ++errors; return all; }
+      depth_max = std::max(depth_max, depth);
+      const rtw::PackedNode& nd = nodes[n];
+      for (int side = 0; side < 2; ++side) {
+        const int32_t code = side ? nd.right : nd.left;
+        const float c[3] = {side ? nd.rc_xy[0] : nd.lc[0], side ? nd.rc_xy[1] : nd.lc[1], side ? nd.rc_z : nd.lc[2]};
+        const float e[3] = {side ? nd.re[0] : nd.le_x, side ? nd.re[1] : nd.le_yz[0], side ? nd.re[2] : nd.le_yz[1]};
+        if (side == 1 && n_nodes == 1 && c[2] >= 1.0e38f) continue;   // the never-entered filler child of a single-leaf tree
+        const rtw::Box3 below = code >= 0 ? visit(code, depth + 1) : prim_box(static_cast<uint32_t>(~code));
+        for (int k = 0; k < 3; ++k)
+          if (!(static_cast<double>(c[k]) - e[k] <= below.lo[k] && below.hi[k] <= static_cast<double>(c[k]) + e[k])) { ++errors; break; }
+        all.grow(below);
+      }
+      return all;
+    }
+  } walk{nodes, sA, sB, tri, seen, n_small, errors, depth_max, d.n_nodes};
+  if (d.n_nodes > 0) walk.visit(0, 1);
+  for (uint8_t c : seen) if (c != 1) ++errors;
+  out->n_static_spheres = d.n_static; out->n_moving_spheres = d.n_moving; out->n_big_spheres = d.n_big; out->n_triangles = d.n_tri;
+  out->n_bvh_nodes = d.n_nodes; out->bvh_max_depth = depth_max; out->leaf_direct = d.leaf_direct; out->arena_bytes = static_cast<int64_t>(scene->arena_bytes);
+  out->bvh_errors = errors; out->bvh_build_ms = scene->gpu_build_ms;
+  return 0;
+}
+
 int rtw_scene_hash(const rtw_scene_desc* desc, uint64_t* out) {
   if (!desc || !out) return fail("rtw_scene_hash: null argument");
   if (desc->nprims < 0 || desc->nmats < 0 || (desc->nprims > 0 && !desc->prims) || (desc->nmats > 0 && !desc->mats)) return fail("rtw_scene_hash: invalid scene description");
@@ -737,8 +855,10 @@ int rtw_prewarm(int32_t first_device, int32_t ngpus) {
     if (g_warm_started >> d & 1) continue;
     g_warm_started |= 1ull << d;
     g_warm_threads.emplace_back([d] {
+      const double t0 = now_ms();
       if (cudaSetDevice(d) == cudaSuccess) cudaFree(nullptr);   // creates the primary context; errors surface in the render call
       cudaGetLastError();
+      if (std::getenv("RTW_TRACE")) std::fprintf(stderr, "rtw trace: context of gpu %d up after %.1f ms\n", d, now_ms() - t0);
     });
   }
   return 0;
@@ -776,7 +896,8 @@ static int render_host(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, fl
   bool hit = false;
   const bool use_cache = (cfg->flags & RTW_FLAG_NO_SCENE_CACHE) == 0;
   if (desc->nprims < 0 || desc->nmats < 0 || (desc->nprims > 0 && !desc->prims) || (desc->nmats > 0 && !desc->mats)) return fail("rtw_scene_upload: invalid scene description");
-  const uint64_t key = rtw::scene_key(desc);
+  hf.gpu_build = rtw::choose_gpu_build(desc, cfg);
+  const uint64_t key = rtw::scene_key(desc) ^ (hf.gpu_build ? 0x6b9d0f5a1c2e3d47ull : 0ull);   // the device tables depend on the builder
   if (int rc = rtw::slot_set_scene(slot, desc, key, use_cache, &hf, nullptr, &hit)) return rc;
   const double t_up = now_ms();
   const size_t npix = static_cast<size_t>(cfg->width) * static_cast<size_t>(cfg->height);
@@ -809,6 +930,7 @@ static int render_host(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, fl
     stats->total_ms = t_end - t_start;
     stats->launches = launches;
     stats->scene_cache_hit = hit ? 1 : 0;
+    stats->bvh_build_gpu_ms = slot->scene.gpu_build_ms;
   }
   return 0;
 }

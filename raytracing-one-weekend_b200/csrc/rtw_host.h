@@ -51,12 +51,17 @@ struct EventPair {  // destroyed on every exit path
 // layout is the device layout.  Pure host code.
 struct HostFlat {
   std::unique_ptr<unsigned char[]> host;
-  size_t bytes = 0;
+  size_t bytes = 0;          // size of the device arena
+  size_t upload_bytes = 0;   // leading part of it that `host` holds and that is copied (all of it unless the device builds the BVH)
   size_t o_sA = 0, o_sB = 0, o_sId = 0, o_big = 0, o_tri = 0, o_triId = 0, o_nodes = 0, o_refs = 0, o_matA = 0, o_matB = 0, o_ctr = 0, o_cw = 0;
   int32_t n_static = 0, n_moving = 0, n_big = 0, n_tri = 0, n_nodes = 0, leaf_direct = 0, bvh_depth = 0;
   int32_t n_cw = 0, n_records = 0, cw_has_spheres = 0;   // compressed wide BVH (scenes with triangles): nodes, leaf-ordered records
   size_t n_leaf_refs = 0;
   double bvh_ms = 0.0;
+  // build on the device (rtw_build.cu): flatten_host leaves the node table empty and keeps its build records for upload_flat
+  bool gpu_build = false;
+  std::shared_ptr<void> gpu_items;   // std::vector<BvhBuilder::Item>
+  size_t n_gpu_items = 0;
 };
 int flatten_host(const rtw_scene_desc* desc, HostFlat* hf);          // 0 or an error code with rtw_last_error() set
 bool mesh_bvh_is_cw8();                                               // RTW_MESH_BVH=cw8: compressed 8-wide BVH for scenes with triangles
@@ -78,9 +83,16 @@ struct rtw_scene {
   int64_t nprims = 0;
   bool has_triangles = false;
   size_t smem_bytes = 0;
+  size_t arena_bytes = 0;
+  int bvh_depth = 0;
+  double gpu_build_ms = 0.0;   // > 0: the BVH was built on the device (rtw_build.cu), time of the build kernels
 };
 
 namespace rtw {
+
+// rtw_build.cu: linear BVH on the device.  items_host: n >= 2 BvhBuilder::Item records (rtw_bvh.h) in host memory; nodes_out: device
+// memory for n - 1 PackedNodes (root = node 0).  Blocks until the tree is built; *depth_out <- deepest root-to-leaf path.
+int gpu_build_bvh(const void* items_host, size_t n, void* nodes_out, cudaStream_t stream, int* depth_out, double* build_ms);
 
 int upload_flat(const HostFlat& hf, const rtw_camera& cam, int64_t nprims, int device, rtw_scene* sc, DevBuf<unsigned char>* borrowed,
                 cudaStream_t stream);
@@ -104,6 +116,7 @@ int slot_prepare(DeviceSlot* s);        // cudaSetDevice + stream/event creation
 // Makes s->scene hold `desc`: a hit costs nothing; a miss uploads `*flat` (flattening `desc` into it first when it is empty).
 int slot_set_scene(DeviceSlot* s, const rtw_scene_desc* desc, uint64_t key, bool use_cache, HostFlat* flat, std::mutex* flat_mutex, bool* hit);
 
+bool choose_gpu_build(const rtw_scene_desc* desc, const rtw_render_cfg* cfg);   // host or device BVH build for a host-buffer render
 void prewarm_join();                    // waits for the context-creation threads of rtw_prewarm
 int fail(const std::string& msg);
 int fail_cuda(const char* what, cudaError_t e);

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -75,7 +76,8 @@ int multi_host(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, int32_t ng
   const size_t npix = static_cast<size_t>(cfg->width) * static_cast<size_t>(cfg->height);
   const int local_rows = rows ? rtw_row_tile_local_rows(cfg->height, tile_rows, ngpus) : cfg->height;
   const size_t local_pix = static_cast<size_t>(local_rows) * static_cast<size_t>(cfg->width);
-  const uint64_t key = rtw::scene_key(desc);
+  const bool gpu_build = rtw::choose_gpu_build(desc, cfg);
+  const uint64_t key = rtw::scene_key(desc) ^ (gpu_build ? 0x6b9d0f5a1c2e3d47ull : 0ull);
   const bool use_cache = (cfg->flags & RTW_FLAG_NO_SCENE_CACHE) == 0;
 
   std::vector<rtw::DeviceSlot*> slots(ngpus, nullptr);
@@ -88,18 +90,24 @@ int multi_host(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, int32_t ng
   for (int g = 0; g < ngpus; ++g) locks.emplace_back(slots[g]->m);
 
   rtw::HostFlat flat;       // flattened at most once, by whichever GPU thread misses its cache first
+  flat.gpu_build = gpu_build;
   std::mutex flat_mutex;
   std::vector<int> rcs(ngpus, 0);
   std::vector<std::string> errs(ngpus);
   std::vector<rtw_stats> sts(ngpus);
   std::vector<char> hits(ngpus, 0);
   std::vector<double> t_scene(ngpus, 0.0);
+  const bool trace = std::getenv("RTW_TRACE") != nullptr;   // per-GPU timeline of the call on stderr
+  struct Mark { double ctx = 0, peer = 0, scene = 0, alloc = 0, done = 0; };
+  std::vector<Mark> marks(ngpus);
+  const double t_joined = now_ms();
 
   // one host thread per GPU: context, peer access, scene (cached), zero, render its shard (waits for its kernel)
   auto work = [&](int g) {
     rtw::DeviceSlot* s = slots[g];
     auto bail = [&](int rc) { rcs[g] = rc ? rc : 1; errs[g] = rtw_last_error(); };
     if (int rc = rtw::slot_prepare(s)) return bail(rc);
+    marks[g].ctx = now_ms();
     if (!rows) {
       for (int q = 0; q < ngpus; ++q) {
         if (q == g || (s->peer_enabled_mask >> q & 1)) continue;
@@ -112,12 +120,14 @@ int multi_host(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, int32_t ng
         s->peer_enabled_mask |= 1 << q;
       }
     }
+    marks[g].peer = now_ms();
     bool hit = false;
     if (int rc = rtw::slot_set_scene(s, desc, key, use_cache, &flat, &flat_mutex, &hit)) return bail(rc);
     hits[g] = hit ? 1 : 0;
-    t_scene[g] = now_ms();
+    t_scene[g] = marks[g].scene = now_ms();
     if (cudaSuccess != s->fx.reserve(std::max(npix, local_pix) * 4)) { fail("rtw_render_multi_gpu: device allocation failed"); return bail(2); }
     if (cudaSuccess != cudaMemsetAsync(s->fx.p, 0, (rows ? local_pix : npix) * 4 * sizeof(long long), s->stream)) { fail("cudaMemsetAsync failed"); return bail(2); }
+    marks[g].alloc = now_ms();
     rtw_render_cfg c = *cfg;
     c.device = g;
     if (rows) {
@@ -132,6 +142,7 @@ int multi_host(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, int32_t ng
     if (c.sample_end > c.sample_begin) {
       if (int rc = rtw_render_device(&s->scene, &c, reinterpret_cast<int64_t*>(s->fx.p), s->stream, &sts[g])) return bail(rc);
     } else if (cudaStreamSynchronize(s->stream) != cudaSuccess) { fail("stream sync failed"); return bail(2); }
+    marks[g].done = now_ms();
   };
   {
     std::vector<std::thread> th;
@@ -191,6 +202,13 @@ int multi_host(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, int32_t ng
     RTW_CUDA(cudaStreamSynchronize(slots[g]->stream));
   }
   const double t_end = now_ms();
+  if (trace) {
+    std::fprintf(stderr, "rtw trace: prewarm join %.1f ms; per GPU (ms since call): context+stream, peer access, scene, buffers, kernel done\n", t_joined - t_start);
+    for (int g = 0; g < ngpus; ++g)
+      std::fprintf(stderr, "rtw trace: gpu %d  %.1f  %.1f  %.1f  %.1f  %.1f\n", g, marks[g].ctx - t_start, marks[g].peer - t_start, marks[g].scene - t_start,
+                   marks[g].alloc - t_start, marks[g].done - t_start);
+    std::fprintf(stderr, "rtw trace: rendered %.1f, combined + downloaded %.1f\n", t_rendered - t_start, t_end - t_start);
+  }
   if (stats) {
     std::memset(stats, 0, sizeof *stats);
     double t_up = t_start;
@@ -210,6 +228,7 @@ int multi_host(const rtw_scene_desc* desc, const rtw_render_cfg* cfg, int32_t ng
     stats->d2h_ms = t_end - t_rendered;      // combine + convert + download
     stats->total_ms = t_end - t_start;
     stats->scene_cache_hit = all_hit;
+    stats->bvh_build_gpu_ms = slots[0]->scene.gpu_build_ms;
   }
   return 0;
 }

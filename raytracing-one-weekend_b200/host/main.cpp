@@ -2,7 +2,7 @@
 //   -t,--threads  -w,--image-width  -s,--samples-per-pixel  -c,--max-child-rays  -a,--aspect-ratio  -n,--balls_sqrt
 //   -m,--moving-spheres  -q,--quick  --dry-run  -l,--load
 // plus device options: --gpus N, --split spp|rows, --tile-rows R, --seed S, --kernel auto|spheres|bvh, --stats,
-// --format p3|p6, --checkpoint FILE [--checkpoint-every N] (progressive / resumable), --scene cover|model|mesh-on-ground,
+// --bvh-build auto|host|gpu, --format p3|p6, --checkpoint FILE [--checkpoint-every N] (progressive / resumable), --scene cover|model|mesh-on-ground,
 // and a mesh utility: --make-mesh OUT.obj --rounds K (high-poly stand-in generated from the -l model).
 #include <cstdlib>
 #include <cstring>
@@ -87,6 +87,12 @@ int main(int argc, char* argv[]) {
     else if (v == "rows") dev.split_rows = true;
     else throw std::invalid_argument("--split must be spp or rows");
   }};
+  table["--bvh-build"] = {true, [&dev](const std::string& v) {
+    if (v == "auto") dev.bvh_build = 0;
+    else if (v == "host") dev.bvh_build = 1;
+    else if (v == "gpu") dev.bvh_build = 2;
+    else throw std::invalid_argument("--bvh-build must be auto, host or gpu");
+  }};
   table["--static-spheres"] = {false, [&cfg](const std::string&) { cfg.moving_spheres = false; }};
   table["--scene"] = {true, [&scene_name](const std::string& v) { scene_name = v; }};
   table["--make-mesh"] = {true, [&make_mesh](const std::string& v) { make_mesh = v; }};
@@ -127,7 +133,16 @@ int main(int argc, char* argv[]) {
   }
 
   if (dry_run) { std::cout << cfg; return 0; }
-  // the CUDA contexts come up on background threads while the scene is built (a cold process pays 0.3-1 s per GPU for them)
+  // The first CUDA call of a process initialises EVERY visible GPU (about 0.7 s each on a box without the persistence daemon: 5.5 s on
+  // an 8-GPU node before the first kernel): make only the GPUs this render uses visible, unless the user already chose.
+  if (make_mesh.empty() && !std::getenv("CUDA_VISIBLE_DEVICES") && dev.ngpus >= 1) {
+    const int first = dev.ngpus > 1 ? 0 : dev.device;
+    std::string list;
+    for (int g = 0; g < dev.ngpus; ++g) list += (g ? "," : "") + std::to_string(first + g);
+    setenv("CUDA_VISIBLE_DEVICES", list.c_str(), 1);
+    dev.device = 0;   // ordinals now count the visible devices
+  }
+  // the CUDA contexts come up on background threads while the scene is built
   if (make_mesh.empty()) rtw_prewarm(dev.ngpus > 1 ? 0 : dev.device, dev.ngpus);
 
   if (!make_mesh.empty()) {

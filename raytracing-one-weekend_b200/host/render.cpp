@@ -27,6 +27,7 @@ DeviceOptions& device_options() {
     if (const char* e = std::getenv("RTW_STATS")) o.stats = std::atoi(e) != 0;
     if (const char* e = std::getenv("RTW_SPLIT")) o.split_rows = std::string(e) == "rows";
     if (const char* e = std::getenv("RTW_TILE_ROWS")) o.tile_rows = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("RTW_BVH_BUILD")) o.bvh_build = std::string(e) == "host" ? 1 : (std::string(e) == "gpu" ? 2 : 0);
     return o;
   }();
   return opts;
@@ -88,7 +89,8 @@ Prepared prepare(const Config& cfg, const DeviceOptions& opt) {
   p.rc.kernel = opt.kernel;
   p.rc.seed = opt.seed;
   p.rc.device = opt.device;
-  p.rc.flags = (opt.stats ? RTW_FLAG_STATS : 0) | (opt.split_rows && opt.ngpus > 1 ? RTW_FLAG_SPLIT_ROWS : 0);
+  p.rc.flags = (opt.stats ? RTW_FLAG_STATS : 0) | (opt.split_rows && opt.ngpus > 1 ? RTW_FLAG_SPLIT_ROWS : 0) |
+               (opt.bvh_build == 1 ? RTW_FLAG_BVH_BUILD_HOST : 0) | (opt.bvh_build == 2 ? RTW_FLAG_BVH_BUILD_GPU : 0);
   p.rc.row_tile_rows = opt.tile_rows;
   return p;
 }
@@ -278,8 +280,9 @@ void render(const Scene& world, const Config& cfg) {
   std::cerr << "kernel " << img.stats.kernel_ms << " ms: " << paths / (img.stats.kernel_ms * 1e3) << " Mpaths/s, "
             << rays / (img.stats.kernel_ms * 1e3) << " Mrays/s (" << rays / std::max(paths, 1.0) << " rays/path)\n";
   // where the wall time went: the first CUDA call of a process creates the context(s) (0.3-1 s per GPU on a cold box)
-  std::cerr << "host: render call " << render_ms << " ms (contexts + flatten + upload " << img.stats.h2d_ms << ", combine + download " << img.stats.d2h_ms
-            << "), image output " << out_ms << " ms\n";
+  std::cerr << "host: render call " << render_ms << " ms (contexts + flatten + upload " << img.stats.h2d_ms;
+  if (img.stats.bvh_build_gpu_ms > 0) std::cerr << " of which BVH build on the device " << img.stats.bvh_build_gpu_ms;
+  std::cerr << ", combine + download " << img.stats.d2h_ms << "), image output " << out_ms << " ms\n";
   std::cerr << "\nDone in " << took.count() << "ms\n";
 }
 

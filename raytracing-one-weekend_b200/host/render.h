@@ -36,6 +36,7 @@ struct DeviceOptions {
   int tile_rows = 8;        // rows per tile of the row split
   bool obj_all_shapes = false;  // -l: take the faces of every shape of the OBJ file, not only shapes[0] as the reference does
   bool binary_ppm = false;  // P6 (binary) instead of the reference's P3 text (the pixels are quantised on the device either way)
+  int bvh_build = 0;        // 0 auto, 1 host (binned SAH), 2 device (linear BVH): RTW_FLAG_BVH_BUILD_HOST / _GPU of the C ABI
   std::string checkpoint;   // progressive rendering: file holding the accumulation buffer + sample cursor (see render_progressive)
   int checkpoint_every = 0; // samples per slice between checkpoint writes (0: one slice)
 };

@@ -22,7 +22,8 @@ run $N bench_n$N --steps 3 --warmup 3
 run $N bench_n${N}_rows --steps 3 --warmup 3 --split rows --no-cpu-baseline --no-cold
 EXE=./raytracing-one-weekend_b200/rtweekend
 for g in 1 $N; do for i in 1 2; do
-  /usr/bin/time -f "wall %e s" $EXE -w 1920 -a 1.7777777777777777 -s 1024 -c 50 --gpus $g > gpurun_out/cover_${g}gpu.ppm 2> gpurun_out/cover_${g}gpu_$i.err; tail -4 gpurun_out/cover_${g}gpu_$i.err | tr '\n' ' '; echo
+  t0=$(date +%s%N); RTW_TRACE=1 $EXE -w 1920 -a 1.7777777777777777 -s 1024 -c 50 --gpus $g > gpurun_out/cover_${g}gpu.ppm 2> gpurun_out/cover_${g}gpu_$i.err; t1=$(date +%s%N)
+  echo "process wall $(( (t1 - t0) / 1000000 )) ms" >> gpurun_out/cover_${g}gpu_$i.err; grep -v "^Started\|^$" gpurun_out/cover_${g}gpu_$i.err | tr '\n' ' '; echo
 done; done
 cmp gpurun_out/cover_1gpu.ppm gpurun_out/cover_${N}gpu.ppm && echo "1-GPU and $N-GPU PPM identical"
 $EXE -w 1920 -a 1.7777777777777777 -s 1024 -c 50 --gpus $N --split rows > gpurun_out/cover_rows.ppm 2> gpurun_out/cover_rows.err; tail -2 gpurun_out/cover_rows.err | tr '\n' ' '; echo

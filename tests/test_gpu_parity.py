@@ -766,3 +766,42 @@ def test_concurrent_renders_of_one_uploaded_scene(gpu):
     for b in bufs:
         assert torch.equal(b, ref)
     ds.close()
+
+
+def test_bvh_built_on_the_device(gpu, port, oracle_mod, tmp_path):
+    """the linear BVH built by the GPU (rtw_build.cu) is a valid tree -- every primitive referenced once, every
+    stored child box contains what is below it (rtw_scene_check reads the arena back) -- and renders the same paths as the host's SAH
+    tree: any correct BVH returns the same closest hit, so the images agree except at exact fp32 ties."""
+    import ctypes as C
+    obj = tmp_path / "standin3.obj"
+    n = C.c_longlong(0)
+    assert gpu.host().rtwh_make_mesh(SUZANNE.encode(), str(obj).encode(), 3, 20221018, 0.08, C.byref(n)) == 0
+    cam = dict(lookfrom=(0, 0, 6), lookat=(0, 0, 0), vup=(0, 1, 0), vfov=40.0, aspect=1.5, aperture=0.0, focus_dist=6.0)
+    dup = np.zeros(3000, gpu.PRIM_DTYPE); dup["kind"] = gpu.RTW_TRIANGLE; dup["a"] = [-1, -1, 0]; dup["b"] = [1, -1, 0]; dup["c"] = [0, 1, 0]
+    two = np.zeros(2, gpu.PRIM_DTYPE); two["radius"] = 0.5; two["a"] = two["b"] = [[-1, 0, 0], [1, 0, 0]]
+    mats = np.zeros(1, gpu.MAT_DTYPE); mats["albedo"] = 0.6
+    scenes = {"cover": gpu.cover_scene(), "grid_6k": gpu.cover_scene(40), "suzanne_on_ground": gpu.mesh_on_ground_scene(SUZANNE, 1.5),
+              "standin_62k": gpu.mesh_on_ground_scene(str(obj), 1.5), "3000 coincident triangles": gpu.custom_scene(dup, mats, **cam),
+              "two spheres": gpu.custom_scene(two, mats, **cam)}
+    for name, scene in scenes.items():
+        ds = gpu.DeviceScene(scene, 0, gpu_build=True)
+        r = ds.check()
+        ds.close()
+        n_tree = r["n_static_spheres"] + r["n_moving_spheres"] + r["n_triangles"]
+        assert r["bvh_errors"] == 0 and r["n_bvh_nodes"] == n_tree - 1 and 1 <= r["bvh_max_depth"] <= 64 and r["bvh_build_ms"] > 0, (name, r)
+        host_tree = gpu.DeviceScene(scene, 0)
+        rh = host_tree.check()
+        host_tree.close()
+        assert rh["bvh_errors"] == 0 and rh["bvh_build_ms"] == 0, (name, rh)    # the same check holds for the host's SAH tree
+        a, sa = gpu.render(scene, 160, 106, 8, 20, seed=3, flags=gpu.FLAG_BVH_BUILD_HOST)
+        b, sb = gpu.render(scene, 160, 106, 8, 20, seed=3, flags=gpu.FLAG_BVH_BUILD_GPU)
+        assert sa["bvh_build_gpu_ms"] == 0 and sb["bvh_build_gpu_ms"] > 0 and sb["scene_cache_hit"] == 0
+        assert sa["paths"] == sb["paths"] and abs(sa["rays"] - sb["rays"]) <= 2e-4 * sa["rays"], name
+        rel = np.abs(a[..., :3] - b[..., :3]) / np.maximum(a[..., :3], 1e-3)
+        assert (rel.max(axis=2) > 1e-5).mean() < (0.05 if "coincident" in name else 2e-3), name   # 3000 copies of one triangle: every hit is a tie
+    # against the oracle: same-stream frame through the device-built tree
+    scene = scenes["standin_62k"]
+    osc = port.scene_custom(scene.prims, scene.mats.view(oracle_mod.MAT_DTYPE), oracle_mod.camera_params(**scene.params))
+    acc, st = gpu.render(scene, 64, 36, 4, 20, seed=6, flags=gpu.FLAG_BVH_BUILD_GPU)
+    ref, _, rays = port.render_philox(osc, 64, 36, 0, 4, 20, seed=6, nthreads=8)
+    assert (np.abs(acc[..., :3] / 4 - ref / 4).max(axis=2) > 1e-3).mean() < 0.03 and abs(st["rays"] - rays) / rays < 0.01
