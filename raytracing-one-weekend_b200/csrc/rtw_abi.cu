@@ -369,7 +369,10 @@ int rtw::upload_flat(const HostFlat& hf, const rtw_camera& c, int64_t nprims, in
   if (hf.gpu_build) {
     int depth = 0;
     const auto* items = static_cast<const std::vector<rtw::BvhBuilder::Item>*>(hf.gpu_items.get());
-    if (int rc = gpu_build_bvh(items->data(), items->size(), sc->arena_ptr + hf.o_nodes, stream, &depth, &sc->gpu_build_ms)) return rc;
+    const bool sah_top = !(std::getenv("RTW_LBVH_SAH_TOP") && std::atoi(std::getenv("RTW_LBVH_SAH_TOP")) == 0);   // A/B knob
+    int top_nodes = 0;
+    if (int rc = gpu_build_bvh(items->data(), items->size(), sc->arena_ptr + hf.o_nodes, stream, sah_top, &depth, &sc->gpu_build_ms, &top_nodes)) return rc;
+    if (std::getenv("RTW_TRACE")) std::fprintf(stderr, "rtw trace: device BVH build %.2f ms, %d top nodes rebuilt with SAH, depth bound %d\n", sc->gpu_build_ms, top_nodes, depth);
     if (depth > rtw::kBvhStack)
       return fail("rtw_scene_upload: the device-built BVH is deeper than the kernels' traversal stack (" + std::to_string(depth) + " > " +
                   std::to_string(rtw::kBvhStack) + " levels): use the host builder (RTW_FLAG_BVH_BUILD_HOST)");
@@ -565,7 +568,7 @@ int rtw_flatten_info(const rtw_scene_desc* desc, rtw_flatten_report* out) {
   {
     const size_t tables = 16 + (hf.n_cw > 0 ? static_cast<size_t>(hf.n_cw) * 80 : static_cast<size_t>(hf.n_nodes) * 64) + ((hf.n_leaf_refs * 4 + 15) & ~size_t(15)) +
                           static_cast<size_t>(hf.n_static + hf.n_moving) * 32 + static_cast<size_t>(hf.n_cw > 0 ? hf.n_records : hf.n_tri) * 48;
-    const rtw::BvhPlan plan = rtw::plan_bvh(tables, hf.n_tri, hf.leaf_direct != 0, false, hf.n_cw > 0);
+    const rtw::BvhPlan plan = rtw::plan_bvh(tables, static_cast<size_t>(hf.n_nodes), hf.n_tri, hf.leaf_direct != 0, false, hf.n_cw > 0);
     out->bvh_variant = plan.variant; out->bvh_warps_per_cta = plan.warps; out->bvh_tables_in_smem = plan.tables_in_smem ? 1 : 0;
     out->reserved2 = 0; out->bvh_smem_bytes = static_cast<int64_t>(plan.smem_bytes);
   }

@@ -9,7 +9,9 @@
 // Any correct BVH returns the same closest hit: parity (primitive ids) does not depend on which builder ran.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <algorithm>
 #include <cfloat>
+#include <vector>
 
 #include "rtw_bvh.h"
 #include "rtw_host.h"
@@ -91,7 +93,7 @@ __device__ __forceinline__ int delta(const unsigned long long* __restrict__ keys
 
 // Karras 2012, one thread per internal node: children codes (>= 0: internal index, < 0: ~sorted leaf position) and parent links
 __global__ void __launch_bounds__(256) k_hierarchy(const unsigned long long* __restrict__ keys, int n, int2* __restrict__ children,
-                                                   int* __restrict__ parent_inner, int* __restrict__ parent_leaf) {
+                                                   int* __restrict__ parent_inner, int* __restrict__ parent_leaf, int* __restrict__ prefix) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
   const int d = delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1) >= 0 ? 1 : -1;
@@ -113,6 +115,7 @@ __global__ void __launch_bounds__(256) k_hierarchy(const unsigned long long* __r
   const int left = lo == gamma ? ~gamma : gamma;
   const int right = hi == gamma + 1 ? ~(gamma + 1) : gamma + 1;
   children[i] = make_int2(left, right);
+  prefix[i] = dnode;   // leading bits shared by every key below this node
   if (left >= 0) parent_inner[left] = i; else parent_leaf[gamma] = i;
   if (right >= 0) parent_inner[right] = i; else parent_leaf[gamma + 1] = i;
   if (i == 0) parent_inner[0] = -1;
@@ -164,6 +167,73 @@ __global__ void __launch_bounds__(256) k_depth(int n, const int* __restrict__ pa
   if ((threadIdx.x & 31) == 0 && depth > 0) atomicMax(max_depth, depth);
 }
 
+
+// ---- SAH over the top of the tree ---------------------------------------------------------------------------------------------------
+// The radix tree splits space at the Morton midpoints, which is what makes it 10-20 % slower to trace than a SAH tree; most of that
+// loss sits in the top levels, which every ray walks.  So the top is rebuilt: the nodes whose keys share fewer than P bits ("top
+// nodes") are discarded, the subtrees hanging below them ("clusters": a few thousand) keep their radix structure, and the host builds a
+// binned-SAH tree over the cluster boxes (a millisecond) whose nodes go back into the slots of the discarded top nodes.
+constexpr int kTopLevels = 4;   // candidate cut depths: 3 * (level + 3) + 1 key bits, i.e. octree levels 3..6
+// counts[l] <- number of top nodes for cut l (clusters = top nodes + 1)
+__global__ void __launch_bounds__(256) k_count_top(const int* __restrict__ prefix, int n, int* __restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int c[kTopLevels];
+#pragma unroll
+  for (int l = 0; l < kTopLevels; ++l) c[l] = (i < n - 1 && prefix[i] < 3 * (l + 3) + 1) ? 1 : 0;
+#pragma unroll
+  for (int l = 0; l < kTopLevels; ++l) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) c[l] += __shfl_xor_sync(0xffffffffu, c[l], off);
+    if ((threadIdx.x & 31) == 0 && c[l]) atomicAdd(counts + l, c[l]);
+  }
+}
+struct Cluster { float lo[3], hi[3]; int code; };   // code: >= 0 internal node of the radix tree, < 0: ~(primitive reference | direct mark)
+// top nodes (prefix < P) -> top[], their non-top children -> clusters[]; counters[0] = #top, counters[1] = #clusters
+__global__ void __launch_bounds__(256) k_collect_top(const GpuBuildItem* __restrict__ items, const int* __restrict__ order, const int* __restrict__ prefix, int n, int P,
+                                                     const int2* __restrict__ children, const NodeBox* __restrict__ boxes, int* __restrict__ top,
+                                                     Cluster* __restrict__ clusters, int* __restrict__ counters, uint8_t* __restrict__ is_top) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  const bool t = prefix[i] < P;
+  is_top[i] = t ? 1 : 0;
+  if (!t) return;
+  top[atomicAdd(counters, 1)] = i;
+  const int2 ch = children[i];
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const int c = side ? ch.y : ch.x;
+    if (c >= 0 && prefix[c] < P) continue;   // another top node
+    Cluster cl;
+    if (c < 0) {
+      const GpuBuildItem it = items[order[~c]];
+      for (int k = 0; k < 3; ++k) { cl.lo[k] = it.box.lo[k]; cl.hi[k] = it.box.hi[k]; }
+      cl.code = static_cast<int>(~(it.ref | BvhBuilder::kDirectMark));
+    } else {
+      const NodeBox b = boxes[c];
+      for (int k = 0; k < 3; ++k) { cl.lo[k] = b.lo[k]; cl.hi[k] = b.hi[k]; }
+      cl.code = c;
+    }
+    clusters[atomicAdd(counters + 1, 1)] = cl;
+  }
+}
+// deepest path from a cluster root down to a leaf (inner nodes), over all clusters
+__global__ void __launch_bounds__(256) k_depth_below_top(int n, const int* __restrict__ parent_inner, const int* __restrict__ parent_leaf,
+                                                         const uint8_t* __restrict__ is_top, int* __restrict__ max_depth) {
+  const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+  int depth = 0;
+  if (leaf < n) {
+    for (int node = parent_leaf[leaf]; node >= 0 && !is_top[node]; node = parent_inner[node]) ++depth;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) depth = max(depth, __shfl_xor_sync(0xffffffffu, depth, off));
+  if ((threadIdx.x & 31) == 0 && depth > 0) atomicMax(max_depth, depth);
+}
+struct SlotNode { int slot; int pad[3]; PackedNode node; };
+__global__ void __launch_bounds__(256) k_scatter_nodes(const SlotNode* __restrict__ src, int count, PackedNode* __restrict__ nodes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) nodes[src[i].slot] = src[i].node;
+}
+
 // centre + half-extent of a box exactly as BvhBuilder::centre_extent does on the host (half-extent rounded up: conservative)
 __device__ __forceinline__ void centre_extent_dev(const float lo[3], const float hi[3], float c[3], float e[3]) {
 #pragma unroll
@@ -204,21 +274,22 @@ __global__ void __launch_bounds__(256) k_pack(const GpuBuildItem* __restrict__ i
 }  // namespace
 
 // items: n >= 2 build records in host memory; nodes_out: device memory for n - 1 PackedNodes.  Runs on `stream`, returns after the
-// build has finished.  *depth_out <- deepest root-to-leaf path (inner nodes).
-int gpu_build_bvh(const void* items_host_v, size_t n, void* nodes_out_v, cudaStream_t stream, int* depth_out, double* build_ms) {
+// build has finished.  sah_top: rebuild the top of the radix tree with the host's SAH builder (a few thousand clusters).
+// *depth_out <- bound on the deepest root-to-leaf path (inner nodes); *top_nodes_out <- nodes replaced by the SAH top (0: none).
+int gpu_build_bvh(const void* items_host_v, size_t n, void* nodes_out_v, cudaStream_t stream, bool sah_top, int* depth_out, double* build_ms, int* top_nodes_out) {
   const GpuBuildItem* items_host = static_cast<const GpuBuildItem*>(items_host_v);
   PackedNode* nodes_out = static_cast<PackedNode*>(nodes_out_v);
   if (n < 2 || n >= (size_t(1) << 30)) return fail("gpu_build_bvh: primitive count out of range");
   const int ni = static_cast<int>(n);
   DevBuf<GpuBuildItem> d_items;
   DevBuf<unsigned long long> d_keys, d_keys_sorted;
-  DevBuf<int> d_vals, d_order, d_parent_inner, d_parent_leaf, d_visits, d_misc;
+  DevBuf<int> d_vals, d_order, d_parent_inner, d_parent_leaf, d_visits, d_misc, d_prefix;
   DevBuf<int2> d_children;
   DevBuf<NodeBox> d_boxes;
   DevBuf<unsigned char> d_temp;
   RTW_CUDA(d_items.alloc(n)); RTW_CUDA(d_keys.alloc(n)); RTW_CUDA(d_keys_sorted.alloc(n)); RTW_CUDA(d_vals.alloc(n)); RTW_CUDA(d_order.alloc(n));
   RTW_CUDA(d_parent_inner.alloc(n)); RTW_CUDA(d_parent_leaf.alloc(n)); RTW_CUDA(d_visits.alloc(n)); RTW_CUDA(d_misc.alloc(8));
-  RTW_CUDA(d_children.alloc(n)); RTW_CUDA(d_boxes.alloc(n));
+  RTW_CUDA(d_children.alloc(n)); RTW_CUDA(d_boxes.alloc(n)); RTW_CUDA(d_prefix.alloc(n));
   RTW_CUDA(cudaMemcpyAsync(d_items.p, items_host, n * sizeof(GpuBuildItem), cudaMemcpyHostToDevice, stream));
   EventPair ev;
   RTW_CUDA(ev.create());
@@ -236,7 +307,7 @@ int gpu_build_bvh(const void* items_host_v, size_t n, void* nodes_out_v, cudaStr
   RTW_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, d_keys.p, d_keys_sorted.p, d_vals.p, d_order.p, ni, 0, 63, stream));
   RTW_CUDA(d_temp.alloc(temp_bytes));
   RTW_CUDA(cub::DeviceRadixSort::SortPairs(d_temp.p, temp_bytes, d_keys.p, d_keys_sorted.p, d_vals.p, d_order.p, ni, 0, 63, stream));
-  k_hierarchy<<<blocks, 256, 0, stream>>>(d_keys_sorted.p, ni, d_children.p, d_parent_inner.p, d_parent_leaf.p);
+  k_hierarchy<<<blocks, 256, 0, stream>>>(d_keys_sorted.p, ni, d_children.p, d_parent_inner.p, d_parent_leaf.p, d_prefix.p);
   count_launch();
   k_refit<<<blocks, 256, 0, stream>>>(d_items.p, d_order.p, ni, d_children.p, d_parent_inner.p, d_parent_leaf.p, d_boxes.p, d_visits.p);
   count_launch();
@@ -245,14 +316,84 @@ int gpu_build_bvh(const void* items_host_v, size_t n, void* nodes_out_v, cudaStr
   k_pack<<<blocks, 256, 0, stream>>>(d_items.p, d_order.p, ni, d_children.p, d_boxes.p, nodes_out);
   count_launch();
   RTW_CUDA(cudaGetLastError());
+  int depth = 0;
+  RTW_CUDA(cudaMemcpyAsync(&depth, d_misc.p + 6, sizeof depth, cudaMemcpyDeviceToHost, stream));
+
+  // ---- SAH over the top of the tree (see k_count_top) ------------------------------------------------------------------------------
+  int top_nodes = 0;
+  if (sah_top && n >= 4096) {
+    DevBuf<int> d_counts;
+    RTW_CUDA(d_counts.alloc(kTopLevels + 4));
+    RTW_CUDA(cudaMemsetAsync(d_counts.p, 0, (kTopLevels + 4) * sizeof(int), stream));
+    k_count_top<<<blocks, 256, 0, stream>>>(d_prefix.p, ni, d_counts.p);
+    count_launch();
+    int counts[kTopLevels];
+    RTW_CUDA(cudaMemcpyAsync(counts, d_counts.p, sizeof counts, cudaMemcpyDeviceToHost, stream));
+    RTW_CUDA(cudaStreamSynchronize(stream));
+    int level = -1;   // the deepest cut with at most 16 384 clusters (and at least 64, else the radix tree is degenerate up there)
+    for (int l = 0; l < kTopLevels; ++l)
+      if (counts[l] + 1 <= 16384 && counts[l] + 1 >= 64) level = l;
+    if (level >= 0) {
+      const int P = 3 * (level + 3) + 1, T = counts[level], Cn = T + 1;
+      DevBuf<int> d_top;
+      DevBuf<Cluster> d_clusters;
+      DevBuf<uint8_t> d_is_top;
+      DevBuf<SlotNode> d_slot_nodes;
+      RTW_CUDA(d_top.alloc(static_cast<size_t>(T))); RTW_CUDA(d_clusters.alloc(static_cast<size_t>(Cn))); RTW_CUDA(d_is_top.alloc(n)); RTW_CUDA(d_slot_nodes.alloc(static_cast<size_t>(T)));
+      int* ctr = d_counts.p + kTopLevels;   // {#top, #clusters, depth below the top}
+      k_collect_top<<<blocks, 256, 0, stream>>>(d_items.p, d_order.p, d_prefix.p, ni, P, d_children.p, d_boxes.p, d_top.p, d_clusters.p, ctr, d_is_top.p);
+      count_launch();
+      k_depth_below_top<<<blocks, 256, 0, stream>>>(ni, d_parent_inner.p, d_parent_leaf.p, d_is_top.p, ctr + 2);
+      count_launch();
+      std::vector<int> top(static_cast<size_t>(T));
+      std::vector<Cluster> clusters(static_cast<size_t>(Cn));
+      int got[3] = {0, 0, 0};
+      RTW_CUDA(cudaMemcpyAsync(top.data(), d_top.p, top.size() * sizeof(int), cudaMemcpyDeviceToHost, stream));
+      RTW_CUDA(cudaMemcpyAsync(clusters.data(), d_clusters.p, clusters.size() * sizeof(Cluster), cudaMemcpyDeviceToHost, stream));
+      RTW_CUDA(cudaMemcpyAsync(got, ctr, sizeof got, cudaMemcpyDeviceToHost, stream));
+      RTW_CUDA(cudaStreamSynchronize(stream));
+      if (got[0] == T && got[1] == Cn) {
+        std::sort(top.begin(), top.end());      // the root of the radix tree (node 0) stays the root: slot 0
+        std::vector<BvhBuilder::Item> citems(clusters.size());
+        for (size_t k = 0; k < clusters.size(); ++k) {
+          for (int a = 0; a < 3; ++a) { citems[k].box.lo[a] = clusters[k].lo[a]; citems[k].box.hi[a] = clusters[k].hi[a]; }
+          citems[k].ref = static_cast<uint32_t>(k);
+        }
+        std::vector<int> code_of(clusters.size());
+        for (size_t k = 0; k < clusters.size(); ++k) code_of[k] = clusters[k].code;
+        std::vector<PackedNode> tnodes(static_cast<size_t>(T));
+        BvhBuilder tb;
+        tb.build_items_direct(citems, tnodes.data());
+        if (tb.max_depth() + got[2] <= kBvhStack) {
+          std::vector<SlotNode> sn(static_cast<size_t>(T));
+          auto remap = [&](int32_t code) -> int32_t {
+            if (code >= 0) return top[static_cast<size_t>(code)];                                   // inner node of the new top -> its slot
+            return code_of[(static_cast<uint32_t>(~code) & ~BvhBuilder::kDirectMark) & 0x1fffffffu];   // leaf of the new top -> the cluster
+          };
+          for (int j = 0; j < T; ++j) {
+            sn[static_cast<size_t>(j)].slot = top[static_cast<size_t>(j)];
+            sn[static_cast<size_t>(j)].node = tnodes[static_cast<size_t>(j)];
+            sn[static_cast<size_t>(j)].node.left = remap(tnodes[static_cast<size_t>(j)].left);
+            sn[static_cast<size_t>(j)].node.right = remap(tnodes[static_cast<size_t>(j)].right);
+          }
+          RTW_CUDA(cudaMemcpyAsync(d_slot_nodes.p, sn.data(), sn.size() * sizeof(SlotNode), cudaMemcpyHostToDevice, stream));
+          k_scatter_nodes<<<static_cast<unsigned>((T + 255) / 256), 256, 0, stream>>>(d_slot_nodes.p, T, nodes_out);
+          count_launch();
+          RTW_CUDA(cudaGetLastError());
+          RTW_CUDA(cudaStreamSynchronize(stream));
+          depth = tb.max_depth() + got[2];
+          top_nodes = T;
+        }
+      }
+    }
+  }
   RTW_CUDA(cudaEventRecord(ev.b, stream));
-  int misc[8];
-  RTW_CUDA(cudaMemcpyAsync(misc, d_misc.p, sizeof misc, cudaMemcpyDeviceToHost, stream));
   RTW_CUDA(cudaStreamSynchronize(stream));
   float ms = 0.f;
   RTW_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
   if (build_ms) *build_ms = ms;
-  if (depth_out) *depth_out = misc[6];
+  if (depth_out) *depth_out = depth;
+  if (top_nodes_out) *top_nodes_out = top_nodes;
   return 0;
 }
 
