@@ -568,7 +568,7 @@ int rtw_flatten_info(const rtw_scene_desc* desc, rtw_flatten_report* out) {
   {
     const size_t tables = 16 + (hf.n_cw > 0 ? static_cast<size_t>(hf.n_cw) * 80 : static_cast<size_t>(hf.n_nodes) * 64) + ((hf.n_leaf_refs * 4 + 15) & ~size_t(15)) +
                           static_cast<size_t>(hf.n_static + hf.n_moving) * 32 + static_cast<size_t>(hf.n_cw > 0 ? hf.n_records : hf.n_tri) * 48;
-    const rtw::BvhPlan plan = rtw::plan_bvh(tables, static_cast<size_t>(hf.n_nodes), hf.n_tri, hf.leaf_direct != 0, false, hf.n_cw > 0);
+    const rtw::BvhPlan plan = rtw::plan_bvh(tables, hf.n_tri, hf.leaf_direct != 0, false, hf.n_cw > 0);
     out->bvh_variant = plan.variant; out->bvh_warps_per_cta = plan.warps; out->bvh_tables_in_smem = plan.tables_in_smem ? 1 : 0;
     out->reserved2 = 0; out->bvh_smem_bytes = static_cast<int64_t>(plan.smem_bytes);
   }

@@ -70,22 +70,20 @@ struct BvhPlan {
   bool tables_in_smem;
   size_t smem_bytes;    // dynamic shared memory of the launch
 };
-// table_bytes counts 64 bytes per node; the wavefront kernel keeps its nodes at a stride of kWfNodeStride x 16 = 80 bytes in shared
-// memory (one spare quad per node: with a 64-byte stride the same quad of all nodes falls on only two bank groups, which made
-// the node fetch 60 % of the kernel's shared-memory wavefronts and conflict on half of them), so its tables are n_nodes x 16 bytes bigger.
-constexpr int kWfNodeStride = 5;   // float4 per node in the wavefront kernel's shared memory
-inline BvhPlan plan_bvh(size_t table_bytes, size_t n_nodes, int n_tri, bool leaf_direct, bool force_perlane, bool cw = false) {
+// (Measured and not kept: the nodes at an 80-byte stride in shared memory, one spare quad per node, so that the same quad of
+// different nodes spreads over all eight bank groups instead of two.  Bank conflicts 149 M -> 96 M per 8-spp frame, LSU pipe
+// 55 -> 48 %, run time unchanged -- 35.73 against 35.58-35.76 ms at 128 spp -- because the kernel is bound by issue, not by that pipe.)
+inline BvhPlan plan_bvh(size_t table_bytes, int n_tri, bool leaf_direct, bool force_perlane, bool cw = false) {
   if (cw) {  // scenes with triangles: compressed wide BVH, per-lane state machine, three CTAs per SM (the 8-child slab test needs registers)
     if (table_bytes <= kPerLaneSmemTables) return {RTW_BVH_CWIDE, 8, true, table_bytes};
     return {RTW_BVH_CWIDE, 8, false, 0};
   }
   const size_t wf_warp = wf_warp_bytes(kWfRecords);
-  const size_t wf_tables = table_bytes + n_nodes * (kWfNodeStride * 16 - 64);
   if (leaf_direct && !force_perlane) {
-    if (wf_tables + 28 * wf_warp <= kSmemCap) return {RTW_BVH_WAVEFRONT, 28, true, wf_tables + 28 * wf_warp};
+    if (table_bytes + 28 * wf_warp <= kSmemCap) return {RTW_BVH_WAVEFRONT, 28, true, table_bytes + 28 * wf_warp};
     if (n_tri == 0) {
-      if (wf_tables + 24 * wf_warp <= kSmemCap) return {RTW_BVH_WAVEFRONT, 24, true, wf_tables + 24 * wf_warp};
-      if (wf_tables + 20 * wf_warp <= kSmemCap) return {RTW_BVH_WAVEFRONT, 20, true, wf_tables + 20 * wf_warp};
+      if (table_bytes + 24 * wf_warp <= kSmemCap) return {RTW_BVH_WAVEFRONT, 24, true, table_bytes + 24 * wf_warp};
+      if (table_bytes + 20 * wf_warp <= kSmemCap) return {RTW_BVH_WAVEFRONT, 20, true, table_bytes + 20 * wf_warp};
       return {RTW_BVH_WAVEFRONT, 8, false, 16 + 8 * wf_warp};
     }
   }

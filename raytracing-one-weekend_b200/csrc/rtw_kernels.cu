@@ -867,9 +867,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_render_wf(const __grid_consta
         for (uint32_t off = 0; off < bytes; off += kChunk)
           tma_bulk_g2s(dst + off, static_cast<const unsigned char*>(src) + off, min(kChunk, bytes - off), bar);
       };
-      for (int i = 0; i < sc.n_nodes; ++i)   // node by node: 64 bytes each, to an 80-byte stride (bank spread, see plan_bvh)
-        tma_bulk_g2s(smem_raw + so.nodes + static_cast<uint32_t>(i) * (kWfNodeStride * 16u), reinterpret_cast<const unsigned char*>(sc.nodes) + static_cast<size_t>(i) * 64u, 64u, bar);
-      copy(smem_raw + so.refs, sc.leafRefs, so.b_refs);
+      copy(smem_raw + so.nodes, sc.nodes, so.b_nodes); copy(smem_raw + so.refs, sc.leafRefs, so.b_refs);
       copy(smem_raw + so.sa, sc.sphA, so.b_sph); copy(smem_raw + so.sb, sc.sphB, so.b_sph);
       copy(smem_raw + so.tri, sc.tri, so.b_tri);
     }
@@ -1095,8 +1093,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_render_wf(const __grid_consta
       if (state == TRAV && node >= 0) {
         if (STATS) ++n_nodes;
         float4 q0, q1, q2, q3;
-        if (SMEM) { const float4* nq = tb.nodes + kWfNodeStride * node; q0 = nq[0]; q1 = nq[1]; q2 = nq[2]; q3 = nq[3]; }
-        else load_node<false>(tb.nodes, node, q0, q1, q2, q3);
+        load_node<SMEM>(tb.nodes, node, q0, q1, q2, q3);
         float ln, lf, rn, rf;
         node_slabs(q0, q1, q2, idx, idy, idz, odx, ody, odz, best_t, ln, lf, rn, rf);
         const bool hl = ln <= lf, hr = rn <= rf;
@@ -1440,7 +1437,7 @@ cudaError_t launch_render(const RenderParams& p_in, int mode, int rays_per_lane,
     return stats ? launch_sweep_t<2, true>(p, sm_count, smem, stream, nullptr) : launch_sweep_t<2, false>(p, sm_count, smem, stream, nullptr);
   }
   const bool cw = p.sc.n_cw_nodes > 0;
-  const BvhPlan plan = plan_bvh(p.so.records, static_cast<size_t>(p.sc.n_nodes), p.sc.n_tri, p.sc.leaf_direct != 0, force_perlane, cw);   // rtw_internal.h: who gets which kernel
+  const BvhPlan plan = plan_bvh(p.so.records, p.sc.n_tri, p.sc.leaf_direct != 0, force_perlane, cw);   // rtw_internal.h: who gets which kernel
   if (variant) *variant = plan.variant;
   if (plan.variant == RTW_BVH_CWIDE) {
     // scenes with triangles: compressed 8-wide BVH walked by the per-lane state machine; tables in shared memory when they fit
@@ -1459,10 +1456,6 @@ cudaError_t launch_render(const RenderParams& p_in, int mode, int rays_per_lane,
     if (!plan.tables_in_smem) {
       p.so.records = 16u;   // no staged tables in front of the records
       RTW_WF_LAUNCH(false, 8, 3);
-    }
-    {   // tables in shared memory: the nodes sit at an 80-byte stride there (see plan_bvh), everything behind them moves up
-      const uint32_t pad = static_cast<uint32_t>(p.sc.n_nodes) * (kWfNodeStride * 16u - 64u);
-      p.so.refs += pad; p.so.sa += pad; p.so.sb += pad; p.so.tri += pad; p.so.records += pad;
     }
     switch (plan.warps) {
       case 28: RTW_WF_LAUNCH(true, 28, 1);
