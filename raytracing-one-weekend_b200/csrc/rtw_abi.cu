@@ -652,7 +652,7 @@ int rtw_flatten_info(const rtw_scene_desc* desc, rtw_flatten_report* out) {
     for (int which = 0; which < 2; ++which) {
       const int32_t code = which == 0 ? nodes[n].left : nodes[n].right;
       if (code >= 0) { todo.push_back({code, dpt + 1}); continue; }
-      if (which == 1 && seen.size() <= static_cast<size_t>(hf.leaf_direct ? 1 : 31) && hf.n_nodes == 1 && nodes[n].rc_z >= 1.0e38f)
+      if (which == 1 && seen.size() <= static_cast<size_t>(hf.leaf_direct ? 1 : 31) && hf.n_nodes == 1 && nodes[n].c[2][1] >= 1.0e38f)
         continue;  // the never-entered filler child of a single-leaf tree (inverted box)
       const uint32_t v = static_cast<uint32_t>(~code);
       if (hf.leaf_direct) visit_ref(v);
@@ -737,8 +737,8 @@ int rtw_scene_check(const rtw_scene* scene, rtw_flatten_report* out) {
       const rtw::PackedNode& nd = nodes[n];
       for (int side = 0; side < 2; ++side) {
         const int32_t code = side ? nd.right : nd.left;
-        const float c[3] = {side ? nd.rc_xy[0] : nd.lc[0], side ? nd.rc_xy[1] : nd.lc[1], side ? nd.rc_z : nd.lc[2]};
-        const float e[3] = {side ? nd.re[0] : nd.le_x, side ? nd.re[1] : nd.le_yz[0], side ? nd.re[2] : nd.le_yz[1]};
+        const float c[3] = {nd.c[0][side], nd.c[1][side], nd.c[2][side]};
+        const float e[3] = {nd.e[0][side], nd.e[1][side], nd.e[2][side]};
         if (side == 1 && n_nodes == 1 && c[2] >= 1.0e38f) continue;   // the never-entered filler child of a single-leaf tree
         const rtw::Box3 below = code >= 0 ? visit(code, depth + 1) : prim_box(static_cast<uint32_t>(~code));
         for (int k = 0; k < 3; ++k)

@@ -259,13 +259,13 @@ __global__ void __launch_bounds__(256) k_pack(const GpuBuildItem* __restrict__ i
     int code;
     if (ch.x < 0) { const GpuBuildItem it = items[order[~ch.x]]; centre_extent_dev(it.box.lo, it.box.hi, c, e); code = static_cast<int>(~(it.ref | BvhBuilder::kDirectMark)); }
     else { const NodeBox b = boxes[ch.x]; centre_extent_dev(b.lo, b.hi, c, e); code = ch.x; }
-    nd.lc[0] = c[0]; nd.lc[1] = c[1]; nd.lc[2] = c[2]; nd.le_x = e[0]; nd.le_yz[0] = e[1]; nd.le_yz[1] = e[2]; nd.left = code;
+    for (int k = 0; k < 3; ++k) { nd.c[k][0] = c[k]; nd.e[k][0] = e[k]; } nd.left = code;
   }
   {
     int code;
     if (ch.y < 0) { const GpuBuildItem it = items[order[~ch.y]]; centre_extent_dev(it.box.lo, it.box.hi, c, e); code = static_cast<int>(~(it.ref | BvhBuilder::kDirectMark)); }
     else { const NodeBox b = boxes[ch.y]; centre_extent_dev(b.lo, b.hi, c, e); code = ch.y; }
-    nd.rc_xy[0] = c[0]; nd.rc_xy[1] = c[1]; nd.rc_z = c[2]; nd.re[0] = e[0]; nd.re[1] = e[1]; nd.re[2] = e[2]; nd.right = code;
+    for (int k = 0; k < 3; ++k) { nd.c[k][1] = c[k]; nd.e[k][1] = e[k]; } nd.right = code;
   }
   nd.pad0 = 0; nd.pad1 = 0;
   out[i] = nd;

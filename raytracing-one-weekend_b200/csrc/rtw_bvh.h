@@ -26,10 +26,9 @@ struct Box3 {
   }
 };
 
-struct PackedNode {  // 4 x float4, see DevScene::nodes: each child box as centre + half-extent
-  float lc[3], le_x;
-  float le_yz[2], rc_xy[2];
-  float rc_z, re[3];
+struct PackedNode {  // 4 x float4, see DevScene::nodes: each child box as centre + half-extent, the two children of an axis side by side
+  float c[3][2];   // c[axis][child]: (left, right) pairs, so that one packed FFMA2 (fma.rn.f32x2, sm_100) works on both children
+  float e[3][2];   // half-extents, same pairing
   int32_t left, right, pad0, pad1;
 };
 constexpr float kEmptyChildCentre = 3.0e38f;  // centre of a never-entered filler child (half-extent 0)
@@ -374,15 +373,8 @@ class BvhBuilder {
   static void set_child(PackedNode& nd, int which, const Box3& b, int32_t code) {
     float c[3], e[3];
     centre_extent(b, c, e);
-    if (which == 0) {
-      nd.lc[0] = c[0]; nd.lc[1] = c[1]; nd.lc[2] = c[2];
-      nd.le_x = e[0]; nd.le_yz[0] = e[1]; nd.le_yz[1] = e[2];
-      nd.left = code;
-    } else {
-      nd.rc_xy[0] = c[0]; nd.rc_xy[1] = c[1]; nd.rc_z = c[2];
-      nd.re[0] = e[0]; nd.re[1] = e[1]; nd.re[2] = e[2];
-      nd.right = code;
-    }
+    for (int k = 0; k < 3; ++k) { nd.c[k][which] = c[k]; nd.e[k][which] = e[k]; }
+    (which == 0 ? nd.left : nd.right) = code;
   }
   // leaf child code: ~((first << 5) | count) into leaf_refs, or, with single-primitive leaves (kMaxLeaf == 1),
   // ~reference itself: no indirection left on the device

@@ -50,8 +50,9 @@ struct DevScene {
   const int2* triId;
   int32_t n_tri;
   // BVH over small spheres + triangles: 4 float4 per node, each child box as centre c and half-extent e
-  //   q0 = (lc.x, lc.y, lc.z, le.x) q1 = (le.y, le.z, rc.x, rc.y)
-  //   q2 = (rc.z, re.x, re.y, re.z) q3 = (left, right, -, -) as int bits
+  //   (left, right) pairs per axis, so that one packed FFMA2 handles both children:
+  //   q0 = (lc.x, rc.x, lc.y, rc.y) q1 = (lc.z, rc.z, le.x, re.x)
+  //   q2 = (le.y, re.y, le.z, re.z) q3 = (left, right, -, -) as int bits
   //   child >= 0: inner node index; child < 0: leaf, ~child = (first << 5) | count  into leafRefs,
   //   or (leaf_direct) ~child = the primitive reference itself with bit 29 set (so that the code is never -1 = "no node")
   const float4* nodes;
@@ -198,17 +199,45 @@ __device__ __forceinline__ void load_node(const float4* nodes, int node, float4&
 
 // Slab test of both children of a BVH node (Aabb::hit, common-model.h:71-84) against [kTMin, tmax].  With the box stored as
 // centre c and half-extent e >= 0 the entry/exit parameters along one axis are (c -+ e) * (1/d) - o/d = tc -+ e * |1/d|:
-// three FFMA per axis on the FMA pipe and no per-axis min/max on the ALU pipe, which is the busiest pipe of the traversal
-// kernels (profiles/).  Measured on the cover scene: min/max form 6670, FMUL + FADD|.| form 6850, this form 7040 Mpaths/s.
+// three FMAs per axis and box on the FMA pipe and no per-axis min/max on the ALU pipe (measured on the cover scene in round 1:
+// min/max form 6670, FMUL + FADD|.| form 6850, FFMA form 7040 Mpaths/s).
+// The node stores the (left, right) values of an axis side by side.  That layout also feeds the packed FP32 FMA of sm_100 (PTX
+// fma.rn.f32x2, SASS FFMA2: an LDS.128 / LDG.256 drops the pairs into aligned registers, 1/d, -o/d, |1/d| enter as broadcast operands),
+// which issues the 18 FMAs of a node as 9 instructions, bit-identical results.  Built, measured on one box against this scalar form
+// and NOT used (-DRTW_FFMA2_SLABS builds it; scripts/ffma2_probe.cu, profiles/r02_ffma2.txt): FFMA2 runs at half the issue rate of
+// FFMA (same FP32 peak), K2w executes 3.7 % fewer warp instructions and is 0.5 % SLOWER (issue-active 79 -> 76 %), suzanne -1.5 %,
+// the 991k-triangle mesh -2.2 %: these kernels wait on dependent-instruction latency, and the packed form has less ILP per node.
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void up2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
 __device__ __forceinline__ void node_slabs(const float4 q0, const float4 q1, const float4 q2, float idx, float idy, float idz, float odx,
                                            float ody, float odz, float tmax, float& ln, float& lf, float& rn, float& rf) {
   const float ax = fabsf(idx), ay = fabsf(idy), az = fabsf(idz);
-  float cx = fmaf(q0.x, idx, -odx), cy = fmaf(q0.y, idy, -ody), cz = fmaf(q0.z, idz, -odz);
-  ln = fmaxf(fmaxf(fmaf(-q0.w, ax, cx), fmaf(-q1.x, ay, cy)), fmaxf(fmaf(-q1.y, az, cz), kTMin));
-  lf = fminf(fminf(fmaf(q0.w, ax, cx), fmaf(q1.x, ay, cy)), fminf(fmaf(q1.y, az, cz), tmax));
-  cx = fmaf(q1.z, idx, -odx); cy = fmaf(q1.w, idy, -ody); cz = fmaf(q2.x, idz, -odz);
-  rn = fmaxf(fmaxf(fmaf(-q2.y, ax, cx), fmaf(-q2.z, ay, cy)), fmaxf(fmaf(-q2.w, az, cz), kTMin));
-  rf = fminf(fminf(fmaf(q2.y, ax, cx), fmaf(q2.z, ay, cy)), fminf(fmaf(q2.w, az, cz), tmax));
+#ifndef RTW_FFMA2_SLABS   // the product: 18 scalar FFMA (the packed form below was measured slower, see the comment above)
+  float cx = fmaf(q0.x, idx, -odx), cy = fmaf(q0.z, idy, -ody), cz = fmaf(q1.x, idz, -odz);
+  ln = fmaxf(fmaxf(fmaf(-q1.z, ax, cx), fmaf(-q2.x, ay, cy)), fmaxf(fmaf(-q2.z, az, cz), kTMin));
+  lf = fminf(fminf(fmaf(q1.z, ax, cx), fmaf(q2.x, ay, cy)), fminf(fmaf(q2.z, az, cz), tmax));
+  cx = fmaf(q0.y, idx, -odx); cy = fmaf(q0.w, idy, -ody); cz = fmaf(q1.y, idz, -odz);
+  rn = fmaxf(fmaxf(fmaf(-q1.w, ax, cx), fmaf(-q2.y, ay, cy)), fmaxf(fmaf(-q2.w, az, cz), kTMin));
+  rf = fminf(fminf(fmaf(q1.w, ax, cx), fmaf(q2.y, ay, cy)), fminf(fmaf(q2.w, az, cz), tmax));
+#else
+  const uint64_t tcx = fma2(pk2(q0.x, q0.y), pk2(idx, idx), pk2(-odx, -odx));
+  const uint64_t tcy = fma2(pk2(q0.z, q0.w), pk2(idy, idy), pk2(-ody, -ody));
+  const uint64_t tcz = fma2(pk2(q1.x, q1.y), pk2(idz, idz), pk2(-odz, -odz));
+  const uint64_t ex = pk2(q1.z, q1.w), ey = pk2(q2.x, q2.y), ez = pk2(q2.z, q2.w);
+  float lnx, rnx, lny, rny, lnz, rnz, lfx, rfx, lfy, rfy, lfz, rfz;
+  up2(fma2(ex, pk2(-ax, -ax), tcx), lnx, rnx); up2(fma2(ex, pk2(ax, ax), tcx), lfx, rfx);
+  up2(fma2(ey, pk2(-ay, -ay), tcy), lny, rny); up2(fma2(ey, pk2(ay, ay), tcy), lfy, rfy);
+  up2(fma2(ez, pk2(-az, -az), tcz), lnz, rnz); up2(fma2(ez, pk2(az, az), tcz), lfz, rfz);
+  ln = fmaxf(fmaxf(lnx, lny), fmaxf(lnz, kTMin));
+  lf = fminf(fminf(lfx, lfy), fminf(lfz, tmax));
+  rn = fmaxf(fmaxf(rnx, rny), fmaxf(rnz, kTMin));
+  rf = fminf(fminf(rfx, rfy), fminf(rfz, tmax));
+#endif
 }
 
 

@@ -54,13 +54,17 @@ struct PrimaryParams {
 
 // Which BVH kernel a scene gets (pure host logic, also reported by rtw_flatten_info so that it can be tested without a GPU).
 //   table_bytes: 16 + nodes + leaf refs + sphere tables + triangles, the shared-memory footprint of the staged tables.
-// Wavefront-per-warp kernel (K2w) while the tables leave room for the per-warp path records: 28 warps per SM (72 registers) up to
-// ~58 KB of tables, and for sphere-only scenes 24 warps up to ~87 KB and 20 warps up to ~111 KB (cover scene with -n 13..17, 678 to
-// 1159 spheres: +12..29 % over the per-lane kernel; 16 warps at 1296 spheres: -2 %, not instantiated).  Sphere-only scenes beyond
-// that: the same kernel with the tables read through L1/L2, three 256-thread CTAs per SM (-n 40, 6 402 spheres: 4 284 against 3 912
-// Mpaths/s; -n 120, 57 603 spheres: 3 307 against 3 267).  Meshes beyond the 28-warp tier, multi-primitive leaves, or on request:
-// the per-lane state machine (K2), its tables in shared memory up to 72 KB.
+// Wavefront-per-warp kernel (K2w) while the tables leave room for the per-warp path records: 32 warps per SM (64 registers: the lane
+// keeps only what the node visits need, 92 records per warp) up to ~46 KB of tables -- the cover scene fits with 176 bytes to spare --,
+// 28 warps (72 registers, 96 records) up to ~58 KB, and for sphere-only scenes 24 warps up to ~87 KB and 20 warps up to ~111 KB (cover
+// scene with -n 13..17, 678 to 1159 spheres: +12..29 % over the per-lane kernel; 16 warps at 1296 spheres: -2 %, not instantiated).
+// Sphere-only scenes beyond that: the same kernel with the tables read through L1/L2, three 256-thread CTAs per SM (-n 40, 6 402 spheres:
+// 4 284 against 3 912 Mpaths/s; -n 120, 57 603 spheres: 3 307 against 3 267).  Meshes beyond the 28-warp tier, multi-primitive leaves, or
+// on request: the per-lane state machine (K2), its tables in shared memory up to 72 KB.
+// Measured on the cover scene (1080p x 128 spp, one box, scripts/r2_gpu10.sh / r2_gpu12.sh): 20 / 24 / 28 warps 39.46 / 37.97 / 35.48 ms,
+// 32 warps with 88 records and batches of 28 / 88, 32 / 92, 30 / 92, 32: 34.91 / 34.96 / 34.84 / 34.68 ms.
 constexpr int kWfRecords = 96;                      // path records per warp of K2w
+constexpr int kWfRecords32 = 92;                    // ... of its 32-warp tier (>= 32 in flight + 2 x 30: a batch of >= 30 records of one kind always exists)
 constexpr size_t kSmemCap = 227u * 1024u;           // dynamic shared memory one CTA may ask for on sm_100
 constexpr size_t kPerLaneSmemTables = 72u * 1024u;  // K2 stages its tables in shared memory up to this size (4 CTAs per SM for the cover scene)
 __host__ __device__ constexpr uint32_t wf_warp_bytes(int P) { return static_cast<uint32_t>((P * (48 + 8 + 4) + 3 * P + 15) & ~15); }
@@ -80,6 +84,7 @@ inline BvhPlan plan_bvh(size_t table_bytes, int n_tri, bool leaf_direct, bool fo
   }
   const size_t wf_warp = wf_warp_bytes(kWfRecords);
   if (leaf_direct && !force_perlane) {
+    if (table_bytes + 32 * wf_warp_bytes(kWfRecords32) <= kSmemCap) return {RTW_BVH_WAVEFRONT, 32, true, table_bytes + 32 * wf_warp_bytes(kWfRecords32)};
     if (table_bytes + 28 * wf_warp <= kSmemCap) return {RTW_BVH_WAVEFRONT, 28, true, table_bytes + 28 * wf_warp};
     if (n_tri == 0) {
       if (table_bytes + 24 * wf_warp <= kSmemCap) return {RTW_BVH_WAVEFRONT, 24, true, table_bytes + 24 * wf_warp};

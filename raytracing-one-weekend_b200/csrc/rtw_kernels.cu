@@ -848,6 +848,10 @@ constexpr int kEnded = -3;   // path ended without a sky term (depth cut / absor
 template <bool SMEM, bool STATS, int NW, int P, int STEPS, int BATCH, int MINB = 1>
 __global__ void __launch_bounds__(NW * 32, MINB) k_render_wf(const __grid_constant__ RenderParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  // LEAN (32 warps per SM: 64 registers): the lane keeps only what the node visits need (1/d, o/d, closest hit); origin, direction
+  // and time of its ray are read back from the record for the ~1 leaf test per ray.  More warps is what this kernel responds to
+  // (20 / 24 / 28 / 32 warps: 39.5 / 38.0 / 35.5 / 34.7 ms), not fewer instructions (rtw_internal.h)
+  constexpr bool LEAN = NW > 28;
   const DevScene& sc = p.sc;
   BvhTables tb{sc.nodes, sc.leafRefs, sc.sphA, sc.sphB, sc.tri};
   if (SMEM) {
@@ -943,12 +947,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_render_wf(const __grid_consta
       if (state == IDLE && rank < n_ready) {
         rec = q_ready[n_ready - 1u - rank];
         const float4 a = recO[rec], b = recD[rec];
-        o = mk<float>(a.x, a.y, a.z); tm = a.w;
-        d = mk<float>(b.x, b.y, b.z); best_t = b.w;
+        best_t = b.w;
         best_i = __float_as_int(recT[rec].w);
-        qa = dot(d, d); qia = fast_rcp(qa);
-        idx = fast_rcp(d.x); idy = fast_rcp(d.y); idz = fast_rcp(d.z);
-        odx = o.x * idx; ody = o.y * idy; odz = o.z * idz;
+        idx = fast_rcp(b.x); idy = fast_rcp(b.y); idz = fast_rcp(b.z);
+        odx = a.x * idx; ody = a.y * idy; odz = a.z * idz;
+        if (!LEAN) {
+          o = mk<float>(a.x, a.y, a.z); tm = a.w;
+          d = mk<float>(b.x, b.y, b.z);
+          qa = dot(d, d); qia = fast_rcp(qa);
+        }
         sp = 0;
         node = sc.n_nodes > 0 ? 0 : kMiss;
         state = node == kMiss ? FIN : TRAV;
@@ -1098,6 +1105,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_render_wf(const __grid_consta
         node_slabs(q0, q1, q2, idx, idy, idz, odx, ody, odz, best_t, ln, lf, rn, rf);
         const bool hl = ln <= lf, hr = rn <= rf;
         const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
+        // (a branch-free form of this -- predicated push / pop, selects -- was measured: 36.54 against 35.48 ms, not kept)
         if (hl && hr) {
           const bool lfirst = ln <= rn;
           node = lfirst ? left : right;
@@ -1114,6 +1122,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_render_wf(const __grid_consta
       }
       if (state == TRAV && node < 0) {
         const uint32_t v = static_cast<uint32_t>(~node);
+        if (LEAN) {
+          const float4 a = recO[rec], b = recD[rec];
+          o = mk<float>(a.x, a.y, a.z); tm = a.w;
+          d = mk<float>(b.x, b.y, b.z);
+          qa = dot(d, d); qia = fast_rcp(qa);
+        }
         auto test_ref = [&](uint32_t ref) {
           const int i = static_cast<int>(ref & 0x1fffffffu);
           if (ref >> 30) {
@@ -1451,13 +1465,31 @@ cudaError_t launch_render(const RenderParams& p_in, int mode, int rays_per_lane,
   if (plan.variant == RTW_BVH_WAVEFRONT) {
     // 96 records per warp, 16 traversal steps between exchanges, shading batches of 32 (tuning record in DESIGN.md)
 #define RTW_WF_LAUNCH(SM, NW, MINB)                                                                                          \
-  return stats ? launch_wf_t<SM, true, NW, kWfRecords, 16, 32, MINB>(p, sm_count, plan.smem_bytes, stream)                   \
-               : launch_wf_t<SM, false, NW, kWfRecords, 16, 32, MINB>(p, sm_count, plan.smem_bytes, stream)
+  return stats ? launch_wf_t<SM, true, NW, kWfRecords, 16, 32, MINB>(p, sm_count, smem_bytes, stream)                   \
+               : launch_wf_t<SM, false, NW, kWfRecords, 16, 32, MINB>(p, sm_count, smem_bytes, stream)
+    int warps = plan.warps;
+    size_t smem_bytes = plan.smem_bytes;
     if (!plan.tables_in_smem) {
       p.so.records = 16u;   // no staged tables in front of the records
       RTW_WF_LAUNCH(false, 8, 3);
     }
-    switch (plan.warps) {
+    if (const char* e = std::getenv("RTW_WF_WARPS")) {   // tuning knob: fewer warps per SM than the plan (20 / 24 / 28)
+      const int w = std::atoi(e);
+      if ((w == 20 || w == 24 || w == 28) && w <= plan.warps) { warps = w; smem_bytes = p.so.records + static_cast<size_t>(w) * wf_warp_bytes(kWfRecords); }
+    }
+#ifdef RTW_TUNE_STEPS
+    if (warps == 32 && !stats && std::getenv("RTW_WF_STEPS")) {
+      const int st = std::atoi(std::getenv("RTW_WF_STEPS"));
+      if (st == 8) return launch_wf_t<true, false, 32, kWfRecords32, 8, 32, 1>(p, sm_count, smem_bytes, stream);
+      if (st == 12) return launch_wf_t<true, false, 32, kWfRecords32, 12, 32, 1>(p, sm_count, smem_bytes, stream);
+      if (st == 20) return launch_wf_t<true, false, 32, kWfRecords32, 20, 32, 1>(p, sm_count, smem_bytes, stream);
+      if (st == 24) return launch_wf_t<true, false, 32, kWfRecords32, 24, 32, 1>(p, sm_count, smem_bytes, stream);
+    }
+#endif
+    if (warps == 32)   // the lean tier: 64 registers, 92 records per warp
+      return stats ? launch_wf_t<true, true, 32, kWfRecords32, 16, 32, 1>(p, sm_count, smem_bytes, stream)
+                   : launch_wf_t<true, false, 32, kWfRecords32, 16, 32, 1>(p, sm_count, smem_bytes, stream);
+    switch (warps) {
       case 28: RTW_WF_LAUNCH(true, 28, 1);
       case 24: RTW_WF_LAUNCH(true, 24, 1);
       default: RTW_WF_LAUNCH(true, 20, 1);

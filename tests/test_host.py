@@ -186,18 +186,18 @@ def test_sample_shard(rtw):
 
 def test_bvh_kernel_plan(rtw, monkeypatch):
     """Which BVH kernel a scene gets is host logic (plan_bvh, csrc/rtw_internal.h), reported by rtw_flatten_info: the wavefront
-    kernel with 28 / 24 / 20 warps per SM while tables + path records fit in the 227 KB of shared memory, the same kernel with the
+    kernel with 32 / 28 / 24 / 20 warps per SM while tables + path records fit in the 227 KB of shared memory, the same kernel with the
     tables in L1/L2 for bigger sphere scenes, the per-lane kernel for meshes; with RTW_MESH_BVH=cw8 scenes with triangles get the
     compressed 8-wide BVH walked by the per-lane state machine, its tables in shared memory while they fit in 72 KB."""
     def plan(scene):
         r = rtw.flatten_info(scene)
         return r["bvh_variant"], r["bvh_warps_per_cta"], r["bvh_tables_in_smem"], r["bvh_smem_bytes"]
     monkeypatch.delenv("RTW_MESH_BVH", raising=False)
-    for nsqrt, warps in ((1, 28), (11, 28), (12, 28), (13, 24), (15, 24), (16, 20), (17, 20)):
+    for nsqrt, warps in ((1, 32), (11, 32), (12, 28), (13, 24), (15, 24), (16, 20), (17, 20)):
         v, w, in_smem, smem = plan(rtw.cover_scene(nsqrt))
         assert (v, w, in_smem) == (rtw.BVH_WAVEFRONT, warps, 1), nsqrt
-        assert smem <= 227 * 1024 and smem + 4 * 6048 > 227 * 1024 or warps == 28   # the largest tier that fits
-    assert plan(rtw.cover_scene(11))[3] == 215760   # cover scene: 46 416 bytes of tables + 28 x 6 048 bytes of records
+        assert smem <= 227 * 1024 and smem + 4 * 6048 > 227 * 1024 or warps >= 28   # the largest tier that fits
+    assert plan(rtw.cover_scene(11))[3] == 46416 + 32 * 5808   # cover scene: 46 416 bytes of tables + 32 warps x 92 records (176 bytes below the cap)
     assert plan(rtw.cover_scene(18))[:3] == (rtw.BVH_WAVEFRONT, 8, 0)
     assert plan(rtw.cover_scene(40))[:3] == (rtw.BVH_WAVEFRONT, 8, 0)
     assert plan(rtw.mesh_on_ground_scene(SUZANNE))[:3] == (rtw.BVH_PERLANE, 8, 0)   # 968 triangles: 108 KB of tables, beyond K2's 72 KB
@@ -207,7 +207,7 @@ def test_bvh_kernel_plan(rtw, monkeypatch):
     rng = np.random.default_rng(0)
     prims["a"] = rng.uniform(-1, 1, (200, 3)); prims["b"] = prims["a"] + 0.1; prims["c"] = prims["a"] + [0.1, 0, 0.05]
     small = rtw.custom_scene(prims, np.zeros(1, rtw.MAT_DTYPE), **cam)
-    assert plan(small)[:3] == (rtw.BVH_WAVEFRONT, 28, 1)   # small meshes fit the first tier
+    assert plan(small)[:3] == (rtw.BVH_WAVEFRONT, 32, 1)   # small meshes fit the first tier
     big = np.zeros(4000, rtw.PRIM_DTYPE)
     big["kind"] = rtw.RTW_TRIANGLE
     big["a"] = rng.uniform(-1, 1, (4000, 3)); big["b"] = big["a"] + 0.01; big["c"] = big["a"] + [0.01, 0, 0.005]
@@ -217,7 +217,7 @@ def test_bvh_kernel_plan(rtw, monkeypatch):
     assert (v, w, in_smem) == (rtw.BVH_CWIDE, 8, 1) and 50_000 < smem < 60_000    # 968 triangles: ~130 wide nodes + 968 records = 57 KB
     assert plan(small)[:3] == (rtw.BVH_CWIDE, 8, 1)
     assert plan(big)[:3] == (rtw.BVH_CWIDE, 8, 0)   # 192 KB of records: read through L1/L2
-    assert plan(rtw.cover_scene(11))[:3] == (rtw.BVH_WAVEFRONT, 28, 1)   # sphere-only scenes are not affected
+    assert plan(rtw.cover_scene(11))[:3] == (rtw.BVH_WAVEFRONT, 32, 1)   # sphere-only scenes are not affected
     assert rtw.scene_hash(small) != (monkeypatch.delenv("RTW_MESH_BVH") or rtw.scene_hash(small))   # the cache key knows the tree format
 
 
