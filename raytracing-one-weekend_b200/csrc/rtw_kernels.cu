@@ -1095,6 +1095,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_render_wf(const __grid_consta
     if (idle == 0xffffffffu && n_ready == 0u) break;   // nothing in flight, nothing queued (hit/miss would have run)
 
     // ---- (4) traversal: STEPS node-or-leaf steps for every lane holding a ray --------------------------------------------
+    // (Measured and not kept, profiles/r02_ffma2.txt: a lane parking its leaf and walking on, the warp's parked leaves tested together
+    // every 2 / 4 / 8 / 16 steps -- 39.2 / 39.2 / 41.0 / 44.1 ms against 34.7, node visits per ray 11.45 -> 11.52 .. 12.09.)
 #pragma unroll 1
     for (int step = 0; step < STEPS; ++step) {
       if (state == TRAV && node >= 0) {
@@ -1477,15 +1479,6 @@ cudaError_t launch_render(const RenderParams& p_in, int mode, int rays_per_lane,
       const int w = std::atoi(e);
       if ((w == 20 || w == 24 || w == 28) && w <= plan.warps) { warps = w; smem_bytes = p.so.records + static_cast<size_t>(w) * wf_warp_bytes(kWfRecords); }
     }
-#ifdef RTW_TUNE_STEPS
-    if (warps == 32 && !stats && std::getenv("RTW_WF_STEPS")) {
-      const int st = std::atoi(std::getenv("RTW_WF_STEPS"));
-      if (st == 8) return launch_wf_t<true, false, 32, kWfRecords32, 8, 32, 1>(p, sm_count, smem_bytes, stream);
-      if (st == 12) return launch_wf_t<true, false, 32, kWfRecords32, 12, 32, 1>(p, sm_count, smem_bytes, stream);
-      if (st == 20) return launch_wf_t<true, false, 32, kWfRecords32, 20, 32, 1>(p, sm_count, smem_bytes, stream);
-      if (st == 24) return launch_wf_t<true, false, 32, kWfRecords32, 24, 32, 1>(p, sm_count, smem_bytes, stream);
-    }
-#endif
     if (warps == 32)   // the lean tier: 64 registers, 92 records per warp
       return stats ? launch_wf_t<true, true, 32, kWfRecords32, 16, 32, 1>(p, sm_count, smem_bytes, stream)
                    : launch_wf_t<true, false, 32, kWfRecords32, 16, 32, 1>(p, sm_count, smem_bytes, stream);
