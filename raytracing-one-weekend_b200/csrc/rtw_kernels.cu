@@ -164,6 +164,27 @@ __device__ __forceinline__ void trace_spheres(const DevScene& sc, const float4* 
   };
 
   // one word = up to 32 consecutive table entries; bit 31-j of the word's mask <- sign of the test of entry base+j
+  // R even: the rays of a lane are handled in PAIRS by the packed FP32 FMA of sm_100 (PTX fma.rn.f32x2, SASS FFMA2): the per-ray
+  // constants sit in 64-bit register pairs, the table entry enters as the instruction's broadcast operand, and the 16 (22) FFMA
+  // per static (moving) sphere and ray pair become 8 (11) FFMA2.  Same fma.rn per half: the masks are bit-identical to the scalar
+  // form.  FFMA2 issues every other cycle at the same FP32 peak (scripts/ffma2_probe.cu), so the loop's LDS / SHF / control now
+  // fit into the free issue slots: this kernel is bound by the FMA pipe, not by latency like the tree walks.
+#ifdef RTW_SWEEP_SCALAR   // A/B build
+  constexpr bool PAIRS = false;
+#else
+  constexpr bool PAIRS = (R % 2 == 0);
+#endif
+  constexpr int H = PAIRS ? R / 2 : 1;
+  uint64_t ux2[H], uy2[H], uz2[H], vx2[H], vy2[H], vz2[H], nou2[H], nov2[H], tm2[H];
+  if (PAIRS) {
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      const int a = 2 * h, b = PAIRS ? 2 * h + 1 : 0;
+      ux2[h] = pk2(ux[a], ux[b]); uy2[h] = pk2(uy[a], uy[b]); uz2[h] = pk2(uz[a], uz[b]);
+      vx2[h] = pk2(vx[a], vx[b]); vy2[h] = pk2(vy[a], vy[b]); vz2[h] = pk2(vz[a], vz[b]);
+      nou2[h] = pk2(-ou[a], -ou[b]); nov2[h] = pk2(-ov[a], -ov[b]); tm2[h] = pk2(ray.tm[a], ray.tm[b]);
+    }
+  }
   auto sweep_word = [&](int base, int cnt, bool moving, uint32_t (&m)[R]) {
 #pragma unroll
     for (int r = 0; r < R; ++r) m[r] = 0u;
@@ -174,12 +195,25 @@ __device__ __forceinline__ void trace_spheres(const DevScene& sc, const float4* 
 #pragma unroll kSweepUnroll
       for (int j = 0; j < cnt; ++j) {
         const float4 An = sA[base + j + 1];
+        if (PAIRS) {
+          const uint64_t ax = pk2(A.x, A.x), ay = pk2(A.y, A.y), az = pk2(A.z, A.z), nw = pk2(-A.w, -A.w);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float pu = fmaf(A.x, ux[r], fmaf(A.y, uy[r], fmaf(A.z, uz[r], -ou[r])));
-          const float pv = fmaf(A.x, vx[r], fmaf(A.y, vy[r], fmaf(A.z, vz[r], -ov[r])));
-          const float sgn = fmaf(pu, pu, fmaf(pv, pv, -A.w));
-          m[r] = __funnelshift_l(__float_as_uint(sgn), m[r], 1);
+          for (int h = 0; h < H; ++h) {
+            const uint64_t pu = fma2(ax, ux2[h], fma2(ay, uy2[h], fma2(az, uz2[h], nou2[h])));
+            const uint64_t pv = fma2(ax, vx2[h], fma2(ay, vy2[h], fma2(az, vz2[h], nov2[h])));
+            float s0, s1;
+            up2(fma2(pu, pu, fma2(pv, pv, nw)), s0, s1);
+            m[2 * h] = __funnelshift_l(__float_as_uint(s0), m[2 * h], 1);
+            m[PAIRS ? 2 * h + 1 : 0] = __funnelshift_l(__float_as_uint(s1), m[PAIRS ? 2 * h + 1 : 0], 1);
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float pu = fmaf(A.x, ux[r], fmaf(A.y, uy[r], fmaf(A.z, uz[r], -ou[r])));
+            const float pv = fmaf(A.x, vx[r], fmaf(A.y, vy[r], fmaf(A.z, vz[r], -ov[r])));
+            const float sgn = fmaf(pu, pu, fmaf(pv, pv, -A.w));
+            m[r] = __funnelshift_l(__float_as_uint(sgn), m[r], 1);
+          }
         }
         A = An;
       }
@@ -189,13 +223,28 @@ __device__ __forceinline__ void trace_spheres(const DevScene& sc, const float4* 
       for (int j = 0; j < cnt; ++j) {
         const float4 An = sA[base + j + 1];
         const float4 Bn = sB[base + j + 1];
+        if (PAIRS) {
+          const uint64_t ax = pk2(A.x, A.x), ay = pk2(A.y, A.y), az = pk2(A.z, A.z), nw = pk2(-A.w, -A.w);
+          const uint64_t bx = pk2(B.x, B.x), by = pk2(B.y, B.y), bz = pk2(B.z, B.z);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float cx = fmaf(ray.tm[r], B.x, A.x), cy = fmaf(ray.tm[r], B.y, A.y), cz = fmaf(ray.tm[r], B.z, A.z);
-          const float pu = fmaf(cx, ux[r], fmaf(cy, uy[r], fmaf(cz, uz[r], -ou[r])));
-          const float pv = fmaf(cx, vx[r], fmaf(cy, vy[r], fmaf(cz, vz[r], -ov[r])));
-          const float sgn = fmaf(pu, pu, fmaf(pv, pv, -A.w));
-          m[r] = __funnelshift_l(__float_as_uint(sgn), m[r], 1);
+          for (int h = 0; h < H; ++h) {
+            const uint64_t cx = fma2(tm2[h], bx, ax), cy = fma2(tm2[h], by, ay), cz = fma2(tm2[h], bz, az);
+            const uint64_t pu = fma2(cx, ux2[h], fma2(cy, uy2[h], fma2(cz, uz2[h], nou2[h])));
+            const uint64_t pv = fma2(cx, vx2[h], fma2(cy, vy2[h], fma2(cz, vz2[h], nov2[h])));
+            float s0, s1;
+            up2(fma2(pu, pu, fma2(pv, pv, nw)), s0, s1);
+            m[2 * h] = __funnelshift_l(__float_as_uint(s0), m[2 * h], 1);
+            m[PAIRS ? 2 * h + 1 : 0] = __funnelshift_l(__float_as_uint(s1), m[PAIRS ? 2 * h + 1 : 0], 1);
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float cx = fmaf(ray.tm[r], B.x, A.x), cy = fmaf(ray.tm[r], B.y, A.y), cz = fmaf(ray.tm[r], B.z, A.z);
+            const float pu = fmaf(cx, ux[r], fmaf(cy, uy[r], fmaf(cz, uz[r], -ou[r])));
+            const float pv = fmaf(cx, vx[r], fmaf(cy, vy[r], fmaf(cz, vz[r], -ov[r])));
+            const float sgn = fmaf(pu, pu, fmaf(pv, pv, -A.w));
+            m[r] = __funnelshift_l(__float_as_uint(sgn), m[r], 1);
+          }
         }
         A = An; B = Bn;
       }
