@@ -49,9 +49,9 @@ enum rtw_bvh_variant { RTW_BVH_NONE = 0, RTW_BVH_PERLANE = 1, RTW_BVH_WAVEFRONT 
 /* STATS: count tests / node visits (slower).  SPLIT_ROWS: multi-GPU row-tile split instead of the sample split.
  * NO_SCENE_CACHE: the host-buffer entry points re-flatten, re-build and re-upload the scene even when it is the one the device
  * already holds from the previous call (what the first call of a process pays; bench.py's end-to-end leg uses it).
- * BVH_BUILD_GPU / BVH_BUILD_HOST: where the host-buffer entry points (and rtw_scene_upload_ex) build the BVH: linear BVH on the
- * device (a few ms for a million triangles, ~10-20 % slower to trace) or binned SAH on the host cores.  Neither: the device for
- * scenes of >= 200 000 primitives rendered with < 2e9 paths, the host otherwise. */
+ * BVH_BUILD_GPU / BVH_BUILD_HOST: where the host-buffer entry points (and rtw_scene_upload_ex) build the BVH: on the device (radix
+ * tree, its top and its subtrees rebuilt with SAH: ~15 ms for a million triangles, ~3 % slower to trace) or binned SAH on the host
+ * cores (~80 ms).  Neither: the device for scenes of >= 200 000 primitives rendered with < 6e9 paths, the host otherwise. */
 enum rtw_flags { RTW_FLAG_STATS = 1, RTW_FLAG_SPLIT_ROWS = 2, RTW_FLAG_NO_SCENE_CACHE = 4, RTW_FLAG_BVH_BUILD_GPU = 16, RTW_FLAG_BVH_BUILD_HOST = 32 };
 
 /* One primitive, in scene insertion order (index in the array == primitive id used for parity).

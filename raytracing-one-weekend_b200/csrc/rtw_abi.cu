@@ -370,9 +370,12 @@ int rtw::upload_flat(const HostFlat& hf, const rtw_camera& c, int64_t nprims, in
     int depth = 0;
     const auto* items = static_cast<const std::vector<rtw::BvhBuilder::Item>*>(hf.gpu_items.get());
     const bool sah_top = !(std::getenv("RTW_LBVH_SAH_TOP") && std::atoi(std::getenv("RTW_LBVH_SAH_TOP")) == 0);   // A/B knob
-    int top_nodes = 0;
-    if (int rc = gpu_build_bvh(items->data(), items->size(), sc->arena_ptr + hf.o_nodes, stream, sah_top, &depth, &sc->gpu_build_ms, &top_nodes)) return rc;
-    if (std::getenv("RTW_TRACE")) std::fprintf(stderr, "rtw trace: device BVH build %.2f ms, %d top nodes rebuilt with SAH, depth bound %d\n", sc->gpu_build_ms, top_nodes, depth);
+    const bool sah_clusters = !(std::getenv("RTW_LBVH_SAH_CLUSTERS") && std::atoi(std::getenv("RTW_LBVH_SAH_CLUSTERS")) == 0);   // A/B knob
+    int top_nodes = 0, clusters_rebuilt = 0;
+    if (int rc = gpu_build_bvh(items->data(), items->size(), sc->arena_ptr + hf.o_nodes, stream, sah_top, sah_clusters, &depth, &sc->gpu_build_ms, &top_nodes, &clusters_rebuilt)) return rc;
+    if (std::getenv("RTW_TRACE"))
+      std::fprintf(stderr, "rtw trace: device BVH build %.2f ms, %d top nodes rebuilt with SAH on the host, %d subtrees below them with SAH on the device, depth bound %d\n",
+                   sc->gpu_build_ms, top_nodes, clusters_rebuilt, depth);
     if (depth > rtw::kBvhStack)
       return fail("rtw_scene_upload: the device-built BVH is deeper than the kernels' traversal stack (" + std::to_string(depth) + " > " +
                   std::to_string(rtw::kBvhStack) + " levels): use the host builder (RTW_FLAG_BVH_BUILD_HOST)");
@@ -446,15 +449,16 @@ int rtw::slot_prepare(DeviceSlot* s) {
   return 0;
 }
 
-// Where the BVH of a host-buffer render is built.  Explicit flags win; otherwise the device builds it for big scenes rendered with
-// few paths: the linear BVH takes ~5 ms for a million triangles against ~80 ms for the SAH tree on 16 host cores, and costs ~10-20 %
-// of trace speed, so it pays while the render itself is shorter than about half a second.
+// Where the BVH of a host-buffer render is built.  Explicit flags win; otherwise the device builds it for big scenes unless the render
+// is very long: the device build (radix tree, SAH top on the host, SAH inside the subtrees on the device) takes ~15 ms for a million
+// triangles against ~80 ms for the SAH tree on 16 host cores and traces 3.3 % slower (991k-triangle mesh: 36.8 against 35.6 ms per
+// 133 M paths), so it pays while the render itself is shorter than about two seconds.
 bool rtw::choose_gpu_build(const rtw_scene_desc* desc, const rtw_render_cfg* cfg) {
   if (cfg->flags & RTW_FLAG_BVH_BUILD_HOST) return false;
   if (cfg->flags & RTW_FLAG_BVH_BUILD_GPU) return true;
   if (mesh_bvh_is_cw8()) return false;
   const double paths = static_cast<double>(cfg->width) * cfg->height * (cfg->sample_end - cfg->sample_begin);
-  return desc->nprims >= 200000 && paths < 2.0e9;
+  return desc->nprims >= 200000 && paths < 6.0e9;
 }
 
 int rtw::slot_set_scene(DeviceSlot* s, const rtw_scene_desc* desc, uint64_t key, bool use_cache, HostFlat* flat, std::mutex* flat_mutex, bool* hit) {

@@ -5,7 +5,8 @@
 // in the Construction of BVHs, Octrees, and k-d Trees", HPG 2012) built in one pass, bounds fitted bottom-up with one atomic flag per
 // node, and the result packed straight into the 64-byte two-child nodes the traversal kernels walk (child boxes as centre + half-extent
 // rounded up exactly as the host builder does, rtw_bvh.h).  A million triangles take a few milliseconds instead of the ~80 ms of the
-// binned-SAH build on 16 host cores; the tree is a plain spatial-median tree, so rays visit more nodes (measured in DESIGN.md).
+// binned-SAH build on 16 host cores.  The radix tree is a plain spatial-median tree and traces 14 % slower than the SAH tree, so its top
+// (host SAH over a few thousand subtree boxes) and the subtrees themselves (binned SAH, one warp per subtree) are rebuilt: 3.3 % slower.
 // Any correct BVH returns the same closest hit: parity (primitive ids) does not depend on which builder ran.
 #include <cub/device/device_radix_sort.cuh>
 
@@ -93,7 +94,8 @@ __device__ __forceinline__ int delta(const unsigned long long* __restrict__ keys
 
 // Karras 2012, one thread per internal node: children codes (>= 0: internal index, < 0: ~sorted leaf position) and parent links
 __global__ void __launch_bounds__(256) k_hierarchy(const unsigned long long* __restrict__ keys, int n, int2* __restrict__ children,
-                                                   int* __restrict__ parent_inner, int* __restrict__ parent_leaf, int* __restrict__ prefix) {
+                                                   int* __restrict__ parent_inner, int* __restrict__ parent_leaf, int* __restrict__ prefix,
+                                                   int* __restrict__ range_other) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
   const int d = delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1) >= 0 ? 1 : -1;
@@ -116,6 +118,7 @@ __global__ void __launch_bounds__(256) k_hierarchy(const unsigned long long* __r
   const int right = hi == gamma + 1 ? ~(gamma + 1) : gamma + 1;
   children[i] = make_int2(left, right);
   prefix[i] = dnode;   // leading bits shared by every key below this node
+  range_other[i] = j;  // the node covers the sorted positions [min(i, j), max(i, j)]
   if (left >= 0) parent_inner[left] = i; else parent_leaf[gamma] = i;
   if (right >= 0) parent_inner[right] = i; else parent_leaf[gamma + 1] = i;
   if (i == 0) parent_inner[0] = -1;
@@ -271,25 +274,212 @@ __global__ void __launch_bounds__(256) k_pack(const GpuBuildItem* __restrict__ i
   out[i] = nd;
 }
 
+
+// ---- SAH inside the clusters ---------------------------------------------------------------------------------------------------------
+// What is left of the radix tree after the top has been rebuilt are the clusters: a few thousand subtrees of ~60 primitives each, still
+// split at Morton midpoints.  One WARP per cluster rebuilds its subtree with binned SAH (16 bins on each of the three axes, all in
+// shared memory) and writes it over the cluster's own node slots: in Karras' numbering a node i covering the sorted positions [a, b] is
+// i = a or i = b, and the b - a inner nodes below and including it are exactly the slots [a, b - 1] (i = a) or [a + 1, b] (i = b).  The
+// cluster root keeps its slot, so nothing above it changes.  Clusters beyond kSahMax primitives keep their radix structure.
+constexpr int kSahWarps = 4;     // warps per CTA (42 KB of static shared memory)
+constexpr int kSahMax = 1024;    // largest cluster that is rebuilt
+constexpr int kSahBins = 16;
+struct SahWarp {
+  int idx[kSahMax], tmp[kSahMax];    // item indices of the cluster, permuted in place range by range
+  int bins[3][kSahBins][7];          // per axis and bin: box lo[3], hi[3] (ordered ints), count
+  int4 stack[48];                    // pending ranges: (lo, hi, local node index, depth)
+};
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, off));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+  return v;
+}
+__device__ __forceinline__ float half_area3(const float lo[3], const float hi[3]) {
+  const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+  return dx * dy + dy * dz + dz * dx;
+}
+// median_from: ranges at this depth or deeper are split in the middle of their (Morton-ordered) list, which bounds the depth of a
+// cluster's subtree by median_from + log2(kSahMax) whatever the geometry looks like
+__global__ void __launch_bounds__(kSahWarps * 32) k_sah_clusters(const GpuBuildItem* __restrict__ items, const int* __restrict__ order,
+                                                                const int* __restrict__ range_other, const Cluster* __restrict__ clusters, int n_clusters,
+                                                                int median_from, PackedNode* __restrict__ nodes, int* __restrict__ stats) {
+  __shared__ SahWarp sm[kSahWarps];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int cid = blockIdx.x * kSahWarps + w;
+  if (cid >= n_clusters) return;   // whole warps leave; only __syncwarp below
+  const int c = clusters[cid].code;
+  if (c < 0) return;               // a single primitive
+  const int j = range_other[c];
+  const int a = min(c, j), b = max(c, j), m = b - a + 1;
+  if (m < 3 || m > kSahMax) { if (lane == 0 && m > kSahMax) atomicAdd(stats + 1, 1); return; }
+  SahWarp& S = sm[w];
+  const int s0 = c == a ? a : a + 1;
+  auto slot = [&](int local) { return c == a ? s0 + local : (local == 0 ? c : s0 + local - 1); };
+  for (int i = lane; i < m; i += 32) S.idx[i] = order[a + i];
+  int sp = 0, deepest = 1;
+  if (lane == 0) S.stack[0] = make_int4(0, m, 0, 1);
+  sp = 1;
+  __syncwarp();
+  while (sp > 0) {
+    const int4 top = S.stack[--sp];
+    __syncwarp();
+    const int lo = top.x, hi = top.y, L = top.z, depth = top.w, k = hi - lo;
+    deepest = max(deepest, depth);
+    float llo[3], lhi[3], rlo[3], rhi[3];
+    int nl = 0;
+    bool split_done = false;
+    if (k > 2 && depth < median_from) {
+      // centroid bounds of the range
+      float cl[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, ch[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+      for (int i = lo + lane; i < hi; i += 32) {
+        const Box3 bx = items[S.idx[i]].box;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { const float cc = 0.5f * (bx.lo[q] + bx.hi[q]); cl[q] = fminf(cl[q], cc); ch[q] = fmaxf(ch[q], cc); }
+      }
+      float scale[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        cl[q] = warp_min(cl[q]); ch[q] = warp_max(ch[q]);
+        scale[q] = ch[q] > cl[q] ? static_cast<float>(kSahBins) * 0.999f / (ch[q] - cl[q]) : 0.0f;
+      }
+      for (int i = lane; i < 3 * kSahBins * 7; i += 32) {
+        const int f = i % 7;
+        (&S.bins[0][0][0])[i] = f < 3 ? 0x7f7fffff : (f < 6 ? static_cast<int>(0xff7fffffu ^ 0x7fffffffu) : 0);   // +FLT_MAX, ordered(-FLT_MAX), 0
+      }
+      __syncwarp();
+      for (int i = lo + lane; i < hi; i += 32) {
+        const Box3 bx = items[S.idx[i]].box;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int bn = min(kSahBins - 1, static_cast<int>((0.5f * (bx.lo[q] + bx.hi[q]) - cl[q]) * scale[q]));
+          int* B = S.bins[q][bn];
+#pragma unroll
+          for (int r = 0; r < 3; ++r) { atomicMin(B + r, float_as_ordered(bx.lo[r])); atomicMax(B + 3 + r, float_as_ordered(bx.hi[r])); }
+          atomicAdd(B + 6, 1);
+        }
+      }
+      __syncwarp();
+      // lane = (axis, split position): cost of putting bins [0, s] left and (s, kSahBins) right
+      float cost = FLT_MAX;
+      int my_nl = 0;
+      float xl[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, xh[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}, yl[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, yh[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+      for (int cand = lane; cand < 3 * (kSahBins - 1); cand += 32) {
+        const int ax = cand / (kSahBins - 1), s = cand - ax * (kSahBins - 1);
+        float tl[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, th[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}, ul[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, uh[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        int cntl = 0, cntr = 0;
+        for (int bn = 0; bn < kSahBins; ++bn) {
+          const int* B = S.bins[ax][bn];
+          const int cnt = B[6];
+          if (cnt == 0) continue;
+          if (bn <= s) { cntl += cnt; for (int r = 0; r < 3; ++r) { tl[r] = fminf(tl[r], ordered_as_float(B[r])); th[r] = fmaxf(th[r], ordered_as_float(B[3 + r])); } }
+          else { cntr += cnt; for (int r = 0; r < 3; ++r) { ul[r] = fminf(ul[r], ordered_as_float(B[r])); uh[r] = fmaxf(uh[r], ordered_as_float(B[3 + r])); } }
+        }
+        if (cntl > 0 && cntr > 0) {
+          const float cst = half_area3(tl, th) * cntl + half_area3(ul, uh) * cntr;
+          if (cst < cost) {
+            cost = cst; my_nl = cntl | (cand << 16);
+            for (int r = 0; r < 3; ++r) { xl[r] = tl[r]; xh[r] = th[r]; yl[r] = ul[r]; yh[r] = uh[r]; }
+          }
+        }
+      }
+      const float best = warp_min(cost);
+      if (best < FLT_MAX) {
+        const unsigned who = __ballot_sync(0xffffffffu, cost == best);
+        const int src = __ffs(who) - 1;
+        const int packed = __shfl_sync(0xffffffffu, my_nl, src);
+        nl = packed & 0xffff;
+        const int cand = packed >> 16, ax = cand / (kSahBins - 1), s = cand - ax * (kSahBins - 1);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          llo[r] = __shfl_sync(0xffffffffu, xl[r], src); lhi[r] = __shfl_sync(0xffffffffu, xh[r], src);
+          rlo[r] = __shfl_sync(0xffffffffu, yl[r], src); rhi[r] = __shfl_sync(0xffffffffu, yh[r], src);
+        }
+        // stable partition of idx[lo, hi) by "bin on the chosen axis <= s" through tmp
+        int nleft = 0, nright = 0;
+        for (int base = lo; base < hi; base += 32) {
+          const int i = base + lane;
+          bool valid = i < hi, left = false;
+          int id = 0;
+          if (valid) {
+            id = S.idx[i];
+            const Box3 bx = items[id].box;
+            const float cc = 0.5f * (bx.lo[ax] + bx.hi[ax]);
+            const float lo_ax = ax == 0 ? cl[0] : (ax == 1 ? cl[1] : cl[2]), sc_ax = ax == 0 ? scale[0] : (ax == 1 ? scale[1] : scale[2]);
+            left = min(kSahBins - 1, static_cast<int>((cc - lo_ax) * sc_ax)) <= s;
+          }
+          const unsigned ml = __ballot_sync(0xffffffffu, valid && left), mr = __ballot_sync(0xffffffffu, valid && !left);
+          const unsigned below = (1u << lane) - 1u;
+          if (valid && left) S.tmp[lo + nleft + __popc(ml & below)] = id;
+          if (valid && !left) S.tmp[lo + nl + nright + __popc(mr & below)] = id;
+          nleft += __popc(ml); nright += __popc(mr);
+        }
+        __syncwarp();
+        for (int i = lo + lane; i < hi; i += 32) S.idx[i] = S.tmp[i];
+        __syncwarp();
+        split_done = true;
+      }
+    }
+    if (!split_done) {   // two primitives, coincident centroids, or past the depth guard: split the list in the middle
+      nl = k / 2;
+      float tl[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, th[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}, ul[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, uh[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+      for (int i = lo + lane; i < hi; i += 32) {
+        const Box3 bx = items[S.idx[i]].box;
+        if (i < lo + nl) { for (int r = 0; r < 3; ++r) { tl[r] = fminf(tl[r], bx.lo[r]); th[r] = fmaxf(th[r], bx.hi[r]); } }
+        else { for (int r = 0; r < 3; ++r) { ul[r] = fminf(ul[r], bx.lo[r]); uh[r] = fmaxf(uh[r], bx.hi[r]); } }
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) { llo[r] = warp_min(tl[r]); lhi[r] = warp_max(th[r]); rlo[r] = warp_min(ul[r]); rhi[r] = warp_max(uh[r]); }
+    }
+    const int nr = k - nl;
+    const int lL = L + 1, lR = L + nl;   // local preorder numbering: the left subtree owns nl - 1 nodes
+    if (lane == 0) {
+      PackedNode nd;
+      float cc[3], ee[3];
+      centre_extent_dev(llo, lhi, cc, ee);
+      for (int r = 0; r < 3; ++r) { nd.c[r][0] = cc[r]; nd.e[r][0] = ee[r]; }
+      centre_extent_dev(rlo, rhi, cc, ee);
+      for (int r = 0; r < 3; ++r) { nd.c[r][1] = cc[r]; nd.e[r][1] = ee[r]; }
+      nd.left = nl > 1 ? slot(lL) : static_cast<int>(~(items[S.idx[lo]].ref | BvhBuilder::kDirectMark));
+      nd.right = nr > 1 ? slot(lR) : static_cast<int>(~(items[S.idx[lo + nl]].ref | BvhBuilder::kDirectMark));
+      nd.pad0 = 0; nd.pad1 = 0;
+      nodes[slot(L)] = nd;
+      int q = sp;
+      if (nr > 1) S.stack[q++] = make_int4(lo + nl, hi, lR, depth + 1);
+      if (nl > 1) S.stack[q++] = make_int4(lo, lo + nl, lL, depth + 1);
+    }
+    sp += (nr > 1 ? 1 : 0) + (nl > 1 ? 1 : 0);
+    __syncwarp();
+  }
+  if (lane == 0) { atomicMax(stats, deepest); atomicAdd(stats + 2, 1); }
+}
+
 }  // namespace
 
 // items: n >= 2 build records in host memory; nodes_out: device memory for n - 1 PackedNodes.  Runs on `stream`, returns after the
 // build has finished.  sah_top: rebuild the top of the radix tree with the host's SAH builder (a few thousand clusters).
-// *depth_out <- bound on the deepest root-to-leaf path (inner nodes); *top_nodes_out <- nodes replaced by the SAH top (0: none).
-int gpu_build_bvh(const void* items_host_v, size_t n, void* nodes_out_v, cudaStream_t stream, bool sah_top, int* depth_out, double* build_ms, int* top_nodes_out) {
+// sah_clusters: then rebuild every subtree below that top with binned SAH on the device, one warp each (k_sah_clusters).
+// *depth_out <- bound on the deepest root-to-leaf path (inner nodes); *top_nodes_out <- nodes replaced by the SAH top (0: none);
+// *clusters_rebuilt_out <- subtrees rebuilt on the device.
+int gpu_build_bvh(const void* items_host_v, size_t n, void* nodes_out_v, cudaStream_t stream, bool sah_top, bool sah_clusters, int* depth_out, double* build_ms,
+                  int* top_nodes_out, int* clusters_rebuilt_out) {
   const GpuBuildItem* items_host = static_cast<const GpuBuildItem*>(items_host_v);
   PackedNode* nodes_out = static_cast<PackedNode*>(nodes_out_v);
   if (n < 2 || n >= (size_t(1) << 30)) return fail("gpu_build_bvh: primitive count out of range");
   const int ni = static_cast<int>(n);
   DevBuf<GpuBuildItem> d_items;
   DevBuf<unsigned long long> d_keys, d_keys_sorted;
-  DevBuf<int> d_vals, d_order, d_parent_inner, d_parent_leaf, d_visits, d_misc, d_prefix;
+  DevBuf<int> d_vals, d_order, d_parent_inner, d_parent_leaf, d_visits, d_misc, d_prefix, d_range_other;
   DevBuf<int2> d_children;
   DevBuf<NodeBox> d_boxes;
   DevBuf<unsigned char> d_temp;
   RTW_CUDA(d_items.alloc(n)); RTW_CUDA(d_keys.alloc(n)); RTW_CUDA(d_keys_sorted.alloc(n)); RTW_CUDA(d_vals.alloc(n)); RTW_CUDA(d_order.alloc(n));
   RTW_CUDA(d_parent_inner.alloc(n)); RTW_CUDA(d_parent_leaf.alloc(n)); RTW_CUDA(d_visits.alloc(n)); RTW_CUDA(d_misc.alloc(8));
-  RTW_CUDA(d_children.alloc(n)); RTW_CUDA(d_boxes.alloc(n)); RTW_CUDA(d_prefix.alloc(n));
+  RTW_CUDA(d_children.alloc(n)); RTW_CUDA(d_boxes.alloc(n)); RTW_CUDA(d_prefix.alloc(n)); RTW_CUDA(d_range_other.alloc(n));
   RTW_CUDA(cudaMemcpyAsync(d_items.p, items_host, n * sizeof(GpuBuildItem), cudaMemcpyHostToDevice, stream));
   EventPair ev;
   RTW_CUDA(ev.create());
@@ -307,7 +497,7 @@ int gpu_build_bvh(const void* items_host_v, size_t n, void* nodes_out_v, cudaStr
   RTW_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, d_keys.p, d_keys_sorted.p, d_vals.p, d_order.p, ni, 0, 63, stream));
   RTW_CUDA(d_temp.alloc(temp_bytes));
   RTW_CUDA(cub::DeviceRadixSort::SortPairs(d_temp.p, temp_bytes, d_keys.p, d_keys_sorted.p, d_vals.p, d_order.p, ni, 0, 63, stream));
-  k_hierarchy<<<blocks, 256, 0, stream>>>(d_keys_sorted.p, ni, d_children.p, d_parent_inner.p, d_parent_leaf.p, d_prefix.p);
+  k_hierarchy<<<blocks, 256, 0, stream>>>(d_keys_sorted.p, ni, d_children.p, d_parent_inner.p, d_parent_leaf.p, d_prefix.p, d_range_other.p);
   count_launch();
   k_refit<<<blocks, 256, 0, stream>>>(d_items.p, d_order.p, ni, d_children.p, d_parent_inner.p, d_parent_leaf.p, d_boxes.p, d_visits.p);
   count_launch();
@@ -323,8 +513,8 @@ int gpu_build_bvh(const void* items_host_v, size_t n, void* nodes_out_v, cudaStr
   int top_nodes = 0;
   if (sah_top && n >= 4096) {
     DevBuf<int> d_counts;
-    RTW_CUDA(d_counts.alloc(kTopLevels + 4));
-    RTW_CUDA(cudaMemsetAsync(d_counts.p, 0, (kTopLevels + 4) * sizeof(int), stream));
+    RTW_CUDA(d_counts.alloc(kTopLevels + 8));
+    RTW_CUDA(cudaMemsetAsync(d_counts.p, 0, (kTopLevels + 8) * sizeof(int), stream));
     k_count_top<<<blocks, 256, 0, stream>>>(d_prefix.p, ni, d_counts.p);
     count_launch();
     int counts[kTopLevels];
@@ -380,9 +570,24 @@ int gpu_build_bvh(const void* items_host_v, size_t n, void* nodes_out_v, cudaStr
           k_scatter_nodes<<<static_cast<unsigned>((T + 255) / 256), 256, 0, stream>>>(d_slot_nodes.p, T, nodes_out);
           count_launch();
           RTW_CUDA(cudaGetLastError());
-          RTW_CUDA(cudaStreamSynchronize(stream));
           depth = tb.max_depth() + got[2];
           top_nodes = T;
+          // SAH inside the clusters (k_sah_clusters); the depth guard leaves room for the top above and log2(kSahMax) levels below it
+          const int median_from = std::min(32, kBvhStack - tb.max_depth() - 11);
+          if (sah_clusters && median_from >= 4) {
+            int* st = ctr + 3;   // {deepest rebuilt cluster, clusters too big to rebuild, clusters rebuilt}: zeroed with d_counts... the three ints after ctr[2]
+            k_sah_clusters<<<static_cast<unsigned>((Cn + kSahWarps - 1) / kSahWarps), kSahWarps * 32, 0, stream>>>(d_items.p, d_order.p, d_range_other.p, d_clusters.p, Cn,
+                                                                                                                 median_from, nodes_out, st);
+            count_launch();
+            RTW_CUDA(cudaGetLastError());
+            int cs[3] = {0, 0, 0};
+            RTW_CUDA(cudaMemcpyAsync(cs, st, sizeof cs, cudaMemcpyDeviceToHost, stream));
+            RTW_CUDA(cudaStreamSynchronize(stream));
+            // clusters that kept their radix structure (too big) are bounded by got[2], the rebuilt ones by what the kernel saw
+            depth = tb.max_depth() + (cs[1] > 0 ? std::max(got[2], cs[0]) : cs[0]);
+            if (clusters_rebuilt_out) *clusters_rebuilt_out = cs[2];
+          }
+          RTW_CUDA(cudaStreamSynchronize(stream));
         }
       }
     }
