@@ -225,7 +225,7 @@ RTW_API int rtw_flatten_info(const rtw_scene_desc* desc, rtw_flatten_report* out
  * bvh_max_depth, bvh_errors and bvh_build_ms (time of the device build, 0 for a host-built tree). */
 RTW_API int rtw_scene_check(const rtw_scene* scene, rtw_flatten_report* out);
 
-/* FP32 FFMA micro-benchmark: sustained TFLOP/s (2 flop per FMA) and the SM clock seen, the denominator of the
+/* FP32 FMA micro-benchmark (scalar FFMA and packed FFMA2 chains, the higher rate): sustained TFLOP/s (2 flop per FMA) and the SM clock seen, the denominator of the
  * sphere-scene roofline (MEASURED_PEAKS.json carries only HBM and bf16 figures). */
 RTW_API int rtw_fp32_peak(int32_t device, double seconds, double* tflops, double* sm_mhz);
 

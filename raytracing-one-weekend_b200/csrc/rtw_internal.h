@@ -111,7 +111,7 @@ cudaError_t launch_debug_scatter(long long n, const int* kind, const float* fuzz
                                  const uint8_t* front, const float* ball, const float* coin, float* out_dir, float* out_att,
                                  const float* albedo, uint8_t* scattered, cudaStream_t stream);
 cudaError_t launch_debug_samples(long long n, uint64_t seed, float* ball, float* disk, float* uni, cudaStream_t stream);
-cudaError_t launch_ffma_peak(float* out, int blocks, int iters, cudaStream_t stream);
+cudaError_t launch_ffma_peak(float* out, int blocks, int iters, bool packed, cudaStream_t stream);   // packed: FFMA2, two FMAs per lane and instruction
 void count_launch();                 // other translation units report their own kernels
 unsigned long long launch_count();
 

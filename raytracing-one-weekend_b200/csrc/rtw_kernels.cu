@@ -1399,8 +1399,29 @@ __global__ void k_debug_samples(long long n, uint2 key, float* ball, float* disk
   uni[4 * k] = u01(x.x); uni[4 * k + 1] = u01(x.y); uni[4 * k + 2] = u01(x.z); uni[4 * k + 3] = u01(x.w);
 }
 
-// 8 independent FFMA chains per thread: the sustained FP32 FMA rate that bounds K1.
+// 8 independent FMA chains per thread: the sustained FP32 FMA rate that bounds K1.  PACKED: the chains are FFMA2 (fma.rn.f32x2, two
+// FMAs per lane and instruction, one instruction every other cycle): the same pipe, but the issue slots no longer limit it, and it
+// measures ~4 % above the scalar form (scripts/ffma2_probe.cu: 74.2 against 71.2 TFLOP/s).  rtw_fp32_peak reports the higher one.
+template <bool PACKED>
 __global__ void __launch_bounds__(256) k_ffma_peak(float* out, int iters, float a, float b) {
+  if (PACKED) {
+    uint64_t x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = pk2(static_cast<float>(threadIdx.x + j), static_cast<float>(threadIdx.x + j) + 0.5f);
+    const uint64_t a2 = pk2(a, a), b2 = pk2(b, b);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = fma2(x[j], a2, b2);
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { float lo, hi; up2(x[j], lo, hi); s += lo + hi; }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    return;
+  }
   float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
@@ -1605,8 +1626,9 @@ cudaError_t launch_debug_samples(long long n, uint64_t seed, float* ball, float*
   RTW_COUNT_LAUNCH();
   return cudaGetLastError();
 }
-cudaError_t launch_ffma_peak(float* out, int blocks, int iters, cudaStream_t stream) {
-  k_ffma_peak<<<blocks, 256, 0, stream>>>(out, iters, 0.999999f, 1e-7f);
+cudaError_t launch_ffma_peak(float* out, int blocks, int iters, bool packed, cudaStream_t stream) {
+  if (packed) k_ffma_peak<true><<<blocks, 256, 0, stream>>>(out, iters, 0.999999f, 1e-7f);
+  else k_ffma_peak<false><<<blocks, 256, 0, stream>>>(out, iters, 0.999999f, 1e-7f);
   RTW_COUNT_LAUNCH();
   return cudaGetLastError();
 }

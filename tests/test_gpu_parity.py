@@ -780,7 +780,14 @@ def test_bvh_built_on_the_device(gpu, port, oracle_mod, tmp_path):
     dup = np.zeros(3000, gpu.PRIM_DTYPE); dup["kind"] = gpu.RTW_TRIANGLE; dup["a"] = [-1, -1, 0]; dup["b"] = [1, -1, 0]; dup["c"] = [0, 1, 0]
     two = np.zeros(2, gpu.PRIM_DTYPE); two["radius"] = 0.5; two["a"] = two["b"] = [[-1, 0, 0], [1, 0, 0]]
     mats = np.zeros(1, gpu.MAT_DTYPE); mats["albedo"] = 0.6
-    scenes = {"cover": gpu.cover_scene(), "grid_6k": gpu.cover_scene(40), "suzanne_on_ground": gpu.mesh_on_ground_scene(SUZANNE, 1.5),
+    # device SAH inside the subtrees (k_sah_clusters needs >= 4096 primitives for a SAH top): random small triangles plus stacks of
+    # coincident ones (zero-extent centroid bounds: the median fallback) and one stack too big for a warp's shared memory (radix kept)
+    rng = np.random.default_rng(5)
+    mix = np.zeros(9000, gpu.PRIM_DTYPE); mix["kind"] = gpu.RTW_TRIANGLE
+    mix["a"] = rng.uniform(-1.5, 1.5, (9000, 3)); mix["b"] = mix["a"] + rng.uniform(-0.05, 0.05, (9000, 3)); mix["c"] = mix["a"] + rng.uniform(-0.05, 0.05, (9000, 3))
+    for lo, hi in ((0, 40), (100, 700), (1000, 2500)):
+        mix["a"][lo:hi] = mix["a"][lo]; mix["b"][lo:hi] = mix["b"][lo]; mix["c"][lo:hi] = mix["c"][lo]
+    scenes = {"cover": gpu.cover_scene(), "9000 triangles with coincident stacks": gpu.custom_scene(mix, mats, **cam), "grid_6k": gpu.cover_scene(40), "suzanne_on_ground": gpu.mesh_on_ground_scene(SUZANNE, 1.5),
               "standin_62k": gpu.mesh_on_ground_scene(str(obj), 1.5), "3000 coincident triangles": gpu.custom_scene(dup, mats, **cam),
               "two spheres": gpu.custom_scene(two, mats, **cam)}
     for name, scene in scenes.items():
