@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 #include <vector>
 
 #include "rtw_bvh.h"
@@ -521,8 +522,10 @@ int gpu_build_bvh(const void* items_host_v, size_t n, void* nodes_out_v, cudaStr
     RTW_CUDA(cudaMemcpyAsync(counts, d_counts.p, sizeof counts, cudaMemcpyDeviceToHost, stream));
     RTW_CUDA(cudaStreamSynchronize(stream));
     int level = -1;   // the deepest cut with at most 16 384 clusters (and at least 64, else the radix tree is degenerate up there)
+    int max_clusters = 16384;
+    if (const char* e = std::getenv("RTW_LBVH_MAX_CLUSTERS")) max_clusters = std::max(64, std::atoi(e));   // tuning knob
     for (int l = 0; l < kTopLevels; ++l)
-      if (counts[l] + 1 <= 16384 && counts[l] + 1 >= 64) level = l;
+      if (counts[l] + 1 <= max_clusters && counts[l] + 1 >= 64) level = l;
     if (level >= 0) {
       const int P = 3 * (level + 3) + 1, T = counts[level], Cn = T + 1;
       DevBuf<int> d_top;
