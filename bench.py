@@ -622,7 +622,7 @@ def main() -> int:
     rays_gpu = rays_total / world  # per launch (per GPU)
     paths_gpu = paths_total / world
     peak_tflops, _ = rtw.fp32_peak(local_rank, 1.0)
-    peak_note = "FFMA micro-benchmark (rtw_fp32_peak) measured in this run; MEASURED_PEAKS.json carries no FP32 figure; nominal %.1f" % NOMINAL_FP32_TFLOPS
+    peak_note = "FP32 FMA micro-benchmark (rtw_fp32_peak: scalar FFMA and packed FFMA2 chains, the higher rate) measured in this run; MEASURED_PEAKS.json carries no FP32 figure; nominal %.1f" % NOMINAL_FP32_TFLOPS
     fam = "cover" if args.workload.startswith("cover") else ("dragon" if args.workload.startswith("dragon") else "suzanne")
 
     def ncu(kernel_key, prefer=""):
