@@ -801,28 +801,38 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_bvh(const __gri
         }
       }
     } else {
+    // RTW_K2_V inner-node visits per leaf phase (as in K2w: one convergence point less per extra visit).  Same box, 1080p x 64 spp,
+    // (steps per traversal phase, V) on suzanne / the 991k-triangle mesh, ms per frame (scripts/r2_gpu27.sh): (4, 1) 16.84 / 35.51
+    // (4, 2) 16.13 / 34.28  (4, 4) 16.37 / 35.37  (6, 2) 15.95 / 34.02  (6, 3) 16.15 / 34.16  (8, 2) 15.98 / 34.06  (8, 4) 16.29 / 34.30
+#ifndef RTW_K2_V
+#define RTW_K2_V 2
+#endif
+    static_assert(STEPS % RTW_K2_V == 0, "steps per traversal phase must be a multiple of the visits per leaf phase");
 #pragma unroll 1
-    for (int step = 0; step < STEPS; ++step) {
-      if (state == TRAV && node >= 0) {
-        if (STATS) ++n_nodes;
-        float4 q0, q1, q2, q3;
-        load_node<SMEM>(tb.nodes, node, q0, q1, q2, q3);
-        float ln, lf, rn, rf;
-        node_slabs(q0, q1, q2, idx, idy, idz, odx, ody, odz, best_t, ln, lf, rn, rf);
-        const bool hl = ln <= lf, hr = rn <= rf;
-        const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
-        if (hl && hr) {
-          const bool lfirst = ln <= rn;
-          node = lfirst ? left : right;
-          if (sp < kBvhStack) stack[sp++] = lfirst ? right : left;
-        } else if (hl) {
-          node = left;
-        } else if (hr) {
-          node = right;
-        } else if (sp > 0) {
-          node = stack[--sp];
-        } else {
-          node = kMiss; state = DONE;
+    for (int step = 0; step < STEPS / RTW_K2_V; ++step) {
+#pragma unroll
+      for (int vv = 0; vv < RTW_K2_V; ++vv) {
+        if (state == TRAV && node >= 0) {
+          if (STATS) ++n_nodes;
+          float4 q0, q1, q2, q3;
+          load_node<SMEM>(tb.nodes, node, q0, q1, q2, q3);
+          float ln, lf, rn, rf;
+          node_slabs(q0, q1, q2, idx, idy, idz, odx, ody, odz, best_t, ln, lf, rn, rf);
+          const bool hl = ln <= lf, hr = rn <= rf;
+          const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
+          if (hl && hr) {
+            const bool lfirst = ln <= rn;
+            node = lfirst ? left : right;
+            if (sp < kBvhStack) stack[sp++] = lfirst ? right : left;
+          } else if (hl) {
+            node = left;
+          } else if (hr) {
+            node = right;
+          } else if (sp > 0) {
+            node = stack[--sp];
+          } else {
+            node = kMiss; state = DONE;
+          }
         }
       }
       bool do_leaf = true;
@@ -1146,8 +1156,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_render_wf(const __grid_consta
     // ---- (4) traversal: STEPS node-or-leaf steps for every lane holding a ray --------------------------------------------
     // (Measured and not kept, profiles/r02_ffma2.txt: a lane parking its leaf and walking on, the warp's parked leaves tested together
     // every 2 / 4 / 8 / 16 steps -- 39.2 / 39.2 / 41.0 / 44.1 ms against 34.7, node visits per ray 11.45 -> 11.52 .. 12.09.)
-#pragma unroll 1
-    for (int step = 0; step < STEPS; ++step) {
+    auto visit = [&]() {
       if (state == TRAV && node >= 0) {
         if (STATS) ++n_nodes;
         float4 q0, q1, q2, q3;
@@ -1171,6 +1180,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_render_wf(const __grid_consta
           node = kMiss; state = FIN;
         }
       }
+    };
+    auto leaf = [&]() {
       if (state == TRAV && node < 0) {
         const uint32_t v = static_cast<uint32_t>(~node);
         if (LEAN) {
@@ -1198,6 +1209,22 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_render_wf(const __grid_consta
         if (sp > 0) node = stack[--sp];
         else { node = kMiss; state = FIN; }
       }
+    };
+    // Loop shape: RTW_WF_V inner-node visits, then ONE leaf check, RTW_WF_R times per phase.  Checking for a leaf after every visit
+    // costs a convergence point (BSSY / two ISETP / BRA / BSYNC at 32 lanes) per visit for a test that 1 visit in 12 needs; a lane
+    // that reaches its leaf early idles for at most V - 1 visits.  Cover 1080p x 128 spp, 32 warps (scripts/r2_gpu24.sh, r2_gpu25.sh):
+    // (V, R) = (1, 16) 34.69 ms  (2, 6) 35.00  (2, 8) 33.84  (2, 10) 33.78  (3, 5) 33.67  (3, 6) 33.27  (3, 7) 33.25  (4, 4) 33.52
+    // (4, 5) 33.22  (4, 6) 33.30  (5, 4) 33.17  (6, 3) 34.00; the same step unrolled twice WITH both leaf checks: 36.1 (spills).
+#ifndef RTW_WF_V
+#define RTW_WF_V 4
+#define RTW_WF_R 5
+#endif
+    static_assert(STEPS == 16, "the loop shape below was tuned together with 16-step phases; STEPS only names the tuning generation");
+#pragma unroll 1
+    for (int step = 0; step < RTW_WF_R; ++step) {
+#pragma unroll
+      for (int v = 0; v < RTW_WF_V; ++v) visit();
+      leaf();
     }
   }
 
@@ -1560,10 +1587,13 @@ cudaError_t launch_render(const RenderParams& p_in, int mode, int rays_per_lane,
 #undef RTW_WF_LAUNCH
   }
   // <steps per traversal phase, lanes that must need service before the service phase runs, CTAs per SM>: tables in shared memory
-  // (sphere scenes) 8 / 24; tables in L1/L2 4 / 20 (the whole (steps, threshold) landscape is within +-4 %: DESIGN.md)
+  // (sphere scenes) 8 / 24; tables in L1/L2 6 / 20 with two visits per leaf phase (the (steps, threshold) landscape is within +-4 %: DESIGN.md)
   if (plan.tables_in_smem)
     return stats ? launch_bvh_t<true, true, 8, 24, 4>(p, sm_count, plan.smem_bytes, stream) : launch_bvh_t<true, false, 8, 24, 4>(p, sm_count, plan.smem_bytes, stream);
-  return stats ? launch_bvh_t<false, true, 4, 20, 4>(p, sm_count, 0, stream) : launch_bvh_t<false, false, 4, 20, 4>(p, sm_count, 0, stream);
+#ifndef RTW_K2_STEPS
+#define RTW_K2_STEPS 6
+#endif
+  return stats ? launch_bvh_t<false, true, RTW_K2_STEPS, 20, 4>(p, sm_count, 0, stream) : launch_bvh_t<false, false, RTW_K2_STEPS, 20, 4>(p, sm_count, 0, stream);
 }
 
 cudaError_t launch_primary_f32(const PrimaryParams& p, int mode, cudaStream_t stream) {
