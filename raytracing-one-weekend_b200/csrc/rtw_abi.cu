@@ -872,6 +872,7 @@ int rtw_prewarm(int32_t first_device, int32_t ngpus) {
 }
 
 void rtw_release_cached_buffers(void) {
+  rtw::release_build_scratch();
   std::lock_guard<std::mutex> lock(g_slots_mutex);
   for (int d = 0; d < 64; ++d) {
     rtw::DeviceSlot* s = g_slots[d];

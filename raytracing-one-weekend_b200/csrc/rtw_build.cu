@@ -12,6 +12,8 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <mutex>
+#include <type_traits>
 #include <cstdlib>
 #include <vector>
 
@@ -461,6 +463,21 @@ __global__ void __launch_bounds__(kSahWarps * 32) k_sah_clusters(const GpuBuildI
 
 }  // namespace
 
+namespace {
+template <typename T> struct Carved { T* p = nullptr; };   // a slice of the scratch allocation
+struct BuildScratch { std::mutex m; DevBuf<unsigned char> pool; };
+BuildScratch g_scratch[64];   // per device; builds on one device take turns
+}  // namespace
+void release_build_scratch() {   // rtw_release_cached_buffers
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int d = 0; d < 64; ++d) {
+    std::lock_guard<std::mutex> lock(g_scratch[d].m);
+    if (g_scratch[d].pool.p) { cudaSetDevice(d); g_scratch[d].pool.alloc(0); }
+  }
+  cudaSetDevice(cur);
+}
+
 // items: n >= 2 build records in host memory; nodes_out: device memory for n - 1 PackedNodes.  Runs on `stream`, returns after the
 // build has finished.  sah_top: rebuild the top of the radix tree with the host's SAH builder (a few thousand clusters).
 // sah_clusters: then rebuild every subtree below that top with binned SAH on the device, one warp each (k_sah_clusters).
@@ -472,15 +489,43 @@ int gpu_build_bvh(const void* items_host_v, size_t n, void* nodes_out_v, cudaStr
   PackedNode* nodes_out = static_cast<PackedNode*>(nodes_out_v);
   if (n < 2 || n >= (size_t(1) << 30)) return fail("gpu_build_bvh: primitive count out of range");
   const int ni = static_cast<int>(n);
-  DevBuf<GpuBuildItem> d_items;
-  DevBuf<unsigned long long> d_keys, d_keys_sorted;
-  DevBuf<int> d_vals, d_order, d_parent_inner, d_parent_leaf, d_visits, d_misc, d_prefix, d_range_other;
-  DevBuf<int2> d_children;
-  DevBuf<NodeBox> d_boxes;
-  DevBuf<unsigned char> d_temp;
-  RTW_CUDA(d_items.alloc(n)); RTW_CUDA(d_keys.alloc(n)); RTW_CUDA(d_keys_sorted.alloc(n)); RTW_CUDA(d_vals.alloc(n)); RTW_CUDA(d_order.alloc(n));
-  RTW_CUDA(d_parent_inner.alloc(n)); RTW_CUDA(d_parent_leaf.alloc(n)); RTW_CUDA(d_visits.alloc(n)); RTW_CUDA(d_misc.alloc(8));
-  RTW_CUDA(d_children.alloc(n)); RTW_CUDA(d_boxes.alloc(n)); RTW_CUDA(d_prefix.alloc(n)); RTW_CUDA(d_range_other.alloc(n));
+  // every array of the build comes out of ONE grow-only allocation per device (BuildScratch): a build needs fifteen of them, and
+  // allocating and freeing ~400 MB per call cost several times the build itself (47 against 80-130 ms per cold call of the 991k-triangle
+  // mesh while the allocator was still settling)
+  int dev = 0;
+  RTW_CUDA(cudaGetDevice(&dev));
+  BuildScratch& scratch = g_scratch[dev & 63];
+  std::lock_guard<std::mutex> scratch_lock(scratch.m);
+  size_t temp_bytes = 0;
+  RTW_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, static_cast<const unsigned long long*>(nullptr), static_cast<unsigned long long*>(nullptr),
+                                           static_cast<const int*>(nullptr), static_cast<int*>(nullptr), ni, 0, 63, stream));
+  Carved<GpuBuildItem> d_items;
+  Carved<unsigned long long> d_keys, d_keys_sorted;
+  Carved<int> d_vals, d_order, d_parent_inner, d_parent_leaf, d_visits, d_misc, d_prefix, d_range_other, d_counts, d_top;
+  Carved<int2> d_children;
+  Carved<NodeBox> d_boxes;
+  Carved<unsigned char> d_temp;
+  Carved<Cluster> d_clusters;
+  Carved<uint8_t> d_is_top;
+  Carved<SlotNode> d_slot_nodes;
+  constexpr size_t kMaxTop = 16384;   // the SAH top is cut where at most this many subtrees hang below it
+  auto layout = [&](unsigned char* base) {
+    size_t off = 0;
+    auto take = [&](auto& buf, size_t count) {
+      using T = std::remove_pointer_t<decltype(buf.p)>;
+      off = (off + 255) & ~size_t(255);
+      buf.p = reinterpret_cast<T*>(base + off);
+      off += count * sizeof(T);
+    };
+    take(d_items, n); take(d_keys, n); take(d_keys_sorted, n); take(d_vals, n); take(d_order, n);
+    take(d_parent_inner, n); take(d_parent_leaf, n); take(d_visits, n); take(d_misc, 8);
+    take(d_children, n); take(d_boxes, n); take(d_prefix, n); take(d_range_other, n); take(d_temp, temp_bytes);
+    take(d_counts, kTopLevels + 8); take(d_top, kMaxTop); take(d_clusters, kMaxTop + 1); take(d_is_top, n); take(d_slot_nodes, kMaxTop);
+    return off;
+  };
+  const size_t scratch_bytes = layout(nullptr);
+  RTW_CUDA(scratch.pool.reserve(scratch_bytes));
+  layout(scratch.pool.p);
   RTW_CUDA(cudaMemcpyAsync(d_items.p, items_host, n * sizeof(GpuBuildItem), cudaMemcpyHostToDevice, stream));
   EventPair ev;
   RTW_CUDA(ev.create());
@@ -494,9 +539,6 @@ int gpu_build_bvh(const void* items_host_v, size_t n, void* nodes_out_v, cudaStr
   count_launch();
   k_morton<<<blocks, 256, 0, stream>>>(d_items.p, ni, d_misc.p, d_keys.p, d_vals.p);
   count_launch();
-  size_t temp_bytes = 0;
-  RTW_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, d_keys.p, d_keys_sorted.p, d_vals.p, d_order.p, ni, 0, 63, stream));
-  RTW_CUDA(d_temp.alloc(temp_bytes));
   RTW_CUDA(cub::DeviceRadixSort::SortPairs(d_temp.p, temp_bytes, d_keys.p, d_keys_sorted.p, d_vals.p, d_order.p, ni, 0, 63, stream));
   k_hierarchy<<<blocks, 256, 0, stream>>>(d_keys_sorted.p, ni, d_children.p, d_parent_inner.p, d_parent_leaf.p, d_prefix.p, d_range_other.p);
   count_launch();
@@ -513,8 +555,6 @@ int gpu_build_bvh(const void* items_host_v, size_t n, void* nodes_out_v, cudaStr
   // ---- SAH over the top of the tree (see k_count_top) ------------------------------------------------------------------------------
   int top_nodes = 0;
   if (sah_top && n >= 4096) {
-    DevBuf<int> d_counts;
-    RTW_CUDA(d_counts.alloc(kTopLevels + 8));
     RTW_CUDA(cudaMemsetAsync(d_counts.p, 0, (kTopLevels + 8) * sizeof(int), stream));
     k_count_top<<<blocks, 256, 0, stream>>>(d_prefix.p, ni, d_counts.p);
     count_launch();
@@ -525,14 +565,9 @@ int gpu_build_bvh(const void* items_host_v, size_t n, void* nodes_out_v, cudaStr
     int max_clusters = 16384;
     if (const char* e = std::getenv("RTW_LBVH_MAX_CLUSTERS")) max_clusters = std::max(64, std::atoi(e));   // tuning knob
     for (int l = 0; l < kTopLevels; ++l)
-      if (counts[l] + 1 <= max_clusters && counts[l] + 1 >= 64) level = l;
+      if (counts[l] + 1 <= std::min(max_clusters, static_cast<int>(kMaxTop)) && counts[l] + 1 >= 64) level = l;
     if (level >= 0) {
       const int P = 3 * (level + 3) + 1, T = counts[level], Cn = T + 1;
-      DevBuf<int> d_top;
-      DevBuf<Cluster> d_clusters;
-      DevBuf<uint8_t> d_is_top;
-      DevBuf<SlotNode> d_slot_nodes;
-      RTW_CUDA(d_top.alloc(static_cast<size_t>(T))); RTW_CUDA(d_clusters.alloc(static_cast<size_t>(Cn))); RTW_CUDA(d_is_top.alloc(n)); RTW_CUDA(d_slot_nodes.alloc(static_cast<size_t>(T)));
       int* ctr = d_counts.p + kTopLevels;   // {#top, #clusters, depth below the top}
       k_collect_top<<<blocks, 256, 0, stream>>>(d_items.p, d_order.p, d_prefix.p, ni, P, d_children.p, d_boxes.p, d_top.p, d_clusters.p, ctr, d_is_top.p);
       count_launch();

@@ -92,6 +92,7 @@ namespace rtw {
 
 // rtw_build.cu: linear BVH on the device.  items_host: n >= 2 BvhBuilder::Item records (rtw_bvh.h) in host memory; nodes_out: device
 // memory for n - 1 PackedNodes (root = node 0).  Blocks until the tree is built; *depth_out <- deepest root-to-leaf path.
+void release_build_scratch();   // frees the per-device scratch allocation of gpu_build_bvh
 int gpu_build_bvh(const void* items_host, size_t n, void* nodes_out, cudaStream_t stream, bool sah_top, bool sah_clusters, int* depth_out, double* build_ms,
                   int* top_nodes_out, int* clusters_rebuilt_out);
 

@@ -1156,6 +1156,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_render_wf(const __grid_consta
     // ---- (4) traversal: STEPS node-or-leaf steps for every lane holding a ray --------------------------------------------
     // (Measured and not kept, profiles/r02_ffma2.txt: a lane parking its leaf and walking on, the warp's parked leaves tested together
     // every 2 / 4 / 8 / 16 steps -- 39.2 / 39.2 / 41.0 / 44.1 ms against 34.7, node visits per ray 11.45 -> 11.52 .. 12.09.)
+    // (A lane that is not traversing always holds node == kMiss, and leaf codes are < -1, so `node >= 0` / `node < kMiss` alone would
+    // do as conditions: measured 33.54 against 33.22 ms -- the extra compare buys the compiler a better branch layout.  Not used.)
     auto visit = [&]() {
       if (state == TRAV && node >= 0) {
         if (STATS) ++n_nodes;
