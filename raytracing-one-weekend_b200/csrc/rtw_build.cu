@@ -514,7 +514,7 @@ int gpu_build_bvh(const void* items_host_v, size_t n, void* nodes_out_v, cudaStr
     auto take = [&](auto& buf, size_t count) {
       using T = std::remove_pointer_t<decltype(buf.p)>;
       off = (off + 255) & ~size_t(255);
-      buf.p = reinterpret_cast<T*>(base + off);
+      buf.p = base ? reinterpret_cast<T*>(base + off) : nullptr;   // first pass (base == nullptr) only sizes the allocation
       off += count * sizeof(T);
     };
     take(d_items, n); take(d_keys, n); take(d_keys_sorted, n); take(d_vals, n); take(d_order, n);
